@@ -1,0 +1,501 @@
+// C ABI of libbnf_sm100.so (see include/bnf.h): host bookkeeping (parameter
+// layout in the reference's tree_leaves order), workspace carving and the
+// orchestration of the kernels for forward / loglik+grad / MAP steps / VI step.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bnf_kernels.h"
+#include "bnf_tc.h"
+
+using namespace bnf;
+typedef __nv_bfloat16 bf16;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(x)                                                                            \
+  do {                                                                                   \
+    cudaError_t e_ = (x);                                                                \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(BNF_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CUK() CU(cudaGetLastError())
+
+extern "C" int bnf_abi_version(void) { return BNF_ABI_VERSION; }
+extern "C" const char* bnf_last_error(void) { return g_err; }
+
+// -----------------------------------------------------------------------------
+// plan: models.py:216-252 bookkeeping + Flax/tree_leaves parameter order
+// -----------------------------------------------------------------------------
+extern "C" int bnf_plan_create(const bnf_config_t* c, bnf_plan_t** out) {
+  if (!c || !out) return fail(BNF_ERR_INVALID, "null argument");
+  if (c->abi_version != BNF_ABI_VERSION) return fail(BNF_ERR_INVALID, "ABI version mismatch");
+  const int D = c->input_dim, W = c->width, L = c->depth;
+  if (D < 1 || D > kMaxD) return fail(BNF_ERR_INVALID, "input_dim must be in [1,%d]", kMaxD);
+  if (W < 1) return fail(BNF_ERR_INVALID, "width must be positive");
+  if (L < 1 || L > kMaxLayers) return fail(BNF_ERR_INVALID, "depth must be in [1,%d]", kMaxLayers);
+  if (c->n_seasonal < 0 || c->n_seasonal > kMaxSeasonal)
+    return fail(BNF_ERR_INVALID, "n_seasonal must be in [0,%d]", kMaxSeasonal);
+  if (c->n_interactions < 0 || c->n_interactions > kMaxInter)
+    return fail(BNF_ERR_INVALID, "n_interactions must be in [0,%d]", kMaxInter);
+  if (c->likelihood < BNF_NORMAL || c->likelihood > BNF_ZINB)
+    return fail(BNF_ERR_INVALID, "unknown likelihood %d", c->likelihood);
+  if (!c->fourier_degrees || !c->input_scales) return fail(BNF_ERR_INVALID, "null config array");
+
+  bnf_plan* p = new bnf_plan();
+  DevModel& m = p->m;
+  memset(&m, 0, sizeof(m));
+  m.D = D; m.W = W; m.L = L; m.likelihood = c->likelihood;
+  m.n_seasonal = c->n_seasonal; m.n_inter = c->n_interactions;
+  for (int i = 0; i < D; ++i) {
+    m.input_scales[i] = (float)c->input_scales[i];
+    m.fourier_deg[i] = c->fourier_degrees[i];
+    if (m.fourier_deg[i] > 24) { delete p; return fail(BNF_ERR_INVALID, "fourier degree > 24"); }
+  }
+  const float two_pi = (float)(2.0 * M_PI);  // f32(2*pi): models.py:73 evaluates (2*pi*f) in f32 first
+  for (int k = 0; k < m.n_seasonal; ++k) {
+    m.seasonal_w[k] = two_pi * c->seasonal_freq[k];
+    m.seasonal_h[k] = c->seasonal_harm[k];
+  }
+  for (int j = 0; j < m.n_inter; ++j) {
+    m.inter_a[j] = c->interactions[2 * j];
+    m.inter_b[j] = c->interactions[2 * j + 1];
+    if (m.inter_a[j] < 0 || m.inter_a[j] >= D || m.inter_b[j] < 0 || m.inter_b[j] >= D) {
+      delete p;
+      return fail(BNF_ERR_INVALID, "interaction index out of range");
+    }
+  }
+  // feature groups: [scaled_x, fourier_i (deg>0, filtered BEFORE enumeration), seasonal,
+  // interactions]; the name index counts empty groups too (models.py:242-251).
+  std::map<std::string, std::pair<int, int>> shapes;  // name -> (rows, cols)
+  int col = 0, gidx = 0, ngroups = 0;
+  std::vector<std::pair<int*, std::string>> scale_refs;
+  auto add_group = [&](int size, int* col_out, int* off_out) {
+    if (size > 0) {
+      *col_out = col;
+      col += size;
+      std::string nm = "feature_inv_sp_scale" + std::to_string(gidx);
+      shapes[nm] = {0, 0};
+      scale_refs.push_back({off_out, nm});
+      ++ngroups;
+    } else {
+      *col_out = -1;
+      *off_out = -1;
+    }
+    ++gidx;
+  };
+  add_group(D, &m.col_x, &m.off_scale_x);
+  for (int i = 0; i < D; ++i) {
+    if (m.fourier_deg[i] > 0) add_group(2 * m.fourier_deg[i], &m.fourier_col[i], &m.fourier_scale_off[i]);
+    else { m.fourier_col[i] = -1; m.fourier_scale_off[i] = -1; }
+  }
+  add_group(2 * m.n_seasonal, &m.col_seasonal, &m.off_scale_seasonal);
+  add_group(m.n_inter, &m.col_inter, &m.off_scale_inter);
+  m.F = col;
+  m.Fp = (m.F + kFeatPad - 1) / kFeatPad * kFeatPad;
+  m.inv_sqrt_F = 1.0f / sqrtf((float)m.F);
+  m.inv_sqrt_W = 1.0f / sqrtf((float)W);
+  p->n_groups = ngroups;
+
+  for (int l = 0; l <= L; ++l) {
+    int fan = l == 0 ? m.F : W, outw = l == L ? 1 : W;
+    shapes["Dense_" + std::to_string(l) + "/bias"] = {outw, 0};
+    shapes["Dense_" + std::to_string(l) + "/kernel"] = {fan, outw};
+    if (l < L) shapes["inv_sp_layer_scale" + std::to_string(l)] = {0, 0};
+  }
+  shapes["inv_sp_output_scale"] = {0, 0};
+  shapes["log_scale_adjustment"] = {D, 0};
+  shapes["logit_activation_weight"] = {0, 0};
+  // jax.tree_util.tree_leaves on nested dicts: keys sorted at every level.
+  std::vector<std::string> names;
+  for (auto& kv : shapes) names.push_back(kv.first);
+  auto key = [](const std::string& s) {
+    size_t slash = s.find('/');
+    return slash == std::string::npos ? std::make_pair(s, std::string())
+                                      : std::make_pair(s.substr(0, slash), s.substr(slash + 1));
+  };
+  std::sort(names.begin(), names.end(),
+            [&](const std::string& a, const std::string& b) { return key(a) < key(b); });
+  int64_t off = 3;
+  std::map<std::string, int64_t> offs;
+  for (auto& nm : names) {
+    auto sh = shapes[nm];
+    int64_t n = sh.first == 0 ? 1 : (sh.second == 0 ? sh.first : (int64_t)sh.first * sh.second);
+    p->leaves.push_back({nm, off, sh.first, sh.second});
+    offs[nm] = off;
+    off += n;
+  }
+  if (off > 0x7fffffffLL) { delete p; return fail(BNF_ERR_INVALID, "too many parameters"); }
+  m.P = (int)off;
+  for (auto& r : scale_refs) *r.first = (int)offs[r.second];
+  for (int l = 0; l <= L; ++l) {
+    m.off_bias[l] = (int)offs["Dense_" + std::to_string(l) + "/bias"];
+    m.off_kernel[l] = (int)offs["Dense_" + std::to_string(l) + "/kernel"];
+    if (l < L) m.off_layer_scale[l] = (int)offs["inv_sp_layer_scale" + std::to_string(l)];
+  }
+  m.off_out_scale = (int)offs["inv_sp_output_scale"];
+  m.off_lsa = (int)offs["log_scale_adjustment"];
+  m.off_actw = (int)offs["logit_activation_weight"];
+
+  p->sm_count = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+  }
+  cudaGetLastError();  // no GPU is fine for bookkeeping
+  *out = p;
+  return BNF_OK;
+}
+
+extern "C" void bnf_plan_destroy(bnf_plan_t* p) { delete p; }
+
+extern "C" int bnf_plan_info(const bnf_plan_t* p, bnf_plan_info_t* o) {
+  if (!p || !o) return fail(BNF_ERR_INVALID, "null argument");
+  o->num_params = p->m.P;
+  o->num_features = p->m.F;
+  o->padded_features = p->m.Fp;
+  o->num_leaves = (int)p->leaves.size();
+  o->num_feature_groups = p->n_groups;
+  o->sm_count = p->sm_count;
+  return BNF_OK;
+}
+
+extern "C" int bnf_plan_leaf(const bnf_plan_t* p, int32_t leaf, char* name, int32_t name_len,
+                             int64_t* offset, int32_t* rows, int32_t* cols) {
+  if (!p || leaf < 0 || leaf >= (int)p->leaves.size()) return fail(BNF_ERR_INVALID, "bad leaf index");
+  const Leaf& l = p->leaves[leaf];
+  if (name && name_len > 0) snprintf(name, name_len, "%s", l.name.c_str());
+  if (offset) *offset = l.offset;
+  if (rows) *rows = l.rows;
+  if (cols) *cols = l.cols;
+  return BNF_OK;
+}
+
+// -----------------------------------------------------------------------------
+// workspace
+// -----------------------------------------------------------------------------
+namespace {
+struct Carver {
+  char* base; size_t off;
+  explicit Carver(void* b) : base((char*)b), off(0) {}
+  void* take(size_t bytes) {
+    void* r = base ? base + off : nullptr;
+    off += (bytes + 255) / 256 * 256;
+    return r;
+  }
+};
+
+struct Ws {
+  float* derived;
+  void* feat;
+  void* z[kMaxLayers];
+  void* h[kMaxLayers];
+  float* opre; float* r;
+  void* dU[2];
+  float* dfeat;
+  float* ll; float* prior;
+  float* grad;             // MAP / VI internal gradient [n_net, P]
+  float* vz; float* veps; float* vloss;  // VI
+  bf16* wt; bf16* wn;      // bf16 weight staging for the tcgen05 path
+  float* mm;               // small scratch
+  size_t bytes;
+};
+
+Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
+  const DevModel& m = p->m;
+  const size_t ts = prec == BNF_PREC_FP32 ? 4 : 2;
+  Carver c(base);
+  Ws w;
+  memset(&w, 0, sizeof(w));
+  const size_t rows = (size_t)n_net * B;
+  w.derived = (float*)c.take((size_t)n_net * kDerivedStride * 4);
+  w.feat = c.take(rows * m.Fp * ts);
+  const bool g = mode != BNF_WS_FORWARD;
+  for (int l = 0; l < m.L; ++l) {
+    if (g) {
+      w.z[l] = c.take(rows * m.W * ts);
+      w.h[l] = c.take(rows * m.W * ts);
+    } else {
+      w.z[l] = nullptr;
+      w.h[l] = l < 2 ? c.take(rows * m.W * ts) : w.h[l - 2];  // ping-pong
+    }
+  }
+  w.ll = (float*)c.take((size_t)n_net * 4);
+  w.prior = (float*)c.take((size_t)n_net * 4);
+  w.mm = (float*)c.take(64);
+  if (g) {
+    w.opre = (float*)c.take(rows * 4);
+    w.r = (float*)c.take(rows * 4);
+    w.dU[0] = c.take(rows * m.W * ts);
+    w.dU[1] = m.L > 1 ? c.take(rows * m.W * ts) : w.dU[0];
+    w.dfeat = (float*)c.take(rows * m.Fp * 4);
+  }
+  if (mode == BNF_WS_MAP || mode == BNF_WS_VI) w.grad = (float*)c.take((size_t)n_net * m.P * 4);
+  if (mode == BNF_WS_VI) {
+    w.vz = (float*)c.take((size_t)n_net * m.P * 4);
+    w.veps = (float*)c.take((size_t)n_net * m.P * 4);
+    w.vloss = (float*)c.take((size_t)n_net * 4);
+  }
+  if (prec == BNF_PREC_BF16) {
+    size_t per = tc_weight_elems(m);
+    w.wt = (bf16*)c.take((size_t)n_net * per * 2);
+    w.wn = (bf16*)c.take((size_t)n_net * per * 2);
+  }
+  w.bytes = c.off;
+  return w;
+}
+
+int check_common(const bnf_plan* p, int prec, int n_net, int B) {
+  if (!p) return fail(BNF_ERR_INVALID, "null plan");
+  if (prec < 0 || prec > 2) return fail(BNF_ERR_INVALID, "unknown precision %d", prec);
+  if (n_net < 1 || B < 1) return fail(BNF_ERR_INVALID, "n_networks and batch_rows must be positive");
+  if (n_net > 65535) return fail(BNF_ERR_INVALID, "n_networks must be <= 65535");
+  if ((double)n_net * B * std::max(p->m.W, p->m.Fp) > 9.0e18) return fail(BNF_ERR_INVALID, "problem too large");
+  if (prec == BNF_PREC_BF16) {
+    const char* why = tc_unsupported_reason(p->m);
+    if (why) return fail(BNF_ERR_UNSUPPORTED, "bf16 tcgen05 path: %s", why);
+  }
+  return BNF_OK;
+}
+
+// forward (+ optional backward) for n_net networks on B rows.
+template <typename T>
+int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
+            const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
+            float* out_loc, float* ll, float* grad, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const bool tc = prec == BNF_PREC_BF16;
+  launch_prep(m, params, w.derived, n_net, st);
+  launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
+  if (tc) tc_cast_weights(m, params, w.wt, w.wn, n_net, st);
+  for (int l = 0; l < m.L; ++l) {
+    const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
+    if (tc) {
+      int rc = tc_fwd_layer(p, l, params, w.derived, (const bf16*)a_in, w.wt, (bf16*)w.z[l], (bf16*)w.h[l], n_net, B, st);
+      if (rc) return fail(rc, "tc_fwd_layer failed: %s", tc_last_error());
+    } else {
+      launch_fwd_layer_simt_t<T>(m, l, params, w.derived, a_in, l == 0 ? m.F : m.W, l == 0 ? m.Fp : m.W,
+                                 (T*)w.z[l], (T*)w.h[l], n_net, B, st);
+    }
+  }
+  const bool g = grad != nullptr;
+  launch_head<T>(m, params, w.derived, (const T*)w.h[m.L - 1], y, idx, idx_stride, B, out_loc,
+                 ll ? w.opre : nullptr, ll ? w.r : nullptr, ll, g ? grad : nullptr, n_net, st);
+  CUK();
+  if (!g) return BNF_OK;
+  int cur = 0;
+  launch_act_bwd<T>(m, m.L - 1, true, params, w.derived, (const T*)w.z[m.L - 1], (const T*)w.h[m.L - 1],
+                    w.r, (T*)w.dU[cur], B, grad, n_net, st);
+  for (int l = m.L - 1; l >= 0; --l) {
+    const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
+    const int Kin = l == 0 ? m.F : m.W, lda = l == 0 ? m.Fp : m.W;
+    if (tc) {
+      int rc = tc_wgrad(p, l, (const bf16*)a_in, (const bf16*)w.dU[cur], grad, n_net, B, st);
+      if (rc) return fail(rc, "tc_wgrad failed: %s", tc_last_error());
+    } else {
+      launch_wgrad_simt_t<T>(m, l, a_in, Kin, lda, (const T*)w.dU[cur], grad, n_net, B, st);
+    }
+    if (l > 0) {
+      if (tc) {
+        int rc = tc_dgrad(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], nullptr, n_net, B, st);
+        if (rc) return fail(rc, "tc_dgrad failed: %s", tc_last_error());
+      } else {
+        launch_dgrad_simt_t<T, T>(m, l, params, (const T*)w.dU[cur], (T*)w.dU[cur ^ 1], m.W, m.W, n_net, B, st);
+      }
+      launch_act_bwd<T>(m, l - 1, false, params, w.derived, (const T*)w.z[l - 1], (const T*)nullptr,
+                        nullptr, (T*)w.dU[cur ^ 1], B, grad, n_net, st);
+      cur ^= 1;
+    } else {
+      if (tc) {
+        int rc = tc_dgrad(p, 0, w.wn, (const bf16*)w.dU[cur], nullptr, w.dfeat, n_net, B, st);
+        if (rc) return fail(rc, "tc_dgrad failed: %s", tc_last_error());
+      } else {
+        launch_dgrad_simt_t<T, float>(m, 0, params, (const T*)w.dU[cur], w.dfeat, m.F, m.Fp, n_net, B, st);
+      }
+      launch_encode_bwd(m, params, w.derived, x, idx, idx_stride, B, w.dfeat, grad, n_net, st);
+    }
+  }
+  CUK();
+  return BNF_OK;
+}
+
+int run_net_any(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
+                const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
+                float* out_loc, float* ll, float* grad, cudaStream_t st) {
+  if (prec == BNF_PREC_FP32)
+    return run_net<float>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st);
+  return run_net<bf16>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st);
+}
+}  // namespace
+
+extern "C" size_t bnf_workspace_bytes(const bnf_plan_t* p, int32_t prec, int32_t n_net, int32_t B,
+                                      int32_t mode) {
+  if (!p || n_net < 1 || B < 1) return 0;
+  return carve(p, prec, n_net, B, mode, nullptr).bytes;
+}
+
+extern "C" int bnf_forward(const bnf_plan_t* p, int32_t prec, const float* params, int32_t n_net,
+                           const float* x, const int32_t* idx, int64_t idx_stride, int32_t B,
+                           float* out_loc, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_common(p, prec, n_net, B);
+  if (rc) return rc;
+  if (!params || !x || !out_loc || !ws) return fail(BNF_ERR_INVALID, "null pointer");
+  Ws w = carve(p, prec, n_net, B, BNF_WS_FORWARD, ws);
+  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  return run_net_any(p, prec, params, n_net, x, nullptr, idx, idx_stride, B, w, out_loc, nullptr,
+                     nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int bnf_loglik_grad(const bnf_plan_t* p, int32_t prec, const float* params, int32_t n_net,
+                               const float* x, const float* y, const int32_t* idx, int64_t idx_stride,
+                               int32_t B, float* out_ll, float* out_grad, void* ws, size_t ws_bytes,
+                               void* stream) {
+  int rc = check_common(p, prec, n_net, B);
+  if (rc) return rc;
+  if (!params || !x || !y || !out_ll || !ws) return fail(BNF_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(p, prec, n_net, B, BNF_WS_GRAD, ws);
+  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  CU(cudaMemsetAsync(out_ll, 0, (size_t)n_net * 4, st));
+  float* grad = out_grad;
+  if (grad) CU(cudaMemsetAsync(grad, 0, (size_t)n_net * p->m.P * 4, st));
+  // value-only still needs r/opre scratch for the head kernel
+  return run_net_any(p, prec, params, n_net, x, y, idx, idx_stride, B, w, nullptr, out_ll, grad, st);
+}
+
+extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
+                             int32_t* step_count, int32_t n_net, const float* x, const float* y,
+                             const int32_t* idx, int64_t idx_stride, int32_t B, int32_t n_total,
+                             int32_t n_steps, float lr, float prior_weight, float* out_loss, void* ws,
+                             size_t ws_bytes, void* stream) {
+  int rc = check_common(p, prec, n_net, B);
+  if (rc) return rc;
+  if (!params || !am || !av || !step_count || !x || !y || !out_loss || !ws)
+    return fail(BNF_ERR_INVALID, "null pointer");
+  if (n_steps < 1 || n_total < B) return fail(BNF_ERR_INVALID, "bad n_steps / n_rows_total");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(p, prec, n_net, B, BNF_WS_MAP, ws);
+  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  const DevModel& m = p->m;
+  const float c_ll = (float)((double)n_total / (double)B);  // target.shape[0] / batch_size
+  for (int s = 0; s < n_steps; ++s) {
+    launch_tick(step_count, st);
+    CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
+    CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
+    CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, st));
+    // idx == NULL: every step is a full pass over rows [0, B) (full-batch epochs)
+    const int32_t* idx_s = idx ? idx + (size_t)s * B : nullptr;
+    rc = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, st);
+    if (rc) return rc;
+    launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, st);
+    launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss + (size_t)s * n_net, st);
+  }
+  CUK();
+  return BNF_OK;
+}
+
+extern "C" int bnf_vi_step(const bnf_plan_t* p, int32_t prec, float* mu, float* rho, float* am,
+                           float* av, int32_t* step_count, int32_t E, int32_t S, const float* eps,
+                           uint64_t seed, const float* x, const float* y, const int32_t* idx, int32_t B,
+                           int32_t n_total, float lr, float kl_weight, float* out_loss, void* ws,
+                           size_t ws_bytes, void* stream) {
+  if (E < 1 || S < 1) return fail(BNF_ERR_INVALID, "members and samples must be positive");
+  const int n_net = E * S;
+  int rc = check_common(p, prec, n_net, B);
+  if (rc) return rc;
+  if (!mu || !rho || !am || !av || !step_count || !x || !y || !out_loss || !ws)
+    return fail(BNF_ERR_INVALID, "null pointer");
+  if (!(kl_weight > 0.f)) return fail(BNF_ERR_INVALID, "kl_weight must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(p, prec, n_net, B, BNF_WS_VI, ws);
+  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  const DevModel& m = p->m;
+  const float c = (float)((double)n_total / (double)B) / kl_weight;
+  launch_tick(step_count, st);
+  // device draws are keyed by `seed`; the caller passes a fresh seed every step
+  launch_vi_sample(m.P, E, S, mu, rho, eps, w.veps, seed, 0x5649ULL, w.vz, st);
+  CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
+  CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
+  CU(cudaMemsetAsync(w.vloss, 0, (size_t)n_net * 4, st));
+  rc = run_net_any(p, prec, w.vz, n_net, x, y, idx, 0, B, w, nullptr, w.ll, w.grad, st);
+  if (rc) return rc;
+  launch_vi_adam(m.P, E, S, mu, rho, am, av, w.vz, w.veps, w.grad, step_count, c, lr, w.vloss, st);
+  launch_vi_loss(E, S, w.vloss, w.ll, c, out_loss, st);
+  CUK();
+  return BNF_OK;
+}
+
+extern "C" int bnf_vi_sample(const bnf_plan_t* p, const float* mu, const float* rho, int32_t E,
+                             int32_t n_samples, const float* eps, uint64_t seed, float* out,
+                             void* stream) {
+  if (!p || !mu || !rho || !out || E < 1 || n_samples < 1) return fail(BNF_ERR_INVALID, "bad argument");
+  launch_vi_sample(p->m.P, E, n_samples, mu, rho, eps, nullptr, seed, 0x504fULL, out, (cudaStream_t)stream);
+  CUK();
+  return BNF_OK;
+}
+
+extern "C" int bnf_init_params(const bnf_plan_t* p, float lns_init, uint64_t seed, int64_t first_member,
+                               int32_t n_net, float* out, void* stream) {
+  if (!p || !out || n_net < 1) return fail(BNF_ERR_INVALID, "bad argument");
+  launch_init_params(p->m, lns_init, seed, first_member, n_net, out, (cudaStream_t)stream);
+  CUK();
+  return BNF_OK;
+}
+
+extern "C" size_t bnf_quantile_workspace_bytes(int32_t, int32_t) { return 256; }
+
+// inverse normal CDF (host, double): Acklam's rational approximation + one Halley step
+static double ndtri(double pq) {
+  static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                             1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                             6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                             -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                             3.754408661907416e+00};
+  double x;
+  if (pq < 0.02425) {
+    double q = sqrt(-2 * log(pq));
+    x = (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+        ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  } else if (pq <= 1 - 0.02425) {
+    double q = pq - 0.5, r = q * q;
+    x = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+        (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1);
+  } else {
+    double q = sqrt(-2 * log(1 - pq));
+    x = -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) /
+        ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1);
+  }
+  double e = 0.5 * erfc(-x / sqrt(2.0)) - pq;
+  double u = e * sqrt(2 * M_PI) * exp(x * x / 2);
+  return x - u / (1 + x * u / 2);
+}
+
+extern "C" int bnf_mixture_quantiles(const float* means, const float* scales, int32_t M, int32_t N,
+                                     const double* q, int32_t nq, int32_t approximate, float* out,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  if (!means || !scales || !q || !out || M < 1 || N < 1 || nq < 1) return fail(BNF_ERR_INVALID, "bad argument");
+  if (!ws || ws_bytes < 64) return fail(BNF_ERR_WORKSPACE, "workspace too small");
+  std::vector<float> nd(nq);
+  for (int i = 0; i < nq; ++i) {
+    if (!(q[i] > 0.0 && q[i] < 1.0)) return fail(BNF_ERR_INVALID, "quantile must be in (0,1)");
+    nd[i] = (float)ndtri(q[i]);
+  }
+  launch_quantiles(means, scales, M, N, q, nq, approximate != 0, nd.data(), out, (float*)ws, (cudaStream_t)stream);
+  CUK();
+  return BNF_OK;
+}

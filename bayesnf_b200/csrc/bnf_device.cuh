@@ -1,0 +1,122 @@
+// Device math shared by the SIMT (fp32) and tcgen05 (bf16) paths.
+// No -use_fast_math anywhere: the f32 trig arguments reach 1e3..1e5 rad
+// (models.py:73) and need the accurate sinf/cosf slow path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "bnf_model.h"
+
+namespace bnf {
+
+// ---- per-network derived scalars (written by prep_kernel) -------------------
+constexpr int kDvActW = 0;      // sigmoid(logit_activation_weight)   models.py:253
+constexpr int kDvSOut = 1;      // softplus(inv_sp_output_scale)      models.py:270
+constexpr int kDvSigma = 2;     // 0.01 + exp(log_noise_scale)        models.py:163
+constexpr int kDvShape = 3;     // softplus(params[1])                models.py:171
+constexpr int kDvPi = 4;        // sigmoid(params[2])                 models.py:184
+constexpr int kDvSLayer = 8;    // softplus(inv_sp_layer_scale{l})    models.py:265
+constexpr int kDvDenom = 24;    // input_scales[i]*exp(lsa[i])        models.py:221
+constexpr int kDvSX = 40;       // softplus(feature_inv_sp_scale) of scaled_x
+constexpr int kDvSSeas = 41;
+constexpr int kDvSInter = 42;
+constexpr int kDvSFourier = 43; // + input dim i
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // jax.nn.softplus == logaddexp(x, 0)
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+  // numerically safe on both tails
+  if (x >= 0.f) return 1.f / (1.f + expf(-x));
+  float e = expf(x);
+  return e / (1.f + e);
+}
+__device__ __forceinline__ float log_sigmoid_f(float x) { return -softplus_f(-x); }
+
+// activation models.py:255-258 : w*elu(z) + (1-w)*tanh(z)
+__device__ __forceinline__ float act_f(float z, float w) {
+  float elu = z > 0.f ? z : expm1f(z);
+  return w * elu + (1.f - w) * tanhf(z);
+}
+// returns act'(z); *diff = elu(z) - tanh(z)  (d act / d w)
+__device__ __forceinline__ float act_grad_f(float z, float w, float* diff) {
+  float t = tanhf(z);
+  float elu, delu;
+  if (z > 0.f) { elu = z; delu = 1.f; } else { delu = expf(z); elu = expm1f(z); }
+  *diff = elu - t;
+  return w * delu + (1.f - w) * (1.f - t * t);
+}
+
+__device__ __forceinline__ float digamma_f(float x) {
+  // psi(x) for x > 0: upward recurrence to x >= 6 then the asymptotic series.
+  float acc = 0.f;
+  while (x < 6.f) { acc -= 1.f / x; x += 1.f; }
+  float inv = 1.f / x, inv2 = inv * inv;
+  return acc + logf(x) - 0.5f * inv
+         - inv2 * (1.f / 12.f - inv2 * (1.f / 120.f - inv2 * (1.f / 252.f)));
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- feature encode for one row (models.py:216-252) -------------------------
+// xr: the raw input row (D floats); dv: this network's derived scalars.
+// emit(col, value) is called once per feature column in [0, F).
+template <typename Emit>
+__device__ __forceinline__ void encode_row(const DevModel& m, const float* __restrict__ dv,
+                                           const float* xr, Emit emit) {
+  float sx[kMaxD];
+#pragma unroll 4
+  for (int i = 0; i < m.D; ++i) sx[i] = xr[i] / dv[kDvDenom + i];
+  {
+    const float s = dv[kDvSX];
+    for (int i = 0; i < m.D; ++i) emit(m.col_x + i, sx[i] * s);
+  }
+  const float two_pi = 6.283185307179586f;  // f32(2*pi), models.py:85
+  for (int i = 0; i < m.D; ++i) {
+    const int deg = m.fourier_deg[i];
+    if (deg <= 0) continue;
+    const float s = dv[kDvSFourier + i];
+    const int c0 = m.fourier_col[i];
+    float c = two_pi;                        // 2*pi*2^d is exact scaling in f32
+    for (int d = 0; d < deg; ++d, c *= 2.f) {
+      float sn, cs;
+      sincosf(c * sx[i], &sn, &cs);
+      const float den = (float)(d + 1);
+      emit(c0 + d, (cs / den) * s);
+      emit(c0 + deg + d, (sn / den) * s);
+    }
+  }
+  if (m.n_seasonal > 0) {
+    const float s = dv[kDvSSeas];
+    const float t = xr[0];                   // RAW time, models.py:223
+    for (int k = 0; k < m.n_seasonal; ++k) {
+      float sn, cs;
+      sincosf(m.seasonal_w[k] * t, &sn, &cs);
+      emit(m.col_seasonal + k, (cs / m.seasonal_h[k]) * s);
+      emit(m.col_seasonal + m.n_seasonal + k, (sn / m.seasonal_h[k]) * s);
+    }
+  }
+  if (m.n_inter > 0) {
+    const float s = dv[kDvSInter];
+    for (int j = 0; j < m.n_inter; ++j)
+      emit(m.col_inter + j, (sx[m.inter_a[j]] * sx[m.inter_b[j]]) * s);
+  }
+}
+
+}  // namespace bnf

@@ -1,0 +1,863 @@
+// SIMT kernels of the BayesNF hot path: feature encode, fp32 GEMMs (parity
+// mode), head / likelihood, activation backward, encode backward, prior + Adam,
+// VI sampling / gradient assembly, mixture quantiles.  The bf16 tcgen05 GEMMs
+// live in bnf_tc.cu and share every non-GEMM kernel in this file.
+#include <curand_kernel.h>
+
+#include <cfloat>
+#include <cstdio>
+
+#include "bnf_device.cuh"
+#include "bnf_kernels.h"
+
+namespace bnf {
+
+// =============================================================================
+// prep: per-network derived scalars
+// =============================================================================
+__global__ void prep_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                            float* __restrict__ derived, int n_net) {
+  int net = blockIdx.x;
+  if (net >= n_net) return;
+  const float* p = params + (size_t)net * m.P;
+  float* dv = derived + (size_t)net * kDerivedStride;
+  int t = threadIdx.x;
+  if (t == 0) {
+    dv[kDvActW] = sigmoid_f(p[m.off_actw]);
+    dv[kDvSOut] = softplus_f(p[m.off_out_scale]);
+    dv[kDvSigma] = 0.01f + expf(p[0]);
+    dv[kDvShape] = softplus_f(p[1]);
+    dv[kDvPi] = 1.f / (1.f + expf(-p[2]));  // literal models.py:184
+    dv[kDvSX] = softplus_f(p[m.off_scale_x]);
+    dv[kDvSSeas] = m.off_scale_seasonal >= 0 ? softplus_f(p[m.off_scale_seasonal]) : 0.f;
+    dv[kDvSInter] = m.off_scale_inter >= 0 ? softplus_f(p[m.off_scale_inter]) : 0.f;
+  }
+  if (t < m.L) dv[kDvSLayer + t] = softplus_f(p[m.off_layer_scale[t]]);
+  if (t < m.D) {
+    dv[kDvDenom + t] = m.input_scales[t] * expf(p[m.off_lsa + t]);
+    dv[kDvSFourier + t] = m.fourier_scale_off[t] >= 0 ? softplus_f(p[m.fourier_scale_off[t]]) : 0.f;
+  }
+}
+
+// =============================================================================
+// encode: (x rows) -> feat [n_net, B, Fp]  (models.py:216-252)
+// work item = (row, unit); unit = one x column, one (dim,degree) sin/cos pair,
+// one seasonal sin/cos pair, or one interaction column.
+// =============================================================================
+struct UnitInfo { int kind, a, b; };  // kind 0:x 1:fourier(dim a, degree b) 2:seasonal(k=a) 3:inter(j=a)
+
+__device__ __forceinline__ int num_units(const DevModel& m) {
+  int u = m.D;
+  for (int i = 0; i < m.D; ++i) u += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+  return u + m.n_seasonal + m.n_inter;
+}
+__device__ __forceinline__ UnitInfo decode_unit(const DevModel& m, int u) {
+  if (u < m.D) return {0, u, 0};
+  u -= m.D;
+  for (int i = 0; i < m.D; ++i) {
+    int deg = m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+    if (u < deg) return {1, i, u};
+    u -= deg;
+  }
+  if (u < m.n_seasonal) return {2, u, 0};
+  return {3, u - m.n_seasonal, 0};
+}
+
+__device__ __forceinline__ const float* row_ptr(const float* x, const int32_t* idx, int64_t idx_stride,
+                                                int net, int b, int D) {
+  int64_t r = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
+  return x + r * D;
+}
+
+constexpr int kEncRows = 32;
+
+template <typename T>
+__global__ void encode_kernel(const __grid_constant__ DevModel m, const float* __restrict__ derived,
+                              const float* __restrict__ x, const int32_t* __restrict__ idx,
+                              int64_t idx_stride, int B, T* __restrict__ feat) {
+  extern __shared__ float tile[];  // [kEncRows][Fp+1]
+  const int net = blockIdx.y;
+  const int row0 = blockIdx.x * kEncRows;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const int ld = m.Fp + 1;
+  for (int e = threadIdx.x; e < kEncRows * ld; e += blockDim.x) tile[e] = 0.f;
+  __syncthreads();
+  const int U = num_units(m);
+  const float two_pi = 6.283185307179586f;
+  for (int w = threadIdx.x; w < kEncRows * U; w += blockDim.x) {
+    const int u = w / kEncRows, r = w % kEncRows;
+    const int b = row0 + r;
+    if (b >= B) continue;
+    const UnitInfo ui = decode_unit(m, u);
+    const float* xr = row_ptr(x, idx, idx_stride, net, b, m.D);
+    float* trow = tile + r * ld;
+    if (ui.kind == 0) {
+      float sx = xr[ui.a] / dv[kDvDenom + ui.a];
+      trow[m.col_x + ui.a] = sx * dv[kDvSX];
+    } else if (ui.kind == 1) {
+      const int i = ui.a, d = ui.b, deg = m.fourier_deg[i];
+      float sx = xr[i] / dv[kDvDenom + i];
+      float c = two_pi * (float)(1 << d);
+      float sn, cs;
+      sincosf(c * sx, &sn, &cs);
+      const float den = (float)(d + 1), s = dv[kDvSFourier + i];
+      trow[m.fourier_col[i] + d] = (cs / den) * s;
+      trow[m.fourier_col[i] + deg + d] = (sn / den) * s;
+    } else if (ui.kind == 2) {
+      const int k = ui.a;
+      float sn, cs;
+      sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
+      const float s = dv[kDvSSeas], hk = m.seasonal_h[k];
+      trow[m.col_seasonal + k] = (cs / hk) * s;
+      trow[m.col_seasonal + m.n_seasonal + k] = (sn / hk) * s;
+    } else {
+      const int j = ui.a;
+      float sa = xr[m.inter_a[j]] / dv[kDvDenom + m.inter_a[j]];
+      float sb = xr[m.inter_b[j]] / dv[kDvDenom + m.inter_b[j]];
+      trow[m.col_inter + j] = (sa * sb) * dv[kDvSInter];
+    }
+  }
+  __syncthreads();
+  const int rows = min(kEncRows, B - row0);
+  T* out = feat + ((size_t)net * B + row0) * m.Fp;
+  for (int e = threadIdx.x; e < rows * m.Fp; e += blockDim.x) {
+    int r = e / m.Fp, c = e % m.Fp;
+    out[e] = from_f<T>(tile[r * ld + c]);
+  }
+}
+
+// encode backward: dfeat [n_net,B,Fp] f32 -> grads of
+// feature_inv_sp_scale{g} and log_scale_adjustment, accumulated into grad[n_net,P].
+__global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                                  const float* __restrict__ derived, const float* __restrict__ x,
+                                  const int32_t* __restrict__ idx, int64_t idx_stride, int B,
+                                  const float* __restrict__ dfeat, float* __restrict__ grad) {
+  __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
+  const int net = blockIdx.y;
+  const int row0 = blockIdx.x * kEncRows;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const int nacc = m.D + 3 + m.D;
+  for (int e = threadIdx.x; e < nacc; e += blockDim.x) acc[e] = 0.f;
+  __syncthreads();
+  const int U = num_units(m);
+  const float two_pi = 6.283185307179586f;
+  const int lane = threadIdx.x & 31;
+  // every warp processes whole (unit, 32 rows) items -> warp-uniform unit
+  const int items = (kEncRows * U + 31) / 32 * 32;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    const int u = w / kEncRows, r = w % kEncRows;
+    const int b = row0 + r;
+    const bool live = (u < U) && (b < B);
+    float gs = 0.f, gl_a = 0.f, gl_b = 0.f;
+    int slot = 0, dim_a = 0, dim_b = -1;
+    UnitInfo ui = decode_unit(m, u < U ? u : 0);
+    if (ui.kind == 0) { slot = 0; dim_a = ui.a; }
+    else if (ui.kind == 1) { slot = 3 + ui.a; dim_a = ui.a; }
+    else if (ui.kind == 2) { slot = 1; dim_a = -1; }
+    else { slot = 2; dim_a = m.inter_a[ui.a]; dim_b = m.inter_b[ui.a]; }
+    if (live) {
+      const float* xr = row_ptr(x, idx, idx_stride, net, b, m.D);
+      const float* g = dfeat + ((size_t)net * B + b) * m.Fp;
+      if (ui.kind == 0) {
+        float sx = xr[ui.a] / dv[kDvDenom + ui.a];
+        float G = g[m.col_x + ui.a];
+        gs = G * sx;
+        gl_a = dv[kDvSX] * G * (-sx);
+      } else if (ui.kind == 1) {
+        const int i = ui.a, d = ui.b, deg = m.fourier_deg[i];
+        float sx = xr[i] / dv[kDvDenom + i];
+        float c = two_pi * (float)(1 << d);
+        float sn, cs;
+        sincosf(c * sx, &sn, &cs);
+        const float den = (float)(d + 1);
+        float Gc = g[m.fourier_col[i] + d], Gs = g[m.fourier_col[i] + deg + d];
+        gs = Gc * (cs / den) + Gs * (sn / den);
+        float dsx = dv[kDvSFourier + i] * (c / den) * (-sn * Gc + cs * Gs);
+        gl_a = dsx * (-sx);
+      } else if (ui.kind == 2) {
+        const int k = ui.a;
+        float sn, cs;
+        sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
+        float hk = m.seasonal_h[k];
+        gs = g[m.col_seasonal + k] * (cs / hk) + g[m.col_seasonal + m.n_seasonal + k] * (sn / hk);
+      } else {
+        const int j = ui.a;
+        float sa = xr[dim_a] / dv[kDvDenom + dim_a];
+        float sb = xr[dim_b] / dv[kDvDenom + dim_b];
+        float G = g[m.col_inter + j];
+        gs = G * sa * sb;
+        // d(sa*sb)/d lsa_a = -sa*sb, same for b
+        gl_a = dv[kDvSInter] * G * (-sa * sb);
+        gl_b = gl_a;
+      }
+    }
+    gs = warp_sum(gs);
+    gl_a = warp_sum(gl_a);
+    gl_b = warp_sum(gl_b);
+    if (lane == 0 && u < U) {
+      atomicAdd(&acc[m.D + slot], gs);
+      if (dim_a >= 0) atomicAdd(&acc[dim_a], gl_a);
+      if (dim_b >= 0) atomicAdd(&acc[dim_b], gl_b);
+    }
+  }
+  __syncthreads();
+  const float* p = params + (size_t)net * m.P;
+  float* gr = grad + (size_t)net * m.P;
+  for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+    float v = acc[e];
+    if (e < m.D) { atomicAdd(&gr[m.off_lsa + e], v); continue; }
+    int slot = e - m.D, off;
+    if (slot == 0) off = m.off_scale_x;
+    else if (slot == 1) off = m.off_scale_seasonal;
+    else if (slot == 2) off = m.off_scale_inter;
+    else off = m.fourier_scale_off[slot - 3];
+    if (off >= 0) atomicAdd(&gr[off], v * sigmoid_f(p[off]));  // d softplus = sigmoid
+  }
+}
+
+// =============================================================================
+// fp32 SIMT GEMM, 64x64x16 tiles, 256 threads, 4x4 per thread, fused epilogue.
+// Operand element (m,k): A_KC ? A[m*lda+k] : A[k*lda+m]; (k,n): B_KC ? B[n*ldb+k] : B[k*ldb+n]
+// =============================================================================
+template <typename TA, typename TB, bool A_KC, bool B_KC, typename Epi>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const TA* __restrict__ A, size_t a_batch, int lda, const TB* __restrict__ Bm,
+                 size_t b_batch, int ldb, int M, int N, int K, Epi epi) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, net = blockIdx.z;
+  A += (size_t)net * a_batch;
+  Bm += (size_t)net * b_batch;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int mm, kk;
+      if (A_KC) { mm = e >> 4; kk = e & 15; } else { kk = e >> 6; mm = e & 63; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = to_f<TA>(A_KC ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]);
+      As[kk][mm] = v;
+      int nn;
+      if (B_KC) { nn = e >> 4; kk = e & 15; } else { kk = e >> 6; nn = e & 63; }
+      int gn = n0 + nn;
+      gk = k0 + kk;
+      v = 0.f;
+      if (gn < N && gk < K) v = to_f<TB>(B_KC ? Bm[(size_t)gn * ldb + gk] : Bm[(size_t)gk * ldb + gn]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) epi(net, gm, gn, acc[i][j]);
+    }
+}
+
+// forward layer epilogue (models.py:264-268): z = s*(acc/sqrt(fan) + b); h = act(z)
+template <typename T>
+struct EpiFwd {
+  const float* params; const float* derived; int P, off_bias, layer; float isf;
+  T* z; T* h; size_t batch; int ld;
+  __device__ void operator()(int net, int m, int n, float acc) const {
+    const float* dv = derived + (size_t)net * kDerivedStride;
+    float u = acc * isf + params[(size_t)net * P + off_bias + n];
+    float zz = dv[kDvSLayer + layer] * u;
+    size_t o = (size_t)net * batch + (size_t)m * ld + n;
+    if (z) z[o] = from_f<T>(zz);
+    h[o] = from_f<T>(act_f(zz, dv[kDvActW]));
+  }
+};
+template <typename T>
+struct EpiStoreScaled {  // dgrad: out = acc * isf
+  T* out; size_t batch; int ld; float isf;
+  __device__ void operator()(int net, int m, int n, float acc) const {
+    out[(size_t)net * batch + (size_t)m * ld + n] = from_f<T>(acc * isf);
+  }
+};
+struct EpiWgrad {  // grad[net*P + off + m*N + n] += acc*isf
+  float* grad; int P, off, N; float isf;
+  __device__ void operator()(int net, int m, int n, float acc) const {
+    grad[(size_t)net * P + off + (size_t)m * N + n] += acc * isf;
+  }
+};
+
+template <typename T>
+void launch_fwd_layer_simt(const DevModel& m, int layer, const float* params, const float* derived,
+                           const T* a_in, int K, int lda, T* z, T* h, int n_net, int B,
+                           cudaStream_t st) {
+  EpiFwd<T> epi{params, derived, m.P, m.off_bias[layer], layer,
+                layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W, z, h, (size_t)B * m.W, m.W};
+  dim3 grid((m.W + 63) / 64, (B + 63) / 64, n_net);
+  gemm_simt_kernel<T, float, true, false, EpiFwd<T>><<<grid, 256, 0, st>>>(
+      a_in, (size_t)B * lda, lda, params + m.off_kernel[layer], (size_t)m.P, m.W, B, m.W, K, epi);
+}
+template <typename T, typename TO>
+void launch_dgrad_simt(const DevModel& m, int layer, const float* params, const T* dU, TO* out,
+                       int Kout, int ld_out, int n_net, int B, cudaStream_t st) {
+  // out[b,k] = isf * sum_n dU[b,n] * K[k,n]
+  EpiStoreScaled<TO> epi{out, (size_t)B * ld_out, ld_out, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
+  dim3 grid((Kout + 63) / 64, (B + 63) / 64, n_net);
+  gemm_simt_kernel<T, float, true, true, EpiStoreScaled<TO>><<<grid, 256, 0, st>>>(
+      dU, (size_t)B * m.W, m.W, params + m.off_kernel[layer], (size_t)m.P, m.W, B, Kout, m.W, epi);
+}
+template <typename T>
+void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int lda, const T* dU,
+                       float* grad, int n_net, int B, cudaStream_t st) {
+  EpiWgrad epi{grad, m.P, m.off_kernel[layer], m.W, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
+  dim3 grid((m.W + 63) / 64, (Kin + 63) / 64, n_net);
+  gemm_simt_kernel<T, T, false, false, EpiWgrad><<<grid, 256, 0, st>>>(
+      a_in, (size_t)B * lda, lda, dU, (size_t)B * m.W, m.W, Kin, m.W, B, epi);
+}
+
+// =============================================================================
+// head: o = s_out*(h.Ko/sqrt(W) + bo) ; likelihood ; r = dlogp/do  (models.py:269-273,157-191)
+// one warp per row.  Accumulates loglik and the scalar-head gradients.
+// =============================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+            const float* __restrict__ derived, const T* __restrict__ h, const float* __restrict__ y_all,
+            const int32_t* __restrict__ idx, int64_t idx_stride, int B, float* __restrict__ out_loc,
+            float* __restrict__ opre_out, float* __restrict__ r_out, float* __restrict__ ll,
+            float* __restrict__ grad) {
+  const int net = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* p = params + (size_t)net * m.P;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const float* Ko = p + m.off_kernel[m.L];
+  const float bo = p[m.off_bias[m.L]];
+  const float s_out = dv[kDvSOut];
+  const int rows_per_block = 64;
+  float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
+  for (int rr = warp; rr < rows_per_block; rr += 8) {
+    const int b = blockIdx.x * rows_per_block + rr;
+    if (b >= B) break;
+    const T* hr = h + ((size_t)net * B + b) * m.W;
+    float dot = 0.f;
+    for (int n = lane; n < m.W; n += 32) dot = fmaf(to_f<T>(hr[n]), Ko[n], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      const float opre = dot * m.inv_sqrt_W + bo;
+      const float o = s_out * opre;
+      if (out_loc) out_loc[(size_t)net * B + b] = o;
+      if (r_out) {
+        int64_t row = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
+        const float yv = y_all[row];
+        float logp, r;
+        if (m.likelihood == BNF_NORMAL) {
+          const float sg = dv[kDvSigma];
+          const float d = yv / sg - o / sg;              // TFP Normal._log_prob form
+          logp = -0.5f * d * d - (0.9189385332046727f + logf(sg));
+          r = d / sg;
+          a_g0 += (d * d - 1.f) / sg;                     // d/dsigma, chain to lns at the end
+        } else {
+          const float mean = softplus_f(o);
+          const float shp = dv[kDvShape];
+          const float rc = 1.f / shp;                     // total_count
+          const float lg = -logf(shp) - logf(mean);       // logits, models.py:173-175
+          const float sig_l = sigmoid_f(lg);
+          float nb = rc * log_sigmoid_f(-lg) + yv * log_sigmoid_f(lg)
+                     - (lgammaf(1.f + yv) + lgammaf(rc) - lgammaf(1.f + yv + rc)) - logf(rc + yv);
+          float dnb_dl = yv * (1.f - sig_l) - rc * sig_l;
+          float dnb_dr = log_sigmoid_f(-lg) - digamma_f(rc) + digamma_f(1.f + yv + rc) - 1.f / (rc + yv);
+          float wnb = 1.f;                                // d logp / d nb
+          logp = nb;
+          if (m.likelihood == BNF_ZINB) {
+            const float pi = dv[kDvPi];
+            if (yv == 0.f) {
+              const float A = (1.f - pi) * expf(nb), tot = A + pi;
+              logp = logf(tot);
+              wnb = A / tot;
+              a_g2 += (1.f - expf(nb)) / tot;             // d/dpi
+            } else {
+              logp = log1pf(-pi) + nb;
+              a_g2 += -1.f / (1.f - pi);
+            }
+          }
+          r = wnb * dnb_dl * (-sigmoid_f(o) / mean);
+          a_g1 += wnb * (dnb_dl * (-1.f / shp) + dnb_dr * (-1.f / (shp * shp)));  // d/dshape
+        }
+        a_ll += logp;
+        a_gs += r * opre;
+        a_gb += r * s_out;
+        r_out[(size_t)net * B + b] = r;
+        opre_out[(size_t)net * B + b] = opre;
+      }
+    }
+  }
+  if (r_out && lane == 0) atomicAdd(&ll[net], a_ll);
+  if (r_out && grad && lane == 0) {
+    float* g = grad + (size_t)net * m.P;
+    if (m.likelihood == BNF_NORMAL) {
+      atomicAdd(&g[0], a_g0 * expf(p[0]));                // dsigma/dlns = exp(lns)
+    } else {
+      atomicAdd(&g[1], a_g1 * sigmoid_f(p[1]));           // dshape/dp1 = sigmoid
+      if (m.likelihood == BNF_ZINB) {
+        const float pi = dv[kDvPi];
+        atomicAdd(&g[2], a_g2 * pi * (1.f - pi));
+      }
+    }
+    atomicAdd(&g[m.off_out_scale], a_gs * sigmoid_f(p[m.off_out_scale]));
+    atomicAdd(&g[m.off_bias[m.L]], a_gb);
+  }
+}
+
+// =============================================================================
+// activation backward + column reductions for hidden layer `layer`.
+//   IS_HEAD : dh[b,n] = r[b]*s_out*Ko[n]/sqrt(W) (rank-1), also dKo
+//   else    : dh read from `dh_in` (output of the dgrad GEMM), overwritten by dU
+// dz = dh*act'(z); dU = s_l*dz; g_actw += dh*(elu-tanh); g_ls += dz*u; g_b[n] += dU
+// =============================================================================
+constexpr int kActRows = 64;
+template <typename T, bool IS_HEAD>
+__global__ void __launch_bounds__(128)
+act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __restrict__ params,
+               const float* __restrict__ derived, const T* __restrict__ z, const T* __restrict__ h,
+               const float* __restrict__ r, T* __restrict__ dU /* in: dh (unless head), out: dU */,
+               int B, float* __restrict__ grad) {
+  __shared__ float red[2][4];
+  const int net = blockIdx.z;
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int b0 = blockIdx.y * kActRows, b1 = min(B, b0 + kActRows);
+  const float* p = params + (size_t)net * m.P;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const float w = dv[kDvActW], s_l = dv[kDvSLayer + layer];
+  float g_w = 0.f, g_s = 0.f, g_b = 0.f, g_ko = 0.f;
+  if (n < m.W) {
+    float head_c = 0.f;
+    if (IS_HEAD) head_c = dv[kDvSOut] * m.inv_sqrt_W * p[m.off_kernel[m.L] + n];
+    for (int b = b0; b < b1; ++b) {
+      const size_t o = ((size_t)net * B + b) * m.W + n;
+      const float zz = to_f<T>(z[o]);
+      float dh;
+      if (IS_HEAD) {
+        const float rb = r[(size_t)net * B + b];
+        dh = rb * head_c;
+        g_ko += rb * to_f<T>(h[o]);
+      } else {
+        dh = to_f<T>(dU[o]);
+      }
+      float diff;
+      const float da = act_grad_f(zz, w, &diff);
+      const float dz = dh * da;
+      g_w += dh * diff;
+      g_s += dz * zz;                       // = dz*u*s_l ; divided by s_l below
+      const float du = dz * s_l;
+      g_b += du;
+      dU[o] = from_f<T>(du);
+    }
+    float* g = grad + (size_t)net * m.P;
+    atomicAdd(&g[m.off_bias[layer] + n], g_b);
+    if (IS_HEAD) atomicAdd(&g[m.off_kernel[m.L] + n], g_ko * dv[kDvSOut] * m.inv_sqrt_W);
+  }
+  g_w = warp_sum(g_w);
+  g_s = warp_sum(g_s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = g_w; red[1][warp] = g_s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tw = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    float ts = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    float* g = grad + (size_t)net * m.P;
+    atomicAdd(&g[m.off_actw], tw * w * (1.f - w));
+    atomicAdd(&g[m.off_layer_scale[layer]], (ts / s_l) * sigmoid_f(p[m.off_layer_scale[layer]]));
+  }
+}
+
+// =============================================================================
+// prior + Adam (models.py:94-103; inference.py:558-569,580,605-606)
+// g_loss = -(c_ll*g_ll + pw*dlogprior); optax.adam; also sum of log-prior.
+// =============================================================================
+__global__ void tick_kernel(int32_t* step_count) { *step_count += 1; }
+
+__global__ void __launch_bounds__(256)
+map_adam_kernel(int P, float* __restrict__ params, float* __restrict__ am, float* __restrict__ av,
+                const float* __restrict__ g_ll, const int32_t* __restrict__ step_count, float c_ll,
+                float prior_weight, float lr, float* __restrict__ prior_out) {
+  const int net = blockIdx.y;
+  const int t = *step_count;  // already incremented for this step
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  float lp = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)net * P + i;
+    const float th = params[o];
+    float g = -(c_ll * g_ll[o]);
+    if (prior_weight != 0.f) {
+      const float zz = th - (i == 1 ? -1.5f : 0.f);
+      lp += -zz - 2.f * softplus_f(-zz);
+      g = -(c_ll * g_ll[o] + prior_weight * (-tanhf(0.5f * zz)));
+    }
+    const float mm = (1.f - b1) * g + b1 * am[o];
+    const float vv = (1.f - b2) * (g * g) + b2 * av[o];
+    am[o] = mm;
+    av[o] = vv;
+    params[o] = th + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + eps));
+  }
+  if (prior_weight != 0.f) {
+    lp = warp_sum(lp);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&prior_out[net], lp);
+  }
+}
+
+__global__ void map_loss_kernel(int n_net, const float* ll, const float* prior, float c_ll,
+                                float prior_weight, float* out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_net) {
+    out[j] = prior_weight == 0.f ? -(ll[j] * c_ll) : -(ll[j] * c_ll + prior[j] * prior_weight);
+  }
+}
+
+// =============================================================================
+// VI (inference.py:687-739)
+// =============================================================================
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t subseq, uint64_t offset) {
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, subseq, offset, &st);
+  return curand_normal(&st);
+}
+
+// z[s,e,p] = mu[e,p] + sigma[e,p]*eps[s,e,p] ; eps drawn here when eps_in == NULL
+__global__ void __launch_bounds__(256)
+vi_sample_kernel(int P, int E, int S, const float* __restrict__ mu, const float* __restrict__ rho,
+                 const float* __restrict__ eps_in, float* __restrict__ eps_out, uint64_t seed,
+                 uint64_t stream_id, float* __restrict__ z) {
+  const size_t total = (size_t)S * E * P;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t ep = i % ((size_t)E * P);
+    float e = eps_in ? eps_in[i] : philox_normal(seed, stream_id, i);
+    if (eps_out) eps_out[i] = e;
+    const float sg = 1e-4f + softplus_f(rho[ep]);
+    z[i] = mu[ep] + sg * e;
+  }
+}
+
+// Gradient assembly + Adam on (mu, rho) + loss terms.
+//   T(z) = logprior(z) + c*loglik(z), c = (N/B)/kl ;  gT = dlogprior(z) + c*g_ll
+//   dL/dmu = -mean_s gT ; dL/drho = sigmoid(rho)*(-1/sigma - mean_s gT*eps)
+//   loss_e = mean_s [ logq(z_s) - logprior(z_s) ] - c*mean_s loglik_s   (second part added later)
+__global__ void __launch_bounds__(256)
+vi_adam_kernel(int P, int E, int S, float* __restrict__ mu, float* __restrict__ rho,
+               float* __restrict__ am, float* __restrict__ av, const float* __restrict__ z,
+               const float* __restrict__ eps, const float* __restrict__ g_ll,
+               const int32_t* __restrict__ step_count, float c, float lr, float* __restrict__ loss_acc) {
+  const int e = blockIdx.y;
+  const int t = *step_count;
+  const float b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  const float invS = 1.f / (float)S;
+  float lacc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)e * P + i;
+    const float rh = rho[o], m0 = mu[o];
+    const float sg = 1e-4f + softplus_f(rh);
+    const float loc = (i == 1 ? -1.5f : 0.f);
+    float s_gt = 0.f, s_gte = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const size_t os = ((size_t)s * E + e) * P + i;
+      const float zz = z[os] - loc, ee = eps[os];
+      const float gt = -tanhf(0.5f * zz) + c * g_ll[os];
+      s_gt += gt;
+      s_gte += gt * ee;
+      // log q - log prior for this coordinate
+      lacc += (-0.5f * ee * ee - 0.9189385332046727f - logf(sg)) - (-zz - 2.f * softplus_f(-zz));
+    }
+    const float gmu = -s_gt * invS;
+    const float grho = sigmoid_f(rh) * (-1.f / sg - s_gte * invS);
+    // Adam state layout: [E, 2, P]  (mu block then rho block per member)
+    const size_t om = ((size_t)e * 2 + 0) * P + i, orr = ((size_t)e * 2 + 1) * P + i;
+    float mm = (1.f - b1) * gmu + b1 * am[om], vv = (1.f - b2) * (gmu * gmu) + b2 * av[om];
+    am[om] = mm; av[om] = vv;
+    mu[o] = m0 + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + aeps));
+    mm = (1.f - b1) * grho + b1 * am[orr]; vv = (1.f - b2) * (grho * grho) + b2 * av[orr];
+    am[orr] = mm; av[orr] = vv;
+    rho[o] = rh + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + aeps));
+  }
+  lacc = warp_sum(lacc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&loss_acc[e], lacc * invS);
+}
+
+__global__ void vi_loss_kernel(int E, int S, const float* loss_acc, const float* ll, float c, float* out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) {
+    float sll = 0.f;
+    for (int s = 0; s < S; ++s) sll += ll[(size_t)s * E + e];
+    out[e] = loss_acc[e] - c * sll / (float)S;
+  }
+}
+
+// =============================================================================
+// init (inference.py:399-427, :203-231): TruncatedNormal(0,1,[-2,2]) kernels
+// =============================================================================
+__global__ void __launch_bounds__(256)
+init_params_kernel(const __grid_constant__ DevModel m, float lns_init, uint64_t seed,
+                   int64_t first_member, float* __restrict__ params) {
+  const int net = blockIdx.y;
+  float* p = params + (size_t)net * m.P;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.P; i += gridDim.x * blockDim.x) {
+    bool is_kernel = false;
+    for (int l = 0; l <= m.L; ++l) {
+      int fan = l == 0 ? m.F : m.W, out = l == m.L ? 1 : m.W;
+      if (i >= m.off_kernel[l] && i < m.off_kernel[l] + fan * out) is_kernel = true;
+    }
+    float v = 0.f;
+    if (i == 0) v = lns_init;
+    else if (is_kernel) {
+      curandStatePhilox4_32_10_t st;
+      curand_init(seed, (uint64_t)(first_member + net), (uint64_t)i * 16, &st);
+      // rejection sampling on the Philox stream of this (member, parameter)
+      v = curand_normal(&st);
+      for (int it = 0; it < 14 && fabsf(v) > 2.f; ++it) v = curand_normal(&st);
+      if (fabsf(v) > 2.f) v = 0.f;  // p ~ 0.0455^15: unreachable in practice
+    }
+    p[i] = v;
+  }
+}
+
+// =============================================================================
+// mixture quantiles (inference.py:42-84)
+// =============================================================================
+__global__ void minmax_kernel(const float* __restrict__ v, size_t n, float* __restrict__ out /*[2]: min,max as ordered ints*/) {
+  float lo = FLT_MAX, hi = -FLT_MAX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float x = v[i];
+    lo = fminf(lo, x);
+    hi = fmaxf(hi, x);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // float atomic min/max through the order-preserving int mapping
+    auto enc = [](float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; };
+    atomicMin((int*)&out[0], enc(lo));
+    atomicMax((int*)&out[1], enc(hi));
+  }
+}
+__global__ void minmax_init_kernel(float* mm) {
+  ((int*)mm)[0] = 0x7fffffff; ((int*)mm)[1] = (int)0x80000000;
+  ((int*)mm)[2] = 0x7fffffff; ((int*)mm)[3] = (int)0x80000000;
+}
+__device__ __forceinline__ float dec_ordered(float enc) {
+  int i = __float_as_int(enc);
+  return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+__device__ __forceinline__ float mix_cdf(const float* __restrict__ means, const float* __restrict__ scales,
+                                         int M, int N, int n, float xq) {
+  float acc = 0.f;
+  for (int c = 0; c < M; ++c) {
+    float zz = (xq - means[(size_t)c * N + n]) / scales[c];
+    acc += 0.5f * erfcf(-zz * 0.7071067811865476f);
+  }
+  return acc / (float)M;
+}
+
+__global__ void __launch_bounds__(128)
+quantile_root_kernel(const float* __restrict__ means, const float* __restrict__ scales, int M, int N,
+                     const float* __restrict__ mm /* enc min/max of means [0,1], scales [2,3] */,
+                     float q, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float smax = dec_ordered(mm[3]);
+  float b = dec_ordered(mm[0]) - 5.f * smax;   // low
+  float a = dec_ordered(mm[1]) + 5.f * smax;   // high
+  float fa = mix_cdf(means, scales, M, N, n, a) - q;
+  float fb = mix_cdf(means, scales, M, N, n, b) - q;
+  float c = a, fc = fa, t = 0.5f;
+  float best = fabsf(fa) < fabsf(fb) ? a : b, fbest = fminf(fabsf(fa), fabsf(fb));
+  for (int it = 0; it < 60 && fbest > 1e-5f; ++it) {
+    const float xt = a + t * (b - a);
+    const float ft = mix_cdf(means, scales, M, N, n, xt) - q;
+    const bool same = (ft > 0.f) == (fa > 0.f) && (ft < 0.f) == (fa < 0.f);
+    if (same) { c = a; fc = fa; } else { c = b; fc = fb; b = a; fb = fa; }
+    a = xt; fa = ft;
+    if (fabsf(ft) < fbest) { fbest = fabsf(ft); best = xt; }
+    const float xi = (a - b) / (c - b), phi = (fa - fb) / (fc - fb);
+    if (phi * phi < xi && (1.f - phi) * (1.f - phi) < 1.f - xi) {
+      t = fa / (fb - fa) * fc / (fb - fc) + (c - a) / (b - a) * fa / (fc - fa) * fb / (fc - fb);
+    } else {
+      t = 0.5f;
+    }
+    const float tl = 1e-8f / fmaxf(fabsf(b - a), 1e-30f);
+    t = fminf(fmaxf(t, tl), 1.f - tl);
+    if (!(t == t) || isinf(t)) t = 0.5f;
+    if (fabsf(b - a) <= 2.f * FLT_EPSILON * fabsf(a) + 1e-30f) break;
+  }
+  out[n] = best;
+}
+
+__global__ void __launch_bounds__(128)
+quantile_approx_kernel(const float* __restrict__ means, const float* __restrict__ scales, int M, int N,
+                       float ndtri_q, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < M; ++c) {
+    float mu = means[(size_t)c * N + n], sg = scales[c];
+    s1 += mu;
+    s2 += sg * sg + mu * mu;
+  }
+  const float mean = s1 / (float)M;
+  const float sd = sqrtf(s2 / (float)M - mean * mean);
+  out[n] = mean + sd * ndtri_q;
+}
+
+// =============================================================================
+// host-side launch wrappers
+// =============================================================================
+void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, cudaStream_t st) {
+  prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net);
+}
+
+template <typename T>
+void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
+                   int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st) {
+  dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
+  size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
+  encode_kernel<T><<<grid, 256, smem, st>>>(m, derived, x, idx, idx_stride, B, feat);
+}
+template void launch_encode<float>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, float*, int, cudaStream_t);
+template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, __nv_bfloat16*, int, cudaStream_t);
+
+void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
+                       const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
+                       int n_net, cudaStream_t st) {
+  dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
+  encode_bwd_kernel<<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+}
+
+template <typename T>
+void launch_head(const DevModel& m, const float* params, const float* derived, const T* h,
+                 const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
+                 float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st) {
+  dim3 grid((B + 63) / 64, n_net);
+  head_kernel<T><<<grid, 256, 0, st>>>(m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
+}
+template void launch_head<float>(const DevModel&, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
+template void launch_head<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
+
+template <typename T>
+void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* params,
+                    const float* derived, const T* z, const T* h, const float* r, T* dU, int B,
+                    float* grad, int n_net, cudaStream_t st) {
+  dim3 grid((m.W + 127) / 128, (B + kActRows - 1) / kActRows, n_net);
+  if (is_head)
+    act_bwd_kernel<T, true><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+  else
+    act_bwd_kernel<T, false><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+}
+template void launch_act_bwd<float>(const DevModel&, int, bool, const float*, const float*, const float*, const float*, const float*, float*, int, float*, int, cudaStream_t);
+template void launch_act_bwd<__nv_bfloat16>(const DevModel&, int, bool, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, float*, int, cudaStream_t);
+
+template <typename T>
+void launch_fwd_layer_simt_t(const DevModel& m, int layer, const float* params, const float* derived,
+                             const T* a_in, int K, int lda, T* z, T* h, int n_net, int B, cudaStream_t st) {
+  launch_fwd_layer_simt<T>(m, layer, params, derived, a_in, K, lda, z, h, n_net, B, st);
+}
+template <typename T, typename TO>
+void launch_dgrad_simt_t(const DevModel& m, int layer, const float* params, const T* dU, TO* out,
+                         int Kout, int ld_out, int n_net, int B, cudaStream_t st) {
+  launch_dgrad_simt<T, TO>(m, layer, params, dU, out, Kout, ld_out, n_net, B, st);
+}
+template <typename T>
+void launch_wgrad_simt_t(const DevModel& m, int layer, const T* a_in, int Kin, int lda, const T* dU,
+                         float* grad, int n_net, int B, cudaStream_t st) {
+  launch_wgrad_simt<T>(m, layer, a_in, Kin, lda, dU, grad, n_net, B, st);
+}
+#define BNF_INST(T)                                                                                   \
+  template void launch_fwd_layer_simt_t<T>(const DevModel&, int, const float*, const float*, const T*, \
+                                           int, int, T*, T*, int, int, cudaStream_t);                 \
+  template void launch_dgrad_simt_t<T, T>(const DevModel&, int, const float*, const T*, T*, int, int,  \
+                                          int, int, cudaStream_t);                                    \
+  template void launch_wgrad_simt_t<T>(const DevModel&, int, const T*, int, int, const T*, float*, int, \
+                                       int, cudaStream_t);
+BNF_INST(float)
+BNF_INST(__nv_bfloat16)
+template void launch_dgrad_simt_t<__nv_bfloat16, float>(const DevModel&, int, const float*,
+                                                        const __nv_bfloat16*, float*, int, int, int,
+                                                        int, cudaStream_t);
+#undef BNF_INST
+
+void launch_tick(int32_t* step_count, cudaStream_t st) { tick_kernel<<<1, 1, 0, st>>>(step_count); }
+
+void launch_map_adam(int P, float* params, float* am, float* av, const float* g_ll,
+                     const int32_t* step_count, float c_ll, float prior_weight, float lr,
+                     float* prior_out, int n_net, cudaStream_t st) {
+  int bx = (P + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  map_adam_kernel<<<dim3(bx, n_net), 256, 0, st>>>(P, params, am, av, g_ll, step_count, c_ll,
+                                                   prior_weight, lr, prior_out);
+}
+void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
+                     float* out, cudaStream_t st) {
+  map_loss_kernel<<<(n_net + 127) / 128, 128, 0, st>>>(n_net, ll, prior, c_ll, prior_weight, out);
+}
+
+void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,
+                      float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st) {
+  size_t total = (size_t)S * E * P;
+  int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  vi_sample_kernel<<<blocks, 256, 0, st>>>(P, E, S, mu, rho, eps_in, eps_out, seed, stream_id, z);
+}
+void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float* av, const float* z,
+                    const float* eps, const float* g_ll, const int32_t* step_count, float c, float lr,
+                    float* loss_acc, cudaStream_t st) {
+  int bx = (P + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  vi_adam_kernel<<<dim3(bx, E), 256, 0, st>>>(P, E, S, mu, rho, am, av, z, eps, g_ll, step_count, c, lr, loss_acc);
+}
+void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out, cudaStream_t st) {
+  vi_loss_kernel<<<(E + 127) / 128, 128, 0, st>>>(E, S, loss_acc, ll, c, out);
+}
+
+void launch_init_params(const DevModel& m, float lns_init, uint64_t seed, int64_t first_member,
+                        int n_net, float* params, cudaStream_t st) {
+  int bx = (m.P + 255) / 256;
+  if (bx > 2048) bx = 2048;
+  init_params_kernel<<<dim3(bx, n_net), 256, 0, st>>>(m, lns_init, seed, first_member, params);
+}
+
+void launch_quantiles(const float* means, const float* scales, int M, int N, const double* q, int nq,
+                      bool approximate, const float* ndtri_q, float* out, float* mm, cudaStream_t st) {
+  if (!approximate) {
+    minmax_init_kernel<<<1, 1, 0, st>>>(mm);
+    size_t n = (size_t)M * N;
+    int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    minmax_kernel<<<blocks, 256, 0, st>>>(means, n, mm);
+    minmax_kernel<<<1, 256, 0, st>>>(scales, (size_t)M, mm + 2);
+  }
+  for (int i = 0; i < nq; ++i) {
+    if (approximate)
+      quantile_approx_kernel<<<(N + 127) / 128, 128, 0, st>>>(means, scales, M, N, ndtri_q[i], out + (size_t)i * N);
+    else
+      quantile_root_kernel<<<(N + 127) / 128, 128, 0, st>>>(means, scales, M, N, mm, (float)q[i], out + (size_t)i * N);
+  }
+}
+
+}  // namespace bnf

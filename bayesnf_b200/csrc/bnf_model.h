@@ -1,0 +1,54 @@
+// Internal model description shared by host bookkeeping and device kernels.
+// Follows models.py:197-273 (BayesianNeuralField1D) of the reference.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/bnf.h"
+
+namespace bnf {
+
+constexpr int kMaxD = 16;       // input dims
+constexpr int kMaxSeasonal = 64;
+constexpr int kMaxInter = 32;
+constexpr int kMaxLayers = 16;  // hidden layers
+constexpr int kFeatPad = 64;
+constexpr int kDerivedStride = 64;  // floats of derived scalars per network    // K-block of the tensor-core path (128B of bf16)
+
+// Passed by value as a __grid_constant__ kernel parameter (< 4 KB).
+struct DevModel {
+  int D, F, Fp, W, L, P;
+  int likelihood;
+  int n_seasonal, n_inter;
+  // feature column bases (column index inside the F-wide feature row) and the
+  // parameter offset of each group's feature_inv_sp_scale{i} (-1: group absent)
+  int col_x, off_scale_x;
+  int fourier_deg[kMaxD], fourier_col[kMaxD], fourier_scale_off[kMaxD];
+  int col_seasonal, off_scale_seasonal;
+  int col_inter, off_scale_inter;
+  float input_scales[kMaxD];          // f32(input_scales), models.py:221
+  float seasonal_w[kMaxSeasonal];     // f32(2*pi) * f32(freq), models.py:73
+  float seasonal_h[kMaxSeasonal];     // harmonic index (denominator)
+  int inter_a[kMaxInter], inter_b[kMaxInter];
+  // parameter offsets
+  int off_lsa, off_actw, off_out_scale;
+  int off_layer_scale[kMaxLayers];
+  int off_bias[kMaxLayers + 1], off_kernel[kMaxLayers + 1];
+  float inv_sqrt_F, inv_sqrt_W;       // 1/sqrt(fan_in) (models.py:267,272)
+};
+
+struct Leaf {
+  std::string name;
+  int64_t offset;
+  int rows, cols;  // cols==0: 1-D of length rows; rows==0: scalar
+};
+
+}  // namespace bnf
+
+struct bnf_plan {
+  bnf::DevModel m;
+  std::vector<bnf::Leaf> leaves;
+  int n_groups;
+  int sm_count;
+};

@@ -1,0 +1,28 @@
+// tcgen05 (bf16 operands, f32 TMEM accumulators) GEMMs of the dense stack.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "bnf_model.h"
+
+namespace bnf {
+
+// NULL when the plan can run on the tensor-core path, else a reason string.
+const char* tc_unsupported_reason(const DevModel& m);
+const char* tc_last_error();
+// bf16 elements of staged weights per network (all hidden layers, padded K)
+size_t tc_weight_elems(const DevModel& m);
+// f32 master kernels -> bf16 staging: wt = [layer][N=W][Kp] (K-major for the
+// forward GEMM), wn = [layer][Kp][W] (natural (in,out); K-major for dgrad).
+void tc_cast_weights(const DevModel& m, const float* params, __nv_bfloat16* wt, __nv_bfloat16* wn,
+                     int n_net, cudaStream_t st);
+int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived,
+                 const __nv_bfloat16* a_in, const __nv_bfloat16* wt, __nv_bfloat16* z,
+                 __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
+// out_bf (hidden layers) or out_f32 (layer 0 -> dfeat [n_net,B,Fp]) receives isf * dU @ K^T
+int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_bfloat16* dU,
+             __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st);
+int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
+             float* grad, int n_net, int B, cudaStream_t st);
+
+}  // namespace bnf

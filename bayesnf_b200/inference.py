@@ -1,0 +1,434 @@
+"""Inference drivers: the reference's function seam over libbnf_sm100.so.
+
+Mirrors ``bayesnf.inference`` (src/bayesnf/inference.py) for the hot path:
+
+* ``fit_map``      inference.py:376-458 (+ ``ensemble_map`` :510-623)
+* ``fit_vi``       inference.py:336-373 (+ ``ensemble_vi`` :626-764)
+* ``predict_bnf``  inference.py:461-507 (+ batched forecast :103-200,
+                   mixture quantiles :42-100)
+
+Same argument names/meaning, same return structure (host numpy arrays with
+leading ``(num_devices, members_per_device, ...)`` axes), same error behaviour.
+PyTorch is only the device-buffer container / stream / process-group plumbing:
+every FLOP of the model runs in the CUDA kernels behind the C ABI.
+
+Differences that are deliberate and documented in DESIGN.md:
+* "device" = one process (torch.distributed rank) per GPU; each rank fits and
+  returns ITS members (leading axis 1); ``predict_bnf`` all-gathers predictions.
+* ``seed`` may be an int or a JAX-style ``uint32[2]`` key; random streams are
+  device Philox, not threefry, so results are statistically -- not bitwise --
+  those of the reference for the same seed.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import models
+from . import parallel
+
+ArrayT = np.ndarray
+
+_PRECISIONS = {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16,
+               'bf16_simt': _lib.PREC_BF16_SIMT}
+_default_precision = os.environ.get('BAYESNF_B200_PRECISION', 'fp32')
+
+
+def set_default_precision(name: str) -> None:
+  """'fp32' (SIMT, <=1e-5 parity mode) or 'bf16' (tcgen05 tensor cores)."""
+  global _default_precision
+  if name not in _PRECISIONS:
+    raise ValueError(f'unknown precision {name!r}')
+  _default_precision = name
+
+
+def get_default_precision() -> str:
+  return _default_precision
+
+
+def _device() -> torch.device:
+  if not torch.cuda.is_available():
+    raise _lib.BnfError(
+        'bayesnf_b200 needs a CUDA (sm_100) device: there is no CPU fallback.')
+  return torch.device('cuda', torch.cuda.current_device())
+
+
+def _ptr(t: torch.Tensor | None):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def seed_to_int(seed) -> int:
+  """Accept an int or a JAX PRNGKey-like uint32[2] array."""
+  if isinstance(seed, (int, np.integer)):
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+  a = np.asarray(seed).astype(np.uint64).ravel()
+  if a.size == 1:
+    return int(a[0])
+  if a.size != 2:
+    raise ValueError('seed must be an int or a uint32[2] key')
+  return (int(a[0]) << 32) | int(a[1])
+
+
+def fold_in(seed: int, data: int) -> int:
+  """Derive an independent 64-bit seed (splitmix64 finaliser)."""
+  z = (seed + 0x9E3779B97F4A7C15 * (data + 1)) & 0xFFFFFFFFFFFFFFFF
+  z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+  z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+  return z ^ (z >> 31)
+
+
+class Engine:
+  """Device buffers + C calls for one ModelSpec on the current CUDA device."""
+
+  def __init__(self, spec: models.ModelSpec, precision: str | None = None):
+    self.spec = spec
+    self.precision_name = precision or _default_precision
+    if self.precision_name not in _PRECISIONS:
+      raise ValueError(f'unknown precision {self.precision_name!r}')
+    self.prec = _PRECISIONS[self.precision_name]
+    self.device = _device()
+    self._ws: dict[tuple, torch.Tensor] = {}
+
+  def workspace(self, mode: int, n_net: int, rows: int) -> torch.Tensor:
+    key = (mode, n_net, rows)
+    ws = self._ws.get(key)
+    if ws is None:
+      nbytes = _lib.lib.bnf_workspace_bytes(self.spec.plan, self.prec, n_net, rows, mode)
+      if nbytes == 0:
+        raise ValueError('invalid workspace request')
+      self._ws.clear()  # one live workspace: shapes change rarely
+      ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+      self._ws[key] = ws
+    return ws
+
+  # ---- mlp.apply over networks (forecast_inner, inference.py:103-126) ----
+  def forward(self, params: torch.Tensor, x: torch.Tensor, slab: int = 16384) -> torch.Tensor:
+    """params [M,P] f32, x [N,D] f32 -> loc [M,N] f32 (row slabs like :129-181)."""
+    M, N = params.shape[0], x.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+    slab = max(1, min(slab, N))
+    tmp = torch.empty((M, slab), dtype=torch.float32, device=self.device)
+    for s in range(0, N, slab):
+      rows = min(slab, N - s)
+      ws = self.workspace(_lib.WS_FORWARD, M, rows)
+      xs = x[s:s + rows]
+      _lib.check(_lib.lib.bnf_forward(
+          self.spec.plan, self.prec, _ptr(params), M, _ptr(xs), None, 0, rows,
+          _ptr(tmp), _ptr(ws), ws.numel(), _stream()))
+      out[:, s:s + rows] = tmp.view(-1)[:M * rows].view(M, rows)
+    return out
+
+  def loglik_grad(self, params, x, y, idx=None, rows=None, want_grad=True):
+    """-> (loglik [M], grad [M,P] | None).  idx: int32 [M or 1, rows] or None."""
+    M = params.shape[0]
+    if idx is not None:
+      rows = idx.shape[-1]
+      stride = idx.shape[-1] if idx.shape[0] > 1 else 0
+    else:
+      rows = rows or x.shape[0]
+      stride = 0
+    ll = torch.empty(M, dtype=torch.float32, device=self.device)
+    grad = torch.empty((M, self.spec.num_params), dtype=torch.float32,
+                       device=self.device) if want_grad else None
+    ws = self.workspace(_lib.WS_GRAD, M, rows)
+    _lib.check(_lib.lib.bnf_loglik_grad(
+        self.spec.plan, self.prec, _ptr(params), M, _ptr(x), _ptr(y), _ptr(idx), stride,
+        rows, _ptr(ll), _ptr(grad), _ptr(ws), ws.numel(), _stream()))
+    return ll, grad
+
+  def map_steps(self, params, adam_m, adam_v, step_count, x, y, idx, rows, n_total,
+                n_steps, lr, prior_weight) -> torch.Tensor:
+    M = params.shape[0]
+    losses = torch.empty((n_steps, M), dtype=torch.float32, device=self.device)
+    ws = self.workspace(_lib.WS_MAP, M, rows)
+    stride = idx.shape[-1] if (idx is not None and idx.shape[0] > 1) else 0
+    _lib.check(_lib.lib.bnf_map_steps(
+        self.spec.plan, self.prec, _ptr(params), _ptr(adam_m), _ptr(adam_v),
+        _ptr(step_count), M, _ptr(x), _ptr(y), _ptr(idx), stride, rows, n_total, n_steps,
+        lr, prior_weight, _ptr(losses), _ptr(ws), ws.numel(), _stream()))
+    return losses
+
+  def vi_step(self, mu, rho, adam_m, adam_v, step_count, n_mc, eps, seed, x, y, idx,
+              rows, n_total, lr, kl_weight, out_loss):
+    E = mu.shape[0]
+    ws = self.workspace(_lib.WS_VI, E * n_mc, rows)
+    _lib.check(_lib.lib.bnf_vi_step(
+        self.spec.plan, self.prec, _ptr(mu), _ptr(rho), _ptr(adam_m), _ptr(adam_v),
+        _ptr(step_count), E, n_mc, _ptr(eps), C.c_uint64(seed), _ptr(x), _ptr(y), _ptr(idx),
+        rows, n_total, lr, kl_weight, _ptr(out_loss), _ptr(ws), ws.numel(), _stream()))
+
+  def vi_sample(self, mu, rho, n_samples, seed, eps=None) -> torch.Tensor:
+    E = mu.shape[0]
+    out = torch.empty((n_samples, E, self.spec.num_params), dtype=torch.float32,
+                      device=self.device)
+    _lib.check(_lib.lib.bnf_vi_sample(self.spec.plan, _ptr(mu), _ptr(rho), E, n_samples,
+                                      _ptr(eps), C.c_uint64(seed), _ptr(out), _stream()))
+    return out
+
+  def init_params(self, lns_init: float, seed: int, first_member: int, n: int) -> torch.Tensor:
+    out = torch.empty((n, self.spec.num_params), dtype=torch.float32, device=self.device)
+    _lib.check(_lib.lib.bnf_init_params(self.spec.plan, lns_init, C.c_uint64(seed),
+                                        first_member, n, _ptr(out), _stream()))
+    return out
+
+
+def mixture_quantiles(means: torch.Tensor, scales: torch.Tensor, quantiles: Sequence[float],
+                      approximate: bool) -> torch.Tensor:
+  """means [M,N], scales [M] (device f32) -> [len(q), N]."""
+  M, N = means.shape
+  q = (C.c_double * len(quantiles))(*[float(v) for v in quantiles])
+  out = torch.empty((len(quantiles), N), dtype=torch.float32, device=means.device)
+  ws = torch.empty(256, dtype=torch.uint8, device=means.device)
+  _lib.check(_lib.lib.bnf_mixture_quantiles(
+      _ptr(means.contiguous()), _ptr(scales.contiguous()), M, N, q, len(quantiles),
+      1 if approximate else 0, _ptr(out), _ptr(ws), ws.numel(), _stream()))
+  return out
+
+
+def _to_device_data(features, target=None):
+  dev = _device()
+  # jnp.array(...) with x64 disabled: float64 pandas values -> float32 (inference.py:553-554)
+  x = torch.as_tensor(np.ascontiguousarray(np.asarray(features, dtype=np.float64)
+                                           ).astype(np.float32)).to(dev)
+  if x.ndim == 1:
+    x = x[:, None]
+  y = None
+  if target is not None:
+    y = torch.as_tensor(np.asarray(target, dtype=np.float64).astype(np.float32)).to(dev)
+  return x, y
+
+
+def _per_member_permutations(n_members, n_rows, generator, device):
+  """Independent uniform permutation per member (permute_dataset, inference.py:35-39,
+  vmapped over members at :593-595)."""
+  keys = torch.rand((n_members, n_rows), generator=generator, device=device)
+  return keys.argsort(dim=1).to(torch.int32).contiguous()
+
+
+def fit_map(
+    features: ArrayT,
+    target: ArrayT,
+    seed,
+    observation_model: str,
+    model_args: dict[str, Any],
+    num_particles: int,
+    learning_rate: float,
+    num_epochs: int,
+    prior_weight: float = 1.0,
+    batch_size: int | None = None,
+    num_splits: int = 1,
+    precision: str | None = None,
+    init_params: np.ndarray | None = None,
+    batch_indices: np.ndarray | None = None,
+) -> tuple[tuple[np.ndarray, ...], np.ndarray]:
+  """Fit a BNF ensemble by MAP (prior_weight=1) or MLE (prior_weight=0).
+
+  Reference: inference.py:376-458.  ``init_params`` ([members, P]) and
+  ``batch_indices`` ([epochs, members, N] row orders) are test hooks that inject
+  the initial parameters / batch order so the run can be compared with the CPU
+  oracle; by default both come from device RNG streams derived from ``seed``.
+  Returns (params tuple with leading (1, members_on_this_rank * ...) axes,
+  losses (1, members, num_epochs)).
+  """
+  spec = models.ModelSpec(**model_args, observation_model=observation_model)
+  eng = Engine(spec, precision)
+  x, y = _to_device_data(features, target)
+  n_total = y.shape[0]
+  if batch_size is None:
+    batch_size = n_total
+  n_dev, rank = parallel.device_count(), parallel.device_index()
+  members = (num_particles // num_splits) // n_dev
+  if members < 1:
+    raise ValueError('ensemble_size cannot be smaller than device_count.')
+  steps_per_epoch = n_total // batch_size
+  if steps_per_epoch < 1:
+    raise ValueError(f'{batch_size=} exceeds {n_total=}')
+  seed = seed_to_int(seed)
+  target_scale = float(np.nanstd(np.asarray(target, dtype=np.float64)))
+  lns_init = math.log(target_scale / 2.0)
+
+  params_out, losses_out = [], []
+  for i in range(num_splits):
+    seed_i = fold_in(seed, i) if num_splits > 1 else seed
+    init_seed, opt_seed = fold_in(seed_i, 0x1001), fold_in(seed_i, 0x1002)
+    if init_params is not None:
+      p = torch.as_tensor(np.asarray(init_params, dtype=np.float32)).to(eng.device)
+      p = p.reshape(-1, spec.num_params)[i * members:(i + 1) * members].contiguous().clone()
+      if p.shape[0] != members:
+        raise ValueError('init_params has the wrong number of members')
+    else:
+      p = eng.init_params(lns_init, init_seed, rank * members, members)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    step_count = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    gen = torch.Generator(device=eng.device)
+    gen.manual_seed((opt_seed + rank) & 0x7FFFFFFFFFFFFFFF)
+    if batch_size >= n_total and batch_indices is None:
+      losses = eng.map_steps(p, m, v, step_count, x, y, None, batch_size, n_total,
+                             num_epochs, learning_rate, prior_weight)       # [epochs, M]
+      epoch_losses = losses
+    else:
+      per_epoch = []
+      for ep in range(num_epochs):
+        if batch_indices is not None:
+          perm = torch.as_tensor(np.asarray(batch_indices[ep], dtype=np.int32)).to(eng.device)
+          perm = perm.reshape(-1, n_total)[i * members:(i + 1) * members].contiguous()
+        else:
+          perm = _per_member_permutations(members, n_total, gen, eng.device)
+        ls = eng.map_steps(p, m, v, step_count, x, y, perm, batch_size, n_total,
+                           steps_per_epoch, learning_rate, prior_weight)
+        per_epoch.append(ls.mean(dim=0))                                   # :614
+      epoch_losses = torch.stack(per_epoch)
+    params_out.append(p.cpu().numpy()[None])                # (1, members, P)
+    losses_out.append(epoch_losses.t().cpu().numpy()[None])  # (1, members, epochs)
+  flat = np.concatenate(params_out, axis=1)
+  losses = np.concatenate(losses_out, axis=1)
+  return spec.unflatten(flat), losses
+
+
+class SurrogatePosterior:
+  """Mean-field Normal surrogate q = prod N(mu, 1e-4 + softplus(rho)).
+
+  Stand-in for the tfd.JointDistribution the reference returns
+  (inference.py:760-764); holds the variational parameters as reference-ordered
+  tuples with leading (1, members) axes.
+  """
+
+  def __init__(self, spec, mu: np.ndarray, rho: np.ndarray):
+    self.loc = spec.unflatten(mu)
+    self.inv_softplus_scale = spec.unflatten(rho)
+
+  def stddev(self):
+    return tuple(1e-4 + np.logaddexp(r, 0.0) for r in self.inv_softplus_scale)
+
+  def mean(self):
+    return self.loc
+
+
+def fit_vi(
+    features: ArrayT,
+    target: ArrayT,
+    seed,
+    observation_model: str,
+    model_args: dict[str, Any],
+    ensemble_size: int,
+    learning_rate: float,
+    num_epochs: int,
+    sample_size_divergence: int,
+    sample_size_posterior: int,
+    kl_weight: float,
+    batch_size: int | None = None,
+    precision: str | None = None,
+    init_params: tuple[np.ndarray, np.ndarray] | None = None,
+    eps: np.ndarray | None = None,
+    posterior_eps: np.ndarray | None = None,
+) -> tuple[SurrogatePosterior, np.ndarray, tuple[np.ndarray, ...]]:
+  """Fit an ensemble of mean-field surrogate posteriors (inference.py:336-373,
+  :626-764).  ``num_epochs`` is the number of optimisation STEPS, as in the
+  reference.  Test hooks: ``init_params`` = (mu, rho) [members, P]; ``eps``
+  [steps, S, members, P]; ``posterior_eps`` [num_samples, members, P].
+  Returns (surrogate, losses (1, members, steps) already times kl_weight,
+  posterior samples tuple with leading (1, num_samples, members)).
+  """
+  spec = models.ModelSpec(**model_args, observation_model=observation_model)
+  eng = Engine(spec, precision)
+  x, y = _to_device_data(features, target)
+  n_total = y.shape[0]
+  if batch_size is not None:
+    assert n_total >= batch_size, f'{batch_size=} exceeds {n_total=}'
+  rows = batch_size if batch_size is not None else n_total
+  n_dev, rank = parallel.device_count(), parallel.device_index()
+  members = ensemble_size // n_dev
+  if members < 1:
+    raise ValueError('ensemble_size cannot be smaller than device_count.')
+  seed = seed_to_int(seed)
+  init_seed, opt_seed = fold_in(seed, 0x2001), fold_in(seed, 0x2002)
+  fit_seed, sample_seed = fold_in(opt_seed, 1), fold_in(opt_seed, 2)
+  P = spec.num_params
+  if init_params is not None:
+    mu = torch.as_tensor(np.asarray(init_params[0], np.float32)).to(eng.device).reshape(members, P).clone()
+    rho = torch.as_tensor(np.asarray(init_params[1], np.float32)).to(eng.device).reshape(members, P).clone()
+  else:
+    mu = eng.init_params(0.0, init_seed, rank * members, members)   # :203-231, lns mean = 0
+    rho = torch.full((members, P), math.log(math.expm1(0.3)), dtype=torch.float32,
+                     device=eng.device)
+  am = torch.zeros((members, 2, P), dtype=torch.float32, device=eng.device)
+  av = torch.zeros_like(am)
+  step_count = torch.zeros(1, dtype=torch.int32, device=eng.device)
+  losses = torch.empty((num_epochs, members), dtype=torch.float32, device=eng.device)
+  gen = torch.Generator(device=eng.device)
+  gen.manual_seed((fit_seed + rank) & 0x7FFFFFFFFFFFFFFF)
+  for step in range(num_epochs):
+    idx = None
+    if batch_size is not None and batch_size < n_total:
+      # one shared random sub-batch per device per step (inference.py:704-709)
+      idx = torch.randperm(n_total, generator=gen, device=eng.device)[:batch_size]
+      idx = idx.to(torch.int32).contiguous()[None]
+    eps_t = None
+    if eps is not None:
+      eps_t = torch.as_tensor(np.asarray(eps[step], np.float32)).to(eng.device).contiguous()
+    eng.vi_step(mu, rho, am, av, step_count, sample_size_divergence, eps_t,
+                (fold_in(fit_seed, 16 + step) + rank) & 0xFFFFFFFFFFFFFFFF, x, y, idx, rows, n_total,
+                learning_rate, kl_weight, losses[step])
+  pe = None
+  if posterior_eps is not None:
+    pe = torch.as_tensor(np.asarray(posterior_eps, np.float32)).to(eng.device).contiguous()
+  samples = eng.vi_sample(mu, rho, sample_size_posterior,
+                          (sample_seed + rank) & 0xFFFFFFFFFFFFFFFF, pe)
+  surrogate = SurrogatePosterior(spec, mu.cpu().numpy()[None], rho.cpu().numpy()[None])
+  # inference.py:758: transpose to (devices, members, steps) and multiply by kl_weight
+  losses_np = losses.t().cpu().numpy()[None] * kl_weight
+  return surrogate, losses_np, spec.unflatten(samples.cpu().numpy()[None])
+
+
+def predict_bnf(
+    features: ArrayT,
+    observation_model: str,
+    params: Sequence[np.ndarray],
+    model_args: dict[str, Any],
+    quantiles: Sequence[float],
+    ensemble_dims: int = 2,
+    approximate_quantiles: bool = False,
+    precision: str | None = None,
+) -> tuple[np.ndarray, list[np.ndarray]]:
+  """Predict new data from an existing BNF fit (inference.py:461-507).
+
+  Returns (means (num_devices, [num_samples,] members, N), [quantile (N,), ...]).
+  The forward pass runs on this rank's members only; the predictive parameters
+  are all-gathered once (NCCL) and the mixture quantiles are then computed over
+  every member of every rank.
+  """
+  assert ensemble_dims >= 1
+  spec = models.ModelSpec(**model_args, observation_model=observation_model)
+  eng = Engine(spec, precision)
+  x, _ = _to_device_data(features)
+  flat = spec.flatten(params)                       # (1, [S,] E, P)
+  lead = flat.shape[:-1]
+  nets = torch.as_tensor(flat.reshape(-1, spec.num_params)).to(eng.device).contiguous()
+  loc = eng.forward(nets, x)                        # [M_local, N]
+  dist = spec.distribution
+  if dist == models.LikelihoodDist.NORMAL:
+    scales = 0.01 + torch.exp(nets[:, 0])           # models.py:163
+    loc_all = parallel.all_gather_leading(loc)      # (world, M_local, N)  <- the collective
+    sc_all = parallel.all_gather_leading(scales)
+    world = loc_all.shape[0]
+    q = mixture_quantiles(loc_all.reshape(-1, loc.shape[1]), sc_all.reshape(-1),
+                          list(quantiles), approximate_quantiles)
+    means = loc_all.reshape((world,) + tuple(lead[1:]) + (loc.shape[1],)).cpu().numpy()
+    return means, [q[i].cpu().numpy() for i in range(len(quantiles))]
+  # NB / ZINB predictive quantiles (inference.py:271-333: betainc CDF root find) are
+  # SURVEY.md section 8f item 1 ("next"), not built yet.
+  raise NotImplementedError(
+      'predict_bnf for NB/ZINB observation models is not implemented yet; training '
+      '(fit_map / fit_vi) and Engine.forward support them.')

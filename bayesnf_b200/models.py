@@ -1,0 +1,145 @@
+"""Host-side model bookkeeping (mirror of the reference's ``bayesnf.models``).
+
+The arithmetic of the model (feature encode, dense stack, likelihoods, prior)
+runs in libbnf_sm100.so; this module only keeps the reference's host-side
+bookkeeping -- which is pure numpy there too -- and wraps the C plan:
+
+* ``LikelihoodDist``                models.py:30-33
+* ``make_seasonal_frequencies``     models.py:36-59 (bit-exact numpy bookkeeping)
+* ``ModelSpec``                     the static part of ``make_model`` /
+  ``make_prior`` (inference.py:234-268): parameter-leaf table in
+  ``jax.tree_util.tree_leaves`` order, flat <-> tuple conversion.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class LikelihoodDist(enum.Enum):
+  NORMAL = 'NORMAL'
+  NB = 'NB'
+  ZINB = 'ZINB'
+
+
+_LIK_CODE = {LikelihoodDist.NORMAL: _lib.NORMAL, LikelihoodDist.NB: _lib.NB,
+             LikelihoodDist.ZINB: _lib.ZINB}
+
+
+def make_seasonal_frequencies(seasonality_periods, num_harmonics):
+  """Unique Fourier frequencies for the given periods and harmonics.
+
+  Same contract as models.py:36-59: float32 ``h / p`` for ``h = 1..H_i``,
+  duplicates removed keeping the FIRST occurrence (in concatenation order),
+  and the harmonic index carried along.  Raises ValueError like the reference.
+  """
+  periods = np.array(seasonality_periods, dtype=np.float32)
+  num_harmonics = np.asarray(num_harmonics)
+  if np.any(num_harmonics > periods / 2):
+    raise ValueError('Harmonic cannot exceed half seasonal period.')
+  if periods.shape != num_harmonics.shape:
+    raise ValueError('Number of seasonal periods and harmonics must be equal.')
+  if len(num_harmonics.shape) != 1:
+    raise ValueError(
+        'Arguments `num_harmonics` and `seasonality_periods` must be rank 1.')
+  if periods.shape[0] == 0:
+    return (np.zeros(0), np.zeros(0))
+  per_period = [np.arange(1, h + 1, dtype=np.float32) for h in num_harmonics]
+  freqs = np.concatenate([h / p for h, p in zip(per_period, periods)])
+  first_seen = np.sort(np.unique(freqs, return_index=True)[1])
+  return freqs[first_seen], np.concatenate(per_period)[first_seen]
+
+
+class ModelSpec:
+  """Static model description + the C plan built from ``model_args``.
+
+  ``model_args`` keys are the reference's (spatiotemporal.py:360-370):
+  depth, width, input_scales, num_seasonal_harmonics, seasonality_periods,
+  init_x, fourier_degrees, interactions.
+  """
+
+  def __init__(self, *, width, depth, input_scales, num_seasonal_harmonics,
+               seasonality_periods, init_x, fourier_degrees, interactions,
+               observation_model='NORMAL'):
+    self.distribution = LikelihoodDist(observation_model)
+    self.width, self.depth = int(width), int(depth)
+    self.input_dim = int(init_x[-1]) if len(init_x) > 1 else 1
+    self.input_scales = np.ascontiguousarray(input_scales, dtype=np.float64)
+    self.fourier_degrees = np.ascontiguousarray(fourier_degrees).astype(np.int32)
+    self.interactions = np.ascontiguousarray(
+        np.asarray(interactions).reshape(-1, 2)).astype(np.int32)
+    if self.fourier_degrees.shape[0] != self.input_dim:
+      raise ValueError('fourier_degrees must have one entry per input dim.')
+    if self.input_scales.shape[0] != self.input_dim:
+      raise ValueError('input_scales must have one entry per input dim.')
+    freqs, harm = make_seasonal_frequencies(
+        seasonality_periods, np.asarray(num_seasonal_harmonics))
+    self.seasonal_freq = np.ascontiguousarray(freqs, dtype=np.float32)
+    self.seasonal_harm = np.ascontiguousarray(harm, dtype=np.float32)
+
+    cfg = _lib.Config()
+    cfg.abi_version = _lib.BNF_ABI_VERSION
+    cfg.input_dim, cfg.width, cfg.depth = self.input_dim, self.width, self.depth
+    cfg.likelihood = _LIK_CODE[self.distribution]
+    cfg.n_seasonal = len(self.seasonal_freq)
+    cfg.seasonal_freq = self.seasonal_freq.ctypes.data_as(C.POINTER(C.c_float))
+    cfg.seasonal_harm = self.seasonal_harm.ctypes.data_as(C.POINTER(C.c_float))
+    cfg.fourier_degrees = self.fourier_degrees.ctypes.data_as(C.POINTER(C.c_int32))
+    cfg.n_interactions = len(self.interactions)
+    cfg.interactions = self.interactions.ctypes.data_as(C.POINTER(C.c_int32))
+    cfg.input_scales = self.input_scales.ctypes.data_as(C.POINTER(C.c_double))
+    handle = C.c_void_p()
+    _lib.check(_lib.lib.bnf_plan_create(C.byref(cfg), C.byref(handle)))
+    self._plan = handle
+    info = _lib.PlanInfo()
+    _lib.check(_lib.lib.bnf_plan_info(self._plan, C.byref(info)))
+    self.num_params = info.num_params
+    self.num_features = info.num_features
+    self.padded_features = info.padded_features
+    self.num_feature_groups = info.num_feature_groups
+    # leaves after the three scalar heads, in tree_leaves order
+    self.leaf_names, self.leaf_offsets, self.leaf_shapes = [], [], []
+    buf = C.create_string_buffer(64)
+    for i in range(info.num_leaves):
+      off, rows, cols = C.c_int64(), C.c_int32(), C.c_int32()
+      _lib.check(_lib.lib.bnf_plan_leaf(self._plan, i, buf, 64, C.byref(off),
+                                        C.byref(rows), C.byref(cols)))
+      shape = () if rows.value == 0 else (
+          (rows.value,) if cols.value == 0 else (rows.value, cols.value))
+      self.leaf_names.append(buf.value.decode())
+      self.leaf_offsets.append(off.value)
+      self.leaf_shapes.append(shape)
+
+  def __del__(self):
+    plan, self._plan = getattr(self, '_plan', None), None
+    if plan and _lib is not None and getattr(_lib, 'lib', None) is not None:
+      _lib.lib.bnf_plan_destroy(plan)
+
+  @property
+  def plan(self):
+    return self._plan
+
+  # --- flat (.., P) array  <->  reference params tuple -------------------------
+  def unflatten(self, flat: np.ndarray) -> tuple[np.ndarray, ...]:
+    """(..., P) -> (log_noise_scale, shape, inflated_loc_probs, *leaves)."""
+    lead = flat.shape[:-1]
+    out = [flat[..., 0], flat[..., 1], flat[..., 2]]
+    for off, shape in zip(self.leaf_offsets, self.leaf_shapes):
+      n = int(np.prod(shape)) if shape else 1
+      out.append(flat[..., off:off + n].reshape(lead + tuple(shape)))
+    return tuple(out)
+
+  def flatten(self, params: Sequence[np.ndarray]) -> np.ndarray:
+    """Inverse of :meth:`unflatten`; leading dims are kept."""
+    params = [np.asarray(p, dtype=np.float32) for p in params]
+    if len(params) != 3 + len(self.leaf_shapes):
+      raise ValueError(f'expected {3 + len(self.leaf_shapes)} parameter leaves, '
+                       f'got {len(params)}')
+    lead = params[0].shape
+    return np.concatenate([p.reshape(lead + (-1,)) for p in params], axis=-1)

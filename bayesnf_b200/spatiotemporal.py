@@ -1,0 +1,352 @@
+"""Estimator API: drop-in surface of ``bayesnf.spatiotemporal`` for the hot path.
+
+Same classes, constructor keywords, ``fit`` / ``predict`` signatures, attributes
+(``params_``, ``losses_``, ``data_handler``) and error behaviour as the
+reference (src/bayesnf/spatiotemporal.py:195-648); the numerical work is done by
+``bayesnf_b200.inference`` on the GPU.  The pandas bookkeeping below (period
+arithmetic, time indexing, standardisation) is host-side and integer/float64
+exact with the reference -- pinned by tests/test_spatiotemporal.py, which
+replays the reference's own test cases, and tests/golden/bookkeeping.json.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import inference
+from . import parallel
+
+_EPOCH = '2020-01-01'  # origin of the integer time index (spatiotemporal.py:101)
+
+
+def seasonality_to_float(seasonality: str, freq: str) -> float:
+  """Average number of ``freq`` periods per ``seasonality`` period.
+
+  Counted over the four years 2020..2023 so that leap days are averaged in, e.g.
+  ('Y','D') -> 365.25, ('M','D') -> 30.4375 (spatiotemporal.py:31-59).
+  """
+  year_starts = pd.date_range(_EPOCH, periods=5, freq='YS')
+  coarse = year_starts.to_period(seasonality)
+  n_coarse = (coarse[-1] - coarse[0]).n
+  fine = pd.date_range(coarse[0].start_time, coarse[-1].start_time).to_period(freq)
+  n_fine = (fine[-1] - fine[0]).n
+  return n_fine / n_coarse
+
+
+def seasonalities_to_array(seasonalities: Sequence[float | str], freq: str) -> np.ndarray:
+  """Periods (floats or pandas offset aliases) -> float durations in ``freq`` units.
+
+  Raises TypeError for anything shorter than one ``freq`` (spatiotemporal.py:62-95).
+  """
+  periods = []
+  for s in seasonalities:
+    if isinstance(s, str):
+      value = seasonality_to_float(s, freq)
+      if value < 1:
+        raise TypeError(
+            f'seasonality={s!r} should represent a time span greater than '
+            f'freq={freq!r}, but {s} is {value:.2f} of a {freq}')
+    else:
+      value = s
+      if value < 1:
+        raise TypeError(f'seasonality_float={value!r} should be larger than 1.')
+    periods.append(value)
+  return np.array(periods)
+
+
+def _index_time_column(table, column, timetype, freq, time_min=None):
+  """In place: datetime -> integer period index (or float), shifted to start at 0.
+
+  spatiotemporal.py:98-111.  Returns (table, time_min).
+  """
+  if timetype == 'index':
+    origin = pd.to_datetime(_EPOCH).to_period(freq)
+    as_period = table[column].dt.to_period(freq)
+    table[column] = (as_period - origin).apply(lambda delta: delta.n)
+  elif timetype == 'float':
+    table[column] = table[column].apply(float)
+  else:
+    raise ValueError(f'Unknown timetype: {timetype}')
+  if time_min is None:
+    time_min = table[column].min()
+  table[column] = table[column] - time_min
+  return table, time_min
+
+
+class SpatiotemporalDataHandler:
+  """DataFrame -> float feature matrix (spatiotemporal.py:114-192)."""
+
+  def __init__(self, feature_cols, target_col, timetype, freq, standardize=None):
+    self.feature_cols = feature_cols
+    self.target_col = target_col
+    self.timetype = timetype
+    self.freq = freq
+    self.standardize = standardize
+    self.mu_ = None
+    self.std_ = None
+    self.time_min_ = None
+    self.time_scale_ = None
+
+  @property
+  def _time_idx(self) -> int:
+    return 0
+
+  @property
+  def _time_column(self) -> str:
+    return self.feature_cols[self._time_idx]
+
+  def _maybe_filter_target_nans(self, table: pd.DataFrame) -> pd.DataFrame:
+    if self.target_col in table.columns:
+      return table[table[self.target_col].notna()]
+    return table
+
+  def copy_and_filter_table(self, table: pd.DataFrame) -> pd.DataFrame:
+    return self._maybe_filter_target_nans(table.copy())
+
+  def get_target(self, table: pd.DataFrame) -> np.ndarray:
+    return self._maybe_filter_target_nans(table)[self.target_col].values
+
+  def get_train(self, table: pd.DataFrame) -> np.ndarray:
+    """Training features; records time origin/scale and standardisation stats."""
+    table = self.copy_and_filter_table(table)
+    n_cols = len(self.feature_cols)
+    self.mu_, self.std_ = np.zeros(n_cols), np.ones(n_cols)
+    table, self.time_min_ = _index_time_column(
+        table, self._time_column, self.timetype, self.freq, None)
+    features = table[self.feature_cols].values
+    self.time_scale_ = features[:, self._time_idx].max()
+    if self.standardize:
+      if self._time_column in self.standardize:
+        raise TypeError('Do not standardize the time column!')
+      cols = [self.feature_cols.index(c) for c in self.standardize]
+      block = features[:, cols].astype(float)
+      self.mu_[cols] = np.mean(block, axis=0)
+      self.std_[cols] = np.std(block, axis=0)
+      features = (features - self.mu_) / self.std_
+    return features
+
+  def get_test(self, table: pd.DataFrame) -> np.ndarray:
+    """Test features with the training origin / statistics (call after get_train)."""
+    table, _ = _index_time_column(
+        table.copy(), self._time_column, self.timetype, self.freq, self.time_min_)
+    features = table[self.feature_cols].values
+    if self.standardize:
+      features = (features - self.mu_) / self.std_
+    return features
+
+  def get_input_scales(self) -> np.ndarray:
+    scales = np.ones(len(self.feature_cols))
+    scales[self._time_idx] = self.time_scale_
+    return scales
+
+
+class BayesianNeuralFieldEstimator:
+  """Base class; use BayesianNeuralFieldMAP / MLE / VI (spatiotemporal.py:195-468)."""
+
+  _ensemble_dims: int
+  _prior_weight: float = 1.0
+  _scale_epochs_by_batch_size: bool = False
+
+  def __init__(
+      self,
+      *,
+      feature_cols: Sequence[str],
+      target_col: str,
+      seasonality_periods: Sequence[float | str] | None = None,
+      num_seasonal_harmonics: Sequence[int] | None = None,
+      fourier_degrees: Sequence[float] | None = None,
+      interactions: Sequence[tuple[int, int]] | None = None,
+      freq: str | None = None,
+      timetype: str = 'index',
+      depth: int = 2,
+      width: int = 512,
+      observation_model: str = 'NORMAL',
+      standardize: Sequence[str] | None = None,
+      precision: str | None = None,
+  ):
+    """Arguments as in the reference (spatiotemporal.py:217-232).  ``precision``
+    ('fp32' | 'bf16') is the only addition: arithmetic mode of the dense stack
+    on the GPU (default: ``inference.get_default_precision()``)."""
+    self.num_seasonal_harmonics = num_seasonal_harmonics
+    self.seasonality_periods = seasonality_periods
+    self.observation_model = observation_model
+    self.depth = depth
+    self.width = width
+    self.feature_cols = feature_cols
+    self.target_col = target_col
+    self.timetype = timetype
+    self.freq = freq
+    self.fourier_degrees = fourier_degrees
+    self.standardize = standardize
+    self.interactions = interactions
+    self.precision = precision
+    self.losses_ = None
+    self.params_ = None
+    self.data_handler = SpatiotemporalDataHandler(
+        self.feature_cols, self.target_col, self.timetype, self.freq,
+        standardize=self.standardize)
+
+  # ---- kwargs -> model_args (spatiotemporal.py:296-370) ----
+  def _get_fourier_degrees(self, batch_shape) -> np.ndarray:
+    n_dims = batch_shape[-1]
+    if self.fourier_degrees is None:
+      return np.full(n_dims, 5, dtype=int)
+    degrees = np.atleast_1d(self.fourier_degrees).astype(int)
+    if degrees.shape[-1] != n_dims:
+      raise ValueError(
+          'The length of fourier_degrees ({}) must match the input dimension '
+          'dimension ({}).'.format(degrees.shape[-1], n_dims))
+    return degrees
+
+  def _get_interactions(self) -> np.ndarray:
+    if self.interactions is None:
+      return np.zeros((0, 2), dtype=int)
+    pairs = np.array(self.interactions).astype(int)
+    if np.ndim(pairs) != 2 or pairs.shape[-1] != 2:
+      raise ValueError(
+          'The argument for `interactions` should be a 2-d array of integers of '
+          'shape (N, 2), indicating the column indices to interact (the passed '
+          f'shape was {pairs.shape})')
+    return pairs
+
+  def _get_seasonality_periods(self):
+    index_time = self.timetype == 'index'
+    if (index_time and self.freq is None) or (
+        self.timetype == 'float' and self.freq is not None):
+      raise ValueError(f'Invalid {self.freq=} with {self.timetype=}.')
+    if self.seasonality_periods is None:
+      return np.zeros(0)
+    if index_time:
+      return seasonalities_to_array(self.seasonality_periods, self.freq)
+    if self.timetype == 'float':
+      return np.asarray(self.seasonality_periods, dtype=float)
+    assert False, f'Impossible {self.timetype=}.'
+
+  def _get_num_seasonal_harmonics(self):
+    if self.timetype == 'index':       # discrete time: harmonics as given
+      if self.num_seasonal_harmonics is None:
+        return np.zeros(0)
+      return np.array(self.num_seasonal_harmonics)
+    if self.timetype == 'float':       # continuous time: exactly one harmonic/period
+      if self.num_seasonal_harmonics is not None:
+        raise ValueError(f'Cannot use num_seasonal_harmonics with {self.timetype=}.')
+      # any h in (0, min(.5, p/2)] yields arange(1, 1+h) == [1]  (spatiotemporal.py:351-357)
+      return np.fmin(.5, self._get_seasonality_periods() / 2)
+    assert False, f'Impossible {self.timetype=}.'
+
+  def _model_args(self, batch_shape):
+    return {
+        'depth': self.depth,
+        'input_scales': self.data_handler.get_input_scales(),
+        'num_seasonal_harmonics': self._get_num_seasonal_harmonics(),
+        'seasonality_periods': self._get_seasonality_periods(),
+        'width': self.width,
+        'init_x': batch_shape,
+        'fourier_degrees': self._get_fourier_degrees(batch_shape),
+        'interactions': self._get_interactions(),
+    }
+
+  def predict(self, table, quantiles=(0.5,), approximate_quantiles=False):
+    """Predict the target at new times / locations (spatiotemporal.py:372-408).
+
+    Returns ``(means, quantiles)``: ``means`` has shape (num_devices,
+    ensemble_size // num_devices, len(table)) (VI: an extra posterior-sample
+    axis after the device axis); ``quantiles`` is a list with one (len(table),)
+    array per requested quantile.
+    """
+    test_data = self.data_handler.get_test(table)
+    return inference.predict_bnf(
+        test_data,
+        self.observation_model,
+        params=self.params_,
+        model_args=self._model_args(test_data.shape),
+        quantiles=quantiles,
+        ensemble_dims=self._ensemble_dims,
+        approximate_quantiles=approximate_quantiles,
+        precision=self.precision,
+    )
+
+  def fit(self, table, seed):
+    raise NotImplementedError('Should be implemented by subclass')
+
+  def likelihood_model(self, table: pd.DataFrame):
+    """Not provided: the reference returns a TFP distribution object
+    (spatiotemporal.py:433-468); out of scope for the hot path."""
+    raise NotImplementedError(
+        'likelihood_model() returns a tensorflow_probability object in the '
+        'reference and is outside the GPU hot path of bayesnf_b200.')
+
+
+class BayesianNeuralFieldMAP(BayesianNeuralFieldEstimator):
+  """Stochastic ensembles of maximum-a-posteriori estimates (spatiotemporal.py:471-541)."""
+
+  _ensemble_dims = 2
+
+  def fit(self, table, seed, ensemble_size=16, learning_rate=0.005,
+          num_epochs=5_000, batch_size=None, num_splits=1):
+    if ensemble_size < parallel.device_count():
+      raise ValueError('ensemble_size cannot be smaller than device_count. '
+                       'https://github.com/google/bayesnf/issues/28.')
+    train_data = self.data_handler.get_train(table)
+    train_target = self.data_handler.get_target(table)
+    if batch_size is None:
+      batch_size = train_data.shape[0]
+    if self._scale_epochs_by_batch_size:
+      num_epochs = num_epochs * (train_data.shape[0] // batch_size)
+    model_args = self._model_args((batch_size, train_data.shape[-1]))
+    self.params_, self.losses_ = inference.fit_map(
+        train_data,
+        train_target,
+        seed=seed,
+        observation_model=self.observation_model,
+        model_args=model_args,
+        num_particles=ensemble_size,
+        learning_rate=learning_rate,
+        num_epochs=num_epochs,
+        prior_weight=self._prior_weight,
+        batch_size=batch_size,
+        num_splits=num_splits,
+        precision=self.precision)
+    return self
+
+
+class BayesianNeuralFieldMLE(BayesianNeuralFieldMAP):
+  """Maximum-likelihood ensembles: MAP with the prior switched off (:544-551)."""
+
+  _prior_weight = 0.0
+
+
+class BayesianNeuralFieldVI(BayesianNeuralFieldEstimator):
+  """Ensembles of mean-field surrogate posteriors (spatiotemporal.py:554-648)."""
+
+  _ensemble_dims = 3
+  _scale_epochs_by_batch_size = True
+
+  def fit(self, table, seed, ensemble_size=16, learning_rate=0.01,
+          num_epochs=1_000, sample_size_posterior=30, sample_size_divergence=5,
+          kl_weight=0.1, batch_size=None):
+    train_data = self.data_handler.get_train(table)
+    train_target = self.data_handler.get_target(table)
+    if batch_size is None:
+      batch_size = train_data.shape[0]
+    if self._scale_epochs_by_batch_size:
+      num_epochs = num_epochs * (train_data.shape[0] // batch_size)
+    model_args = self._model_args((batch_size, train_data.shape[-1]))
+    _, self.losses_, self.params_ = inference.fit_vi(
+        train_data,
+        train_target,
+        seed=seed,
+        observation_model=self.observation_model,
+        model_args=model_args,
+        ensemble_size=ensemble_size,
+        learning_rate=learning_rate,
+        num_epochs=num_epochs,
+        sample_size_posterior=sample_size_posterior,
+        sample_size_divergence=sample_size_divergence,
+        kl_weight=kl_weight,
+        batch_size=batch_size,
+        precision=self.precision)
+    return self
