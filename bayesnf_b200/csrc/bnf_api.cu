@@ -2,6 +2,7 @@
 // layout in the reference's tree_leaves order), workspace carving and the
 // orchestration of the kernels for forward / loglik+grad / MAP steps / VI step.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -497,5 +498,16 @@ extern "C" int bnf_mixture_quantiles(const float* means, const float* scales, in
   }
   launch_quantiles(means, scales, M, N, q, nq, approximate != 0, nd.data(), out, (float*)ws, (cudaStream_t)stream);
   CUK();
+  return BNF_OK;
+}
+
+extern "C" int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c, int32_t n_net,
+                              int32_t m, int32_t n, int32_t k, void* stream) {
+  if (!a || !b || !c || n_net < 1 || m < 1 || n < 1 || k < 1) return fail(BNF_ERR_INVALID, "bad argument");
+  int dev = 0, sm = 148;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+  int rc = tc_debug_gemm(mn_major, (const bf16*)a, (const bf16*)b, c, n_net, m, n, k, sm, (cudaStream_t)stream);
+  if (rc) return fail(rc, "tc_debug_gemm: %s", tc_last_error());
   return BNF_OK;
 }

@@ -4,11 +4,13 @@
 // live in bnf_tc.cu and share every non-GEMM kernel in this file.
 #include <curand_kernel.h>
 
+#include <atomic>
 #include <cfloat>
 #include <cstdio>
 
 #include "bnf_device.cuh"
 #include "bnf_kernels.h"
+#include "bnf_prof.h"
 
 namespace bnf {
 
@@ -311,6 +313,7 @@ void launch_fwd_layer_simt(const DevModel& m, int layer, const float* params, co
   EpiFwd<T> epi{params, derived, m.P, m.off_bias[layer], layer,
                 layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W, z, h, (size_t)B * m.W, m.W};
   dim3 grid((m.W + 63) / 64, (B + 63) / 64, n_net);
+  BNF_PROF("gemm_simt_fwd", st);
   gemm_simt_kernel<T, float, true, false, EpiFwd<T>><<<grid, 256, 0, st>>>(
       a_in, (size_t)B * lda, lda, params + m.off_kernel[layer], (size_t)m.P, m.W, B, m.W, K, epi);
 }
@@ -320,6 +323,7 @@ void launch_dgrad_simt(const DevModel& m, int layer, const float* params, const 
   // out[b,k] = isf * sum_n dU[b,n] * K[k,n]
   EpiStoreScaled<TO> epi{out, (size_t)B * ld_out, ld_out, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
   dim3 grid((Kout + 63) / 64, (B + 63) / 64, n_net);
+  BNF_PROF("gemm_simt_dgrad", st);
   gemm_simt_kernel<T, float, true, true, EpiStoreScaled<TO>><<<grid, 256, 0, st>>>(
       dU, (size_t)B * m.W, m.W, params + m.off_kernel[layer], (size_t)m.P, m.W, B, Kout, m.W, epi);
 }
@@ -328,6 +332,7 @@ void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int
                        float* grad, int n_net, int B, cudaStream_t st) {
   EpiWgrad epi{grad, m.P, m.off_kernel[layer], m.W, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
   dim3 grid((m.W + 63) / 64, (Kin + 63) / 64, n_net);
+  BNF_PROF("gemm_simt_wgrad", st);
   gemm_simt_kernel<T, T, false, false, EpiWgrad><<<grid, 256, 0, st>>>(
       a_in, (size_t)B * lda, lda, dU, (size_t)B * m.W, m.W, Kin, m.W, B, epi);
 }
@@ -732,6 +737,7 @@ quantile_approx_kernel(const float* __restrict__ means, const float* __restrict_
 // host-side launch wrappers
 // =============================================================================
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, cudaStream_t st) {
+  BNF_PROF("prep", st);
   prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net);
 }
 
@@ -740,6 +746,7 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st) {
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
   size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
+  BNF_PROF("encode", st);
   encode_kernel<T><<<grid, 256, smem, st>>>(m, derived, x, idx, idx_stride, B, feat);
 }
 template void launch_encode<float>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, float*, int, cudaStream_t);
@@ -749,6 +756,7 @@ void launch_encode_bwd(const DevModel& m, const float* params, const float* deri
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
                        int n_net, cudaStream_t st) {
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
+  BNF_PROF("encode_bwd", st);
   encode_bwd_kernel<<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
 }
 
@@ -757,6 +765,7 @@ void launch_head(const DevModel& m, const float* params, const float* derived, c
                  const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
                  float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st) {
   dim3 grid((B + 63) / 64, n_net);
+  BNF_PROF("head", st);
   head_kernel<T><<<grid, 256, 0, st>>>(m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
 }
 template void launch_head<float>(const DevModel&, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
@@ -767,10 +776,13 @@ void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* par
                     const float* derived, const T* z, const T* h, const float* r, T* dU, int B,
                     float* grad, int n_net, cudaStream_t st) {
   dim3 grid((m.W + 127) / 128, (B + kActRows - 1) / kActRows, n_net);
-  if (is_head)
+  if (is_head) {
+    BNF_PROF("act_bwd", st);
     act_bwd_kernel<T, true><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
-  else
+  } else {
+    BNF_PROF("act_bwd", st);
     act_bwd_kernel<T, false><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+  }
 }
 template void launch_act_bwd<float>(const DevModel&, int, bool, const float*, const float*, const float*, const float*, const float*, float*, int, float*, int, cudaStream_t);
 template void launch_act_bwd<__nv_bfloat16>(const DevModel&, int, bool, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, int, float*, int, cudaStream_t);
@@ -804,18 +816,23 @@ template void launch_dgrad_simt_t<__nv_bfloat16, float>(const DevModel&, int, co
                                                         int, cudaStream_t);
 #undef BNF_INST
 
-void launch_tick(int32_t* step_count, cudaStream_t st) { tick_kernel<<<1, 1, 0, st>>>(step_count); }
+void launch_tick(int32_t* step_count, cudaStream_t st) {
+  BNF_PROF("tick", st);
+  tick_kernel<<<1, 1, 0, st>>>(step_count);
+}
 
 void launch_map_adam(int P, float* params, float* am, float* av, const float* g_ll,
                      const int32_t* step_count, float c_ll, float prior_weight, float lr,
                      float* prior_out, int n_net, cudaStream_t st) {
   int bx = (P + 255) / 256;
   if (bx > 1024) bx = 1024;
+  BNF_PROF("map_adam", st);
   map_adam_kernel<<<dim3(bx, n_net), 256, 0, st>>>(P, params, am, av, g_ll, step_count, c_ll,
                                                    prior_weight, lr, prior_out);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, cudaStream_t st) {
+  BNF_PROF("map_loss", st);
   map_loss_kernel<<<(n_net + 127) / 128, 128, 0, st>>>(n_net, ll, prior, c_ll, prior_weight, out);
 }
 
@@ -823,6 +840,7 @@ void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, co
                       float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st) {
   size_t total = (size_t)S * E * P;
   int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  BNF_PROF("vi_sample", st);
   vi_sample_kernel<<<blocks, 256, 0, st>>>(P, E, S, mu, rho, eps_in, eps_out, seed, stream_id, z);
 }
 void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float* av, const float* z,
@@ -830,9 +848,11 @@ void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float
                     float* loss_acc, cudaStream_t st) {
   int bx = (P + 255) / 256;
   if (bx > 1024) bx = 1024;
+  BNF_PROF("vi_adam", st);
   vi_adam_kernel<<<dim3(bx, E), 256, 0, st>>>(P, E, S, mu, rho, am, av, z, eps, g_ll, step_count, c, lr, loss_acc);
 }
 void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out, cudaStream_t st) {
+  BNF_PROF("vi_loss", st);
   vi_loss_kernel<<<(E + 127) / 128, 128, 0, st>>>(E, S, loss_acc, ll, c, out);
 }
 
@@ -840,23 +860,30 @@ void launch_init_params(const DevModel& m, float lns_init, uint64_t seed, int64_
                         int n_net, float* params, cudaStream_t st) {
   int bx = (m.P + 255) / 256;
   if (bx > 2048) bx = 2048;
+  BNF_PROF("init_params", st);
   init_params_kernel<<<dim3(bx, n_net), 256, 0, st>>>(m, lns_init, seed, first_member, params);
 }
 
 void launch_quantiles(const float* means, const float* scales, int M, int N, const double* q, int nq,
                       bool approximate, const float* ndtri_q, float* out, float* mm, cudaStream_t st) {
   if (!approximate) {
+    BNF_PROF("minmax_init", st);
     minmax_init_kernel<<<1, 1, 0, st>>>(mm);
     size_t n = (size_t)M * N;
     int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    BNF_PROF("minmax", st);
     minmax_kernel<<<blocks, 256, 0, st>>>(means, n, mm);
+    BNF_PROF("minmax", st);
     minmax_kernel<<<1, 256, 0, st>>>(scales, (size_t)M, mm + 2);
   }
   for (int i = 0; i < nq; ++i) {
-    if (approximate)
+    if (approximate) {
+      BNF_PROF("quantile_approx", st);
       quantile_approx_kernel<<<(N + 127) / 128, 128, 0, st>>>(means, scales, M, N, ndtri_q[i], out + (size_t)i * N);
-    else
+    } else {
+      BNF_PROF("quantile_root", st);
       quantile_root_kernel<<<(N + 127) / 128, 128, 0, st>>>(means, scales, M, N, mm, (float)q[i], out + (size_t)i * N);
+    }
   }
 }
 

@@ -1,11 +1,543 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 GEMMs of the dense stack (bf16 operands, f32 accumulation in TMEM).
+//
+// One persistent, warp-specialised kernel template serves the three GEMMs of a
+// hidden layer (models.py:263-268 forward and its jax.value_and_grad backward):
+//   fwd   : Z[b,n]  = sum_k A[b,k]  * Wt[n,k]      A,Wt K-major      (+ bias/scale/activation epilogue)
+//   dgrad : dH[b,k] = sum_n dU[b,n] * Wn[k,n]      dU,Wn K-major
+//   wgrad : dK[k,n] = sum_b A[b,k]  * dU[b,n]      both MN-major (no transposed copies in HBM)
+// Per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
+// smem ring of kStages {A 128x64, B BLOCK_Nx64} bf16 tiles in the 128B-swizzle
+// canonical layout written by TMA; two TMEM accumulator stages so the epilogue
+// of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "bnf_device.cuh"
+#include "bnf_prof.h"
 #include "bnf_tc.h"
+
 namespace bnf {
-const char* tc_unsupported_reason(const DevModel&) { return "not built yet"; }
-const char* tc_last_error() { return ""; }
-size_t tc_weight_elems(const DevModel&) { return 0; }
-void tc_cast_weights(const DevModel&, const float*, __nv_bfloat16*, __nv_bfloat16*, int, cudaStream_t) {}
-int tc_fwd_layer(const bnf_plan*, int, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t) { return BNF_ERR_UNSUPPORTED; }
-int tc_dgrad(const bnf_plan*, int, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, float*, int, int, cudaStream_t) { return BNF_ERR_UNSUPPORTED; }
-int tc_wgrad(const bnf_plan*, int, const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, cudaStream_t) { return BNF_ERR_UNSUPPORTED; }
+
+typedef __nv_bfloat16 bf16;
+
+static thread_local char g_tc_err[256] = "";
+const char* tc_last_error() { return g_tc_err; }
+static int tc_fail(int code, const char* msg) {
+  snprintf(g_tc_err, sizeof(g_tc_err), "%s", msg);
+  return code;
 }
+
+const char* tc_unsupported_reason(const DevModel& m) {
+  if (m.W % 64 != 0) return "width must be a multiple of 64";
+  if (m.W < 64) return "width must be >= 64";
+  return nullptr;
+}
+
+static inline int kp_of(const DevModel& m, int layer) { return layer == 0 ? m.Fp : m.W; }
+static inline size_t layer_off(const DevModel& m, int layer) {
+  return layer == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(layer - 1) * m.W * m.W;
+}
+size_t tc_weight_elems(const DevModel& m) { return layer_off(m, m.L); }
+
+// -----------------------------------------------------------------------------
+// weight staging: f32 master (in,out) -> bf16 natural [Kp][W] and transposed [W][Kp]
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                    bf16* __restrict__ wt, bf16* __restrict__ wn, size_t per_net) {
+  __shared__ float tile[32][33];
+  const int net = blockIdx.z / m.L, layer = blockIdx.z % m.L;
+  const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  if (k0 >= Kp) return;
+  const float* src = params + (size_t)net * m.P + m.off_kernel[layer];
+  const size_t base = (size_t)net * per_net + (layer == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(layer - 1) * m.W * m.W);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int k = k0 + r, n = n0 + tx;
+    float v = (k < Kin && n < m.W) ? src[(size_t)k * m.W + n] : 0.f;
+    tile[r][tx] = v;
+    if (k < Kp && n < m.W) wn[base + (size_t)k * m.W + n] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int n = n0 + r, k = k0 + tx;
+    if (n < m.W && k < Kp) wt[base + (size_t)n * Kp + k] = __float2bfloat16_rn(tile[tx][r]);
+  }
+}
+
+void tc_cast_weights(const DevModel& m, const float* params, bf16* wt, bf16* wn, int n_net, cudaStream_t st) {
+  int kmax = m.Fp > m.W ? m.Fp : m.W;
+  dim3 grid((m.W + 31) / 32, (kmax + 31) / 32, n_net * m.L);
+  BNF_PROF("cast_weights", st);
+  cast_weights_kernel<<<grid, 256, 0, st>>>(m, params, wt, wn, tc_weight_elems(m));
+}
+
+// -----------------------------------------------------------------------------
+// PTX wrappers
+// -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (spin == 1024) t0 = clock64();
+    // a protocol bug must surface as a launch failure, never as a hung GPU
+    if (spin > 1024 && (spin & 1023) == 0 && clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride byte offset
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+// -----------------------------------------------------------------------------
+// the GEMM kernel
+// -----------------------------------------------------------------------------
+enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4 };
+
+struct TcArgs {
+  int mode, n_net;
+  int m_tiles, n_tiles, k_splits, k_blocks;   // k_blocks: 64-wide reduction blocks in total
+  int m_valid, n_valid;                       // rows / cols of the output that exist
+  // epilogue
+  const float* params; const float* derived; int P, off_bias, layer; float isf;
+  bf16* out0; bf16* out1; float* outf;
+  long long out_batch; int ld_out; int grad_off;
+};
+
+constexpr int kTcThreads = 192;
+template <int BLOCK_N> struct TcCfg {
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = BLOCK_N * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+template <int BLOCK_N, bool MN_MAJOR>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ TcArgs a) {
+  using Cfg = TcCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_net = a.m_tiles * a.n_tiles * a.k_splits;
+  const int total_tiles = a.n_net * tiles_per_net;
+  const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int net = t / tiles_per_net;
+        int r = t % tiles_per_net;
+        const int n_t = r % a.n_tiles; r /= a.n_tiles;
+        const int split = r % a.k_splits;
+        const int m_t = r / a.k_splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (!MN_MAJOR) {
+            tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+            tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
+          } else {
+            // MN-major: boxes of [64 reduction rows][64 MN elements]
+            for (int j = 0; j < 2; ++j)
+              tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accum, bf16 x bf16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
+                             ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int r = t % tiles_per_net;
+        r /= a.n_tiles;
+        const int split = r % a.k_splits;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad, bd;
+            if (!MN_MAJOR) {
+              ad = make_smem_desc(sa + k * 32, 16, 1024);
+              bd = make_smem_desc(sb + k * 32, 16, 1024);
+            } else {
+              ad = make_smem_desc(sa + k * 2048, 8192, 1024);
+              bd = make_smem_desc(sb + k * 2048, 8192, 1024);
+            }
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int net = t / tiles_per_net;
+      int r = t % tiles_per_net;
+      const int n_t = r % a.n_tiles; r /= a.n_tiles;
+      const int m_t = r / a.k_splits;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_t * 128 + q * 32 + lane;
+      const bool row_ok = row < a.m_valid;
+      const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
+      float s_l = 1.f, w_act = 0.f;
+      if (a.mode == TC_FWD) { s_l = dv[kDvSLayer + a.layer]; w_act = dv[kDvActW]; }
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
+        const int col0 = n_t * BLOCK_N + c;
+        if (a.mode == TC_FWD) {
+          const float* bias = a.params + (size_t)net * a.P + a.off_bias + col0;
+          uint32_t zp[16], hp[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float z0 = s_l * (__uint_as_float(v[j]) * a.isf + __ldg(bias + j));
+            float z1 = s_l * (__uint_as_float(v[j + 1]) * a.isf + __ldg(bias + j + 1));
+            __nv_bfloat162 zz = __floats2bfloat162_rn(z0, z1);
+            __nv_bfloat162 hh = __floats2bfloat162_rn(act_f(z0, w_act), act_f(z1, w_act));
+            zp[j >> 1] = *reinterpret_cast<uint32_t*>(&zz);
+            hp[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          if (row_ok) {
+            const size_t o = (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0;
+            uint4* hz = reinterpret_cast<uint4*>(a.out1 + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hz[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+            if (a.out0) {
+              uint4* zz = reinterpret_cast<uint4*>(a.out0 + o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) zz[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+            }
+          }
+        } else if (a.mode == TC_DGRAD_BF16) {
+          if (row_ok) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j]) * a.isf, __uint_as_float(v[j + 1]) * a.isf);
+              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(a.out0 + (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        } else if (a.mode == TC_DGRAD_F32 || a.mode == TC_PLAIN_F32) {
+          if (row_ok) {
+            float4* o4 = reinterpret_cast<float4*>(a.outf + (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o4[j] = make_float4(__uint_as_float(v[4 * j]) * a.isf, __uint_as_float(v[4 * j + 1]) * a.isf,
+                                  __uint_as_float(v[4 * j + 2]) * a.isf, __uint_as_float(v[4 * j + 3]) * a.isf);
+          }
+        } else {  // TC_WGRAD: grad[net*P + off + row*ld + col] += acc*isf  (split-K partial sums)
+          if (row_ok) {
+            float* o = a.outf + (size_t)net * a.out_batch + a.grad_off + (size_t)row * a.ld_out + col0;
+            if (a.k_splits == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < a.n_valid) o[j] = __uint_as_float(v[j]) * a.isf;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (col0 + j < a.n_valid) atomicAdd(o + j, __uint_as_float(v[j]) * a.isf);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// -----------------------------------------------------------------------------
+// host side: tensor maps + launch
+// -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor [net][rows][cols] (cols contiguous), box = [1][box_rows][64]
+static int make_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint64_t rows, uint64_t nets,
+                    uint64_t row_stride_elems, uint64_t net_stride_elems, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return tc_fail(BNF_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {cols, rows, nets};
+  cuuint64_t strides[2] = {row_stride_elems * 2, net_stride_elems * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_tc_err, sizeof(g_tc_err), "cuTensorMapEncodeTiled failed (%d): cols=%llu rows=%llu nets=%llu box_rows=%u",
+             (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)nets, box_rows);
+    return BNF_ERR_CUDA;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, bool MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, int sm_count, cudaStream_t st) {
+  using Cfg = TcCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+      return tc_fail(BNF_ERR_CUDA, "cudaFuncSetAttribute(smem) failed");
+    attr_set = true;
+  }
+  long long total = (long long)a.n_net * a.m_tiles * a.n_tiles * a.k_splits;
+  int grid = (int)(total < sm_count ? total : sm_count);
+  if (grid < 1) grid = 1;
+  BNF_PROF(a.mode == TC_FWD ? "tc_gemm_fwd" : (a.mode == TC_WGRAD ? "tc_gemm_wgrad" : (a.mode == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  tc_gemm_kernel<BLOCK_N, MN><<<grid, kTcThreads, Cfg::kSmem, st>>>(ma, mb, a);
+  if (cudaGetLastError() != cudaSuccess) return tc_fail(BNF_ERR_CUDA, "tc_gemm_kernel launch failed");
+  return 0;
+}
+
+template <bool MN>
+static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, int sm, cudaStream_t st) {
+  switch (block_n) {
+    case 256: return launch_tc<256, MN>(ma, mb, a, sm, st);
+    case 128: return launch_tc<128, MN>(ma, mb, a, sm, st);
+    case 64: return launch_tc<64, MN>(ma, mb, a, sm, st);
+  }
+  return tc_fail(BNF_ERR_INVALID, "bad BLOCK_N");
+}
+
+static int pick_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+static int sm_count_of(const bnf_plan* p) {
+  if (p->sm_count > 0) return p->sm_count;
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived, const bf16* a_in,
+                 const bf16* wt, bf16* z, bf16* h, int n_net, int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
+  if (rc) return rc;
+  rc = make_map(&mb, wt + layer_off(m, layer), Kp, m.W, n_net, Kp, tc_weight_elems(m), bn);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_FWD; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1; a.k_blocks = Kp / 64;
+  a.m_valid = B; a.n_valid = m.W;
+  a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
+  a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
+  a.out0 = z; a.out1 = h; a.out_batch = (long long)B * m.W; a.ld_out = m.W;
+  return launch_tc_n<false>(bn, ma, mb, a, sm_count_of(p), st);
+}
+
+int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16* out_bf, float* out_f32,
+             int n_net, int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = kp_of(m, layer);          // output columns (in-features, padded)
+  const int bn = pick_block_n(Kp);
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 128);
+  if (rc) return rc;
+  rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m), bn);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = out_bf ? TC_DGRAD_BF16 : TC_DGRAD_F32; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = Kp / bn; a.k_splits = 1; a.k_blocks = m.W / 64;
+  a.m_valid = B; a.n_valid = Kp;
+  a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
+  a.out0 = out_bf; a.outf = out_f32; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
+  return launch_tc_n<false>(bn, ma, mb, a, sm_count_of(p), st);
+}
+
+int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,
+             cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = kp_of(m, layer), Kin = layer == 0 ? m.F : m.W, bn = pick_block_n(m.W);
+  CUtensorMap ma, mb;
+  // MN-major operands: boxes of [64 batch rows][64 contiguous features]
+  int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 64);
+  if (rc) return rc;
+  rc = make_map(&mb, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 64);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_WGRAD; a.n_net = n_net;
+  a.m_tiles = (Kp + 127) / 128; a.n_tiles = m.W / bn; a.k_blocks = (B + 63) / 64;
+  const int sm = sm_count_of(p);
+  long long base_tiles = (long long)n_net * a.m_tiles * a.n_tiles;
+  int splits = 1;
+  if (base_tiles < 2LL * sm) splits = (int)((2LL * sm + base_tiles - 1) / base_tiles);
+  if (splits > a.k_blocks / 4) splits = a.k_blocks / 4;   // >= 4 k-blocks per split
+  if (splits < 1) splits = 1;
+  // every split must own at least one k-block
+  while (splits > 1 && (a.k_blocks + splits - 1) / splits * (splits - 1) >= a.k_blocks) --splits;
+  a.k_splits = splits;
+  a.m_valid = Kin; a.n_valid = m.W;
+  a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
+  a.outf = grad; a.out_batch = m.P; a.ld_out = m.W; a.grad_off = m.off_kernel[layer];
+  return launch_tc_n<true>(bn, ma, mb, a, sm, st);
+}
+
+// debug / test entry: plain C[net][M][N] (f32) = A x B in either operand layout
+int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_net, int M, int N, int K,
+                  int sm_count, cudaStream_t st) {
+  const int bn = pick_block_n(N);
+  if (N % 64 != 0 || (K % 64 != 0 && !mn_major)) return tc_fail(BNF_ERR_INVALID, "N, K must be multiples of 64");
+  CUtensorMap ma, mb;
+  int rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_PLAIN_F32; a.n_net = n_net; a.k_splits = 1; a.isf = 1.f;
+  a.m_tiles = (M + 127) / 128; a.n_tiles = N / bn; a.k_blocks = (K + 63) / 64;
+  a.m_valid = M; a.n_valid = N; a.outf = C; a.out_batch = (long long)M * N; a.ld_out = N;
+  if (!mn_major) {   // A [net][M][K], B [net][N][K]
+    if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
+    if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, bn))) return rc;
+    return launch_tc_n<false>(bn, ma, mb, a, sm_count, st);
+  }
+  // A [net][K][M], B [net][K][N]
+  if ((rc = make_map(&ma, A, M, K, n_net, M, (uint64_t)M * K, 64))) return rc;
+  if ((rc = make_map(&mb, Bm, N, K, n_net, N, (uint64_t)N * K, 64))) return rc;
+  return launch_tc_n<true>(bn, ma, mb, a, sm_count, st);
+}
+
+}  // namespace bnf

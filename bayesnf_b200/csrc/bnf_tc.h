@@ -25,4 +25,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_b
 int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
              float* grad, int n_net, int B, cudaStream_t st);
 
+int tc_debug_gemm(int mn_major, const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, int n_net,
+                  int M, int N, int K, int sm_count, cudaStream_t st);
+
 }  // namespace bnf

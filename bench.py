@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- BayesNF ensemble-training hot path on B200 (contract: see the task brief).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm
+
+A "step" is one MAP training step (encode -> dense stack fwd -> Normal log-lik ->
+backward -> prior + Adam) of every ensemble member over one full batch of
+synthetic spatiotemporal data.  Default workload = BASELINE.json configs[1]:
+chickenpox-shaped MAP, width 256, depth 2, 8 members per GPU, bf16 tensor cores,
+N = 10 440 rows (20 sites x 522 weeks), full batch.  Multi-GPU: members shard
+across ranks with NO data-path collective (weak scaling: 8 members per GPU).
+
+The line printed by rank 0 carries: metric/value (whole-job samples/s with
+inputs resident in HBM), e2e (same metric through the public Engine API with
+pinned-host inputs copied every step and the loss read back every step),
+roofline (dominant kernel, CUDA-event timed inside this script),
+cpu_baseline (the torch-CPU oracle on a bounded sample; "port": the reference's
+JAX path cannot be installed here), clocks, gpu_launches.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'train samples/sec (ensemble x batch rows per second, whole job)'
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    'chickenpox_map_e8': dict(width=256, depth=2, members_per_gpu=8, sites=20, times=522, batch=None,
+                              periods=[4.0, 52.1775], harmonics=[2, 10], objective='map'),
+    # BASELINE.json configs[4] per-GPU shard (roofline run): E=128/8 GPUs, B=65536
+    'wind_map_e16': dict(width=1024, depth=6, members_per_gpu=16, sites=128, times=512, batch=65536,
+                         periods=[7, 365.25 / 12, 365.25], harmonics=[3, 10, 10], objective='map'),
+    # BASELINE.json configs[3]-shaped dense stack (W512 L4) with Normal obs, 8 members
+    'air_quality_map_e8': dict(width=512, depth=4, members_per_gpu=8, sites=64, times=512, batch=None,
+                               periods=[24, 168], harmonics=[4, 4], objective='map'),
+}
+
+
+def synth(wl, seed=20240925):
+  """Seeded synthetic field: T integer time steps x S sites."""
+  rng = np.random.default_rng(seed)
+  T, S = wl['times'], wl['sites']
+  lat, lon = rng.normal(size=S), rng.normal(size=S)
+  lat, lon = (lat - lat.mean()) / lat.std(), (lon - lon.mean()) / lon.std()
+  t = np.repeat(np.arange(T, dtype=np.float64), S)
+  la, lo = np.tile(lat, T), np.tile(lon, T)
+  y = np.zeros(T * S)
+  for p in wl['periods']:
+    y += rng.normal() * np.sin(2 * np.pi * t / p + rng.uniform(0, 6.28))
+  y += 0.7 * la - 0.4 * lo * la + rng.normal(scale=0.5, size=T * S)
+  x = np.stack([t, la, lo], 1)
+  margs = dict(width=wl['width'], depth=wl['depth'], input_scales=np.array([T - 1.0, 1.0, 1.0]),
+               num_seasonal_harmonics=np.array(wl['harmonics']),
+               seasonality_periods=np.array(wl['periods'], dtype=float),
+               init_x=(wl['batch'] or T * S, 3), fourier_degrees=np.array([5, 5, 5]),
+               interactions=np.zeros((0, 2), int))
+  return x, y, margs
+
+
+def flops_per_sample(F, W, L):
+  return 6 * (F * W + (L - 1) * W * W + W)      # fwd + dgrad + wgrad
+
+
+class ClockSampler(threading.Thread):
+  """nvidia-smi style clock / throttle-reason sampling DURING the timed region."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+    self.max_mhz = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:  # pylint: disable=broad-except
+      self.nv = None
+
+  def run(self):
+    if self.nv is None:
+      return
+    nv = self.nv
+    names = {nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown')
+             else nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+             getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+             getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+             getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap'}
+    while not self.stop_flag:
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in names.items():
+          if mask & bit:
+            self.reasons.add(name)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      time.sleep(0.02)
+
+  def summary(self):
+    if not self.samples:
+      return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+    return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(self.reasons)}
+
+
+def peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(hbm_gbs=p['hbm_gbs'], tflops=p['bf16_tflops'], tflops_sustained=p['bf16_tflops_sustained'],
+                source='measured (MEASURED_PEAKS.json)')
+  return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+def cpu_oracle_rate(x, y, margs, budget_s, threads=None):
+  """The CPU baseline: oracle MAP steps (value_and_grad + Adam) of ONE member on the
+  full batch, all host threads, for ~budget_s seconds.  Returns samples/s."""
+  import torch
+  from oracle import bnf_oracle as O
+  if threads:
+    torch.set_num_threads(threads)
+  om = O.OracleModel(**margs)
+  g = torch.Generator().manual_seed(0)
+  p = om.flatten(O.init_map_params(om, y, g))
+  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  B = margs['init_x'][0]
+  xt = torch.tensor(x[:B], dtype=torch.float32)
+  yt = torch.tensor(y[:B], dtype=torch.float32)
+  n_total = len(y)
+  steps, t0 = 0, None
+  while True:
+    loss, gr = O.map_loss_and_grad(om, p, xt, yt, n_total, 1.0, 'NORMAL')
+    p, m, v = O.adam_update(p, gr, m, v, steps + 1, 0.005)
+    steps += 1
+    if steps == 1:                 # first step = warm-up (thread pools, allocator)
+      t0 = time.perf_counter()
+      continue
+    el = time.perf_counter() - t0
+    if el > budget_s and steps >= 4:
+      break
+  timed = steps - 1
+  return B * timed / el, timed, torch.get_num_threads()
+
+
+def run_reference(args, wl, x, y, margs):
+  """--impl reference: the reference's CPU implementation of the path.  JAX is not
+  installable here (no network), so this is the torch-CPU oracle
+  ("port") on all host cores.  One 'step' = one MAP step of one member on the full
+  batch; K steps bounded to a few minutes."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import torch
+  from oracle import bnf_oracle as O
+  om = O.OracleModel(**margs)
+  g = torch.Generator().manual_seed(0)
+  p = om.flatten(O.init_map_params(om, y, g))
+  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  B = margs['init_x'][0]
+  xt, yt = torch.tensor(x[:B], dtype=torch.float32), torch.tensor(y[:B], dtype=torch.float32)
+  t = 0
+  for _ in range(args.warmup):
+    t += 1
+    loss, gr = O.map_loss_and_grad(om, p, xt, yt, len(y), 1.0, 'NORMAL')
+    p, m, v = O.adam_update(p, gr, m, v, t, 0.005)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    t += 1
+    loss, gr = O.map_loss_and_grad(om, p, xt, yt, len(y), 1.0, 'NORMAL')
+    p, m, v = O.adam_update(p, gr, m, v, t, 0.005)
+  el = time.perf_counter() - t0
+  val = B * args.steps / el
+  cores = torch.get_num_threads()
+  sample = f'1 member x {B} rows x {args.steps} steps (of {wl["members_per_gpu"]} members per GPU)'
+  print(json.dumps({
+      'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'samples/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic',
+      'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
+                 'batch_rows': B, 'objective': wl['objective']},
+      'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+      'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--workload', default='chickenpox_map_e8', choices=sorted(WORKLOADS))
+  ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'bf16_simt'])
+  ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-baseline work')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-profile', action='store_true')
+  args = ap.parse_args()
+  wl = WORKLOADS[args.workload]
+  x, y, margs = synth(wl)
+  if args.impl == 'reference':
+    run_reference(args, wl, x, y, margs)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from bayesnf_b200 import _lib, inference, models
+
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+
+  spec = models.ModelSpec(**margs, observation_model='NORMAL')
+  eng = inference.Engine(spec, args.precision)
+  E = wl['members_per_gpu']
+  n_total = len(y)
+  B = wl['batch'] or n_total
+  xd, yd = inference._to_device_data(x, y)
+  lns = float(np.log(np.nanstd(y) / 2))
+  p = eng.init_params(lns, 1234, rank * E, E)
+  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  sc = torch.zeros(1, dtype=torch.int32, device=dev)
+  idx = None
+  if B < n_total:
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    idx = inference._per_member_permutations(E, n_total, gen, dev)[:, :B].contiguous()
+
+  def run(k):
+    return eng.map_steps(p, m, v, sc, xd, yd, idx, B, n_total, k, 0.005, 1.0) if idx is None else \
+        torch.cat([eng.map_steps(p, m, v, sc, xd, yd, idx, B, n_total, 1, 0.005, 1.0) for _ in range(k)])
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- device-resident timing -------------------------------------------------
+  run(max(3, args.warmup))
+  sampler = ClockSampler(local)
+  barrier()
+  sampler.start()
+  l0 = _lib.lib.bnf_debug_launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  losses = run(args.steps)
+  e1.record()
+  barrier()
+  launches = _lib.lib.bnf_debug_launch_count() - l0
+  sampler.stop_flag = True
+  ms = e0.elapsed_time(e1)
+  t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+  ms = float(t_ms[0])
+  assert torch.isfinite(losses).all(), 'non-finite loss in the timed region'
+  value = world * E * B * args.steps / (ms * 1e-3)
+
+  # ---- end to end through the public API, host buffers ------------------------
+  xh = torch.tensor(x.astype(np.float32)).pin_memory()
+  yh = torch.tensor(y.astype(np.float32)).pin_memory()
+  xe, ye = torch.empty_like(xd), torch.empty_like(yd)
+  k_e2e = max(5, min(args.steps, 100))
+
+  def e2e_step():
+    xe.copy_(xh, non_blocking=True)
+    ye.copy_(yh, non_blocking=True)
+    ls = eng.map_steps(p, m, v, sc, xe, ye, idx, B, n_total, 1, 0.005, 1.0)
+    return ls.cpu()
+
+  for _ in range(3):
+    e2e_step()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(k_e2e):
+    e2e_step()
+  barrier()
+  e2e_s = time.perf_counter() - t0
+  t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+  e2e_val = world * E * B * k_e2e / float(t_e[0])
+
+  # ---- per-kernel CUDA-event timing (separate short run; not the headline) ----
+  prof, roof = {}, None
+  pk = peaks()
+  if not args.no_profile:
+    _lib.check(_lib.lib.bnf_debug_profile(1))
+    k_prof = 5
+    run(k_prof)
+    buf = C.create_string_buffer(1 << 16)
+    _lib.check(_lib.lib.bnf_debug_profile_report(buf, len(buf)))
+    _lib.check(_lib.lib.bnf_debug_profile(0))
+    for line in buf.value.decode().strip().splitlines():
+      name, cnt, tot = line.split()
+      prof[name] = {'launches_per_step': int(cnt) / k_prof, 'ms_per_step': float(tot) / k_prof}
+    F, W, L = spec.num_features, wl['width'], wl['depth']
+    Fp = spec.padded_features
+    rows = E * B
+    gemm_flops = {   # algorithmic FLOPs per step of each GEMM class (true F, not padded)
+        'fwd': 2.0 * rows * (F * W + (L - 1) * W * W),
+        'dgrad': 2.0 * rows * (F * W + (L - 1) * W * W),
+        'wgrad': 2.0 * rows * (F * W + (L - 1) * W * W),
+    }
+    best = None
+    for name, d in prof.items():
+      for key in gemm_flops:
+        if name.endswith(key) and 'gemm' in name:
+          tf = gemm_flops[key] / (d['ms_per_step'] * 1e-3) / 1e12
+          d['tflops'] = tf
+          if best is None or d['ms_per_step'] > prof[best]['ms_per_step']:
+            best = name
+    if best:
+      d = prof[best]
+      peak = pk['tflops_sustained'] if args.precision == 'bf16' else None
+      roof = {'bound': 'tensor', 'kernel': best, 'achieved': d['tflops'], 'peak': peak,
+              'unit': 'TFLOP/s', 'frac': (d['tflops'] / peak) if peak else None, 'traffic': None,
+              'peak_source': pk['source'] + ', sustained bf16',
+              'avg_launch_ms': d['ms_per_step'] / d['launches_per_step']}
+
+  # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    val, timed, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget)
+    cpu = {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+           'sample': f'1 member x {margs["init_x"][0]} rows x {timed} MAP steps (torch-CPU oracle, f32)'}
+
+  if rank == 0:
+    fps = flops_per_sample(spec.num_features, wl['width'], wl['depth'])
+    act_bytes = E * B * wl['width'] * (2 if args.precision != 'fp32' else 4) * (2 * wl['depth'] + 2)
+    out = {
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'bf16_simt': 'bf16-storage/f32-fma'}[args.precision],
+        'data': 'synthetic',
+        'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
+                   'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
+                   'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'],
+                   'parallelism': f'members sharded x{world}, no collective in training',
+                   'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
+                         if act_bytes > 126 * 2**20 else
+                         f'activation working set {act_bytes / 2**20:.0f} MiB per step (fits L2; steps '
+                         'are data-dependent so no flush is inserted)'},
+        'per_gpu_samples_per_s': value / world,
+        'algorithmic_tflops_per_gpu': value / world * fps / 1e12,
+        'e2e': {'value': e2e_val, 'unit': 'samples/s', 'steps': k_e2e,
+                'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4),
+                'd2h_bytes_per_step': int(E * 4)},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary(),
+        'roofline': roof,
+        'kernels': prof,
+        'cpu_baseline': cpu,
+        'final_loss_mean': float(losses[-1].mean()),
+    }
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -192,6 +192,21 @@ int bnf_mixture_quantiles(const float* means, const float* scales,
                           void* workspace, size_t workspace_bytes, void* stream);
 size_t bnf_quantile_workspace_bytes(int32_t n_components, int32_t n_points);
 
+/* ---- test / profiling hooks (not part of the reference seam) ----------------
+ * bnf_debug_gemm: run the tcgen05 GEMM kernel alone, C[net][M][N] (f32) =
+ *   mn_major == 0: A[net][M][K] x B[net][N][K]^T   (both K-major, as fwd/dgrad use it)
+ *   mn_major == 1: A[net][K][M]^T x B[net][K][N]   (both MN-major, as wgrad uses it)
+ * A, B are bf16.  Used by tests/test_gpu_tc.py against a plain f32 matmul.      */
+int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c,
+                   int32_t n_networks, int32_t m, int32_t n, int32_t k, void* stream);
+/* Kernel launches issued by this library since load (all threads).             */
+uint64_t bnf_debug_launch_count(void);
+/* enable != 0: bracket every kernel launch with CUDA events on its stream (and
+ * forget earlier records); 0: stop.  bnf_debug_profile_report synchronises the
+ * device and writes "name count total_ms\n" per kernel class into buf.         */
+int bnf_debug_profile(int32_t enable);
+int bnf_debug_profile_report(char* buf, int32_t len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""tcgen05 GEMM kernels (bf16 x bf16 -> f32 in TMEM): the GEMM alone against a
+plain f32 matmul of the same bf16 inputs, then the whole bf16 path against the
+oracle and against the bf16-storage SIMT path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cuda():
+  assert torch.cuda.is_available(), 'gpu tests need a CUDA device (no fallback)'
+  torch.cuda.set_device(0)
+  return torch.device('cuda', 0)
+
+
+def _gemm(mn_major, a, b, nets, m, n, k):
+  from bayesnf_b200 import _lib
+  c = torch.full((nets, m, n), float('nan'), dtype=torch.float32, device=a.device)
+  _lib.check(_lib.lib.bnf_debug_gemm(
+      mn_major, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(c.data_ptr()),
+      nets, m, n, k, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+  torch.cuda.synchronize()
+  return c
+
+
+SHAPES = [(1, 128, 64, 64), (1, 128, 128, 128), (1, 128, 256, 256), (2, 256, 256, 512),
+          (3, 200, 128, 192), (1, 100, 64, 64), (2, 1000, 512, 1024), (1, 77, 320, 64),
+          (1, 4096, 1024, 1024), (8, 10440, 256, 256)]
+
+
+@pytest.mark.parametrize('nets,m,n,k', SHAPES)
+def test_gemm_k_major(cuda, nets, m, n, k):
+  """C = A[M,K] . B[N,K]^T  (operand layout of the forward and dgrad GEMMs)."""
+  g = torch.Generator(device='cuda').manual_seed(m * 7 + n)
+  a = torch.randn(nets, m, k, generator=g, device=cuda).to(torch.bfloat16)
+  b = torch.randn(nets, n, k, generator=g, device=cuda).to(torch.bfloat16)
+  c = _gemm(0, a, b, nets, m, n, k)
+  want = torch.bmm(a.float(), b.float().transpose(1, 2))
+  err = float((c - want).abs().max())
+  assert err <= 2e-3 * float(want.abs().max()), err    # f32 accumulation-order noise only
+
+
+@pytest.mark.parametrize('nets,m,n,k', [(1, 128, 64, 64), (1, 128, 128, 128), (1, 256, 256, 256),
+                                        (2, 128, 256, 1000), (1, 64, 64, 200), (3, 64, 128, 77),
+                                        (2, 1024, 1024, 4096), (8, 256, 256, 10440)])
+def test_gemm_mn_major(cuda, nets, m, n, k):
+  """C = A[K,M]^T . B[K,N]  (wgrad: reduction over batch rows, ragged K zero-filled by TMA)."""
+  g = torch.Generator(device='cuda').manual_seed(m * 3 + k)
+  a = torch.randn(nets, k, m, generator=g, device=cuda).to(torch.bfloat16)
+  b = torch.randn(nets, k, n, generator=g, device=cuda).to(torch.bfloat16)
+  c = _gemm(1, a, b, nets, m, n, k)
+  want = torch.bmm(a.float().transpose(1, 2), b.float())
+  err = float((c - want).abs().max())
+  assert err <= 2e-3 * float(want.abs().max()), err
+
+
+def _cfg(width, depth, n):
+  return dict(width=width, depth=depth, input_scales=[n - 1.0, 1, 1], num_seasonal_harmonics=[2, 10],
+              seasonality_periods=[4.0, 52.1775], init_x=(n, 3), fourier_degrees=[5, 5, 5],
+              interactions=np.zeros((0, 2), int))
+
+
+def _setup(cfg, n, nets, dist='NORMAL'):
+  from bayesnf_b200 import inference, models
+  from test_gpu_parity import _data, _random_params
+  x, y = _data(cfg, n, counts=dist != 'NORMAL')
+  om = O.OracleModel(**cfg)
+  P = _random_params(om, nets, y, seed=3)
+  spec = models.ModelSpec(**cfg, observation_model=dist)
+  xd, yd = inference._to_device_data(x, y)
+  return om, spec, P, xd, yd
+
+
+@pytest.mark.parametrize('width,depth,n', [(256, 2, 100), (256, 2, 1000), (128, 3, 333), (512, 2, 300),
+                                           (64, 2, 200)])
+def test_bf16_tc_matches_bf16_simt(cuda, width, depth, n):
+  """Same bf16 storage, tensor cores vs SIMT f32 FMA: differences are only the
+  accumulation order and the bf16 rounding of the staged weights and of dh -> 1e-2 of scale on values,
+  5e-2 of the leaf scale on gradients (small leaves are cancellation-prone sums)."""
+  from bayesnf_b200 import inference
+  cfg = _cfg(width, depth, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3)
+  out = {}
+  for prec in ('bf16', 'bf16_simt'):
+    eng = inference.Engine(spec, prec)
+    loc = eng.forward(P.cuda(), xd)
+    ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+    out[prec] = (loc.cpu(), ll.cpu(), grad.cpu())
+  a, b = out['bf16'], out['bf16_simt']
+  assert float((a[0] - b[0]).abs().max()) <= 1e-2 * float(b[0].abs().max())
+  assert float(((a[1] - b[1]) / b[1]).abs().max()) <= 1e-2
+  for j in range(3):
+    parts = [(0, 3)] + [(o, o + (int(np.prod(s)) if s else 1))
+                        for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+    for lo, hi in parts:
+      scale = float(b[2][j, lo:hi].abs().max()) + 1e-3 * float(b[2][j].abs().max())
+      assert float((a[2][j, lo:hi] - b[2][j, lo:hi]).abs().max()) <= 5e-2 * scale, (lo, hi)
+
+
+@pytest.mark.parametrize('dist', ['NORMAL', 'ZINB'])
+def test_bf16_tc_vs_oracle(cuda, dist):
+  """bf16 tensor-core path vs the f32 oracle: 3e-2 of scale (bf16 has 8 significand bits)."""
+  from bayesnf_b200 import inference
+  n = 500
+  cfg = _cfg(256, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 2, dist)
+  eng = inference.Engine(spec, 'bf16')
+  ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+  for j in range(2):
+    loss, g = O.map_loss_and_grad(om, P[j], xd.cpu(), yd.cpu(), n, 0.0, dist)
+    assert abs(float(ll[j]) + float(loss)) <= 3e-2 * abs(float(loss))
+    assert float((grad[j].cpu() + g).abs().max() / g.abs().max()) < 3e-2
+
+
+def test_bf16_training_tracks_fp32(cuda):
+  """60 full-batch MAP steps at the benchmark shape: the bf16 loss curve follows fp32's."""
+  from bayesnf_b200 import inference
+  n = 2088
+  cfg = _cfg(256, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 4)
+  x, y = xd.cpu().numpy().astype(np.float64), yd.cpu().numpy().astype(np.float64)
+  res = {}
+  for prec in ('fp32', 'bf16'):
+    _, losses = inference.fit_map(x, y, 0, 'NORMAL', cfg, 4, 0.005, 60, precision=prec,
+                                  init_params=P.numpy())
+    res[prec] = losses[0]
+  assert np.isfinite(res['bf16']).all()
+  rel = np.abs(res['bf16'] - res['fp32']) / np.abs(res['fp32'])
+  assert rel.max() < 2e-2, rel.max()
+  assert (res['bf16'][:, -1] < res['bf16'][:, 0]).all()
