@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "bnf_kernels.h"
+#include "bnf_prof.h"
 #include "bnf_tc.h"
 
 using namespace bnf;
@@ -160,7 +162,17 @@ extern "C" int bnf_plan_create(const bnf_config_t* c, bnf_plan_t** out) {
   return BNF_OK;
 }
 
-extern "C" void bnf_plan_destroy(bnf_plan_t* p) { delete p; }
+extern "C" void bnf_plan_destroy(bnf_plan_t* p) {
+  if (!p) return;
+  if (p->graph_stream) {
+    cudaStreamSynchronize((cudaStream_t)p->graph_stream);
+    if (p->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
+    cudaEventDestroy((cudaEvent_t)p->ev_in);
+    cudaEventDestroy((cudaEvent_t)p->ev_out);
+    cudaStreamDestroy((cudaStream_t)p->graph_stream);
+  }
+  delete p;
+}
 
 extern "C" int bnf_plan_info(const bnf_plan_t* p, bnf_plan_info_t* o) {
   if (!p || !o) return fail(BNF_ERR_INVALID, "null argument");
@@ -391,17 +403,66 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
   const DevModel& m = p->m;
   const float c_ll = (float)((double)n_total / (double)B);  // target.shape[0] / batch_size
-  for (int s = 0; s < n_steps; ++s) {
-    launch_tick(step_count, st);
-    CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
-    CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
-    CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, st));
-    // idx == NULL: every step is a full pass over rows [0, B) (full-batch epochs)
-    const int32_t* idx_s = idx ? idx + (size_t)s * B : nullptr;
-    rc = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, st);
+  int32_t* slot = (int32_t*)(w.mm + 8);
+  CU(cudaMemsetAsync(slot, 0, 4, st));
+  auto one_step = [&](cudaStream_t s, const int32_t* idx_s) -> int {
+    launch_tick(step_count, slot, s);
+    CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, s));
+    CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, s));
+    CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, s));
+    int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s);
+    if (r) return r;
+    launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, s);
+    launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss, slot, s);
+    return BNF_OK;
+  };
+  // Full-batch epochs (idx == NULL) are n_steps identical launches sequences: run the
+  // first directly, capture the second into a CUDA graph and replay it.
+  const bool use_graph = idx == nullptr && n_steps >= 8 && !prof_enabled() && !getenv("BNF_NO_GRAPH");
+  int s0 = 0;
+  if (use_graph) {
+    rc = one_step(st, nullptr);
     if (rc) return rc;
-    launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, st);
-    launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss + (size_t)s * n_net, st);
+    CUK();
+    s0 = 1;
+    if (!p->graph_stream) {
+      cudaStream_t gs; cudaEvent_t e1, e2;
+      CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+      p->graph_stream = gs; p->ev_in = e1; p->ev_out = e2;
+    }
+    cudaStream_t gs = (cudaStream_t)p->graph_stream;
+    if (p->graph_exec) {                       // previous call's graph: finished long ago
+      CU(cudaStreamSynchronize(gs));
+      cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
+      p->graph_exec = nullptr;
+    }
+    CU(cudaEventRecord((cudaEvent_t)p->ev_in, st));
+    CU(cudaStreamWaitEvent(gs, (cudaEvent_t)p->ev_in, 0));
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    rc = one_step(gs, nullptr);
+    cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return fail(BNF_ERR_CUDA, "CUDA graph capture of the MAP step failed (%s)", cudaGetErrorString(ce));
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    p->graph_exec = exec;
+    for (int s = 1; s < n_steps; ++s) CU(cudaGraphLaunch(exec, gs));
+    CU(cudaEventRecord((cudaEvent_t)p->ev_out, gs));
+    CU(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_out, 0));
+    return BNF_OK;
+  }
+  for (int s = s0; s < n_steps; ++s) {
+    // idx == NULL: every step is a full pass over rows [0, B) (full-batch epochs)
+    rc = one_step(st, idx ? idx + (size_t)s * B : nullptr);
+    if (rc) return rc;
   }
   CUK();
   return BNF_OK;
@@ -424,7 +485,7 @@ extern "C" int bnf_vi_step(const bnf_plan_t* p, int32_t prec, float* mu, float* 
   if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
   const DevModel& m = p->m;
   const float c = (float)((double)n_total / (double)B) / kl_weight;
-  launch_tick(step_count, st);
+  launch_tick(step_count, nullptr, st);
   // device draws are keyed by `seed`; the caller passes a fresh seed every step
   launch_vi_sample(m.P, E, S, mu, rho, eps, w.veps, seed, 0x5649ULL, w.vz, st);
   CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));

@@ -48,6 +48,42 @@ __device__ __forceinline__ float act_grad_f(float z, float w, float* diff) {
   return w * delu + (1.f - w) * (1.f - t * t);
 }
 
+// bf16-mode variants: one MUFU.TANH + one MUFU.EX2 per element.  Their error
+// (~2^-11 relative for tanh.approx, 2 ulp for ex2.approx) is below the bf16
+// rounding (2^-9) applied to everything this feeds.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float act_fast(float z, float w) {
+  const float t = tanh_fast(z);
+  const float elu = z > 0.f ? z : ex2_fast(z * 1.4426950408889634f) - 1.f;
+  return fmaf(w, elu - t, t);
+}
+__device__ __forceinline__ float act_grad_fast(float z, float w, float* diff) {
+  const float t = tanh_fast(z);
+  const float e = ex2_fast(z * 1.4426950408889634f);
+  const float elu = z > 0.f ? z : e - 1.f;
+  const float delu = z > 0.f ? 1.f : e;
+  *diff = elu - t;
+  const float dt = fmaf(-t, t, 1.f);
+  return fmaf(w, delu - dt, dt);
+}
+template <bool FAST> __device__ __forceinline__ float act_sel(float z, float w) {
+  return FAST ? act_fast(z, w) : act_f(z, w);
+}
+template <bool FAST> __device__ __forceinline__ float act_grad_sel(float z, float w, float* diff) {
+  return FAST ? act_grad_fast(z, w, diff) : act_grad_f(z, w, diff);
+}
+template <typename T> struct FastMath { static constexpr bool value = false; };
+template <> struct FastMath<__nv_bfloat16> { static constexpr bool value = true; };
+
 __device__ __forceinline__ float digamma_f(float x) {
   // psi(x) for x > 0: upward recurrence to x >= 6 then the asymptotic series.
   float acc = 0.f;

@@ -289,7 +289,7 @@ struct EpiFwd {
     float zz = dv[kDvSLayer + layer] * u;
     size_t o = (size_t)net * batch + (size_t)m * ld + n;
     if (z) z[o] = from_f<T>(zz);
-    h[o] = from_f<T>(act_f(zz, dv[kDvActW]));
+    h[o] = from_f<T>(act_sel<FastMath<T>::value>(zz, dv[kDvActW]));
   }
 };
 template <typename T>
@@ -466,7 +466,7 @@ act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __res
         dh = to_f<T>(dU[o]);
       }
       float diff;
-      const float da = act_grad_f(zz, w, &diff);
+      const float da = act_grad_sel<FastMath<T>::value>(zz, w, &diff);
       const float dz = dh * da;
       g_w += dh * diff;
       g_s += dz * zz;                       // = dz*u*s_l ; divided by s_l below
@@ -492,11 +492,91 @@ act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __res
   }
 }
 
+// Vectorised variant (16-byte loads/stores, 8 bf16 or 4 f32 columns per thread),
+// used when W is a multiple of the vector width and 256 % (W/VEC) == 0 so that a
+// thread keeps the same column group for every row it visits (column sums stay in
+// registers).  Same math as act_bwd_kernel.
+constexpr int kActVecRows = 128;
+template <typename T, bool IS_HEAD>
+__global__ void __launch_bounds__(256)
+act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* __restrict__ params,
+                   const float* __restrict__ derived, const T* __restrict__ z, const T* __restrict__ h,
+                   const float* __restrict__ r, T* __restrict__ dU, int B, float* __restrict__ grad) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr bool FAST = FastMath<T>::value;
+  __shared__ float red[2][8];
+  const int net = blockIdx.y;
+  const int G = m.W / VEC;                     // column groups per row
+  const int cg = threadIdx.x % G;
+  const int rstep = 256 / G;                   // rows covered per pass
+  const int b0 = blockIdx.x * kActVecRows, b1 = min(B, b0 + kActVecRows);
+  const float* p = params + (size_t)net * m.P;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const float w = dv[kDvActW], s_l = dv[kDvSLayer + layer];
+  float g_w = 0.f, g_s = 0.f, g_b[VEC], g_ko[VEC], head_c[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    g_b[k] = 0.f; g_ko[k] = 0.f;
+    head_c[k] = IS_HEAD ? dv[kDvSOut] * m.inv_sqrt_W * p[m.off_kernel[m.L] + cg * VEC + k] : 0.f;
+  }
+  for (int b = b0 + threadIdx.x / G; b < b1; b += rstep) {
+    const size_t o = ((size_t)net * B + b) * m.W + (size_t)cg * VEC;
+    alignas(16) T zv[VEC];
+    alignas(16) T dv_in[VEC];
+    alignas(16) T hv[VEC];
+    alignas(16) T out[VEC];
+    *reinterpret_cast<uint4*>(zv) = *reinterpret_cast<const uint4*>(z + o);
+    float rb = 0.f;
+    if (IS_HEAD) {
+      rb = r[(size_t)net * B + b];
+      *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(h + o);
+    } else {
+      *reinterpret_cast<uint4*>(dv_in) = *reinterpret_cast<const uint4*>(dU + o);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float zz = to_f<T>(zv[k]);
+      float dh;
+      if (IS_HEAD) { dh = rb * head_c[k]; g_ko[k] += rb * to_f<T>(hv[k]); }
+      else dh = to_f<T>(dv_in[k]);
+      float diff;
+      const float da = act_grad_sel<FAST>(zz, w, &diff);
+      const float dz = dh * da;
+      g_w += dh * diff;
+      g_s += dz * zz;
+      const float du = dz * s_l;
+      g_b[k] += du;
+      out[k] = from_f<T>(du);
+    }
+    *reinterpret_cast<uint4*>(dU + o) = *reinterpret_cast<const uint4*>(out);
+  }
+  float* g = grad + (size_t)net * m.P;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    atomicAdd(&g[m.off_bias[layer] + cg * VEC + k], g_b[k]);
+    if (IS_HEAD) atomicAdd(&g[m.off_kernel[m.L] + cg * VEC + k], g_ko[k] * dv[kDvSOut] * m.inv_sqrt_W);
+  }
+  g_w = warp_sum(g_w);
+  g_s = warp_sum(g_s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = g_w; red[1][warp] = g_s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tw = 0.f, ts = 0.f;
+    for (int i = 0; i < 8; ++i) { tw += red[0][i]; ts += red[1][i]; }
+    atomicAdd(&g[m.off_actw], tw * w * (1.f - w));
+    atomicAdd(&g[m.off_layer_scale[layer]], (ts / s_l) * sigmoid_f(p[m.off_layer_scale[layer]]));
+  }
+}
+
 // =============================================================================
 // prior + Adam (models.py:94-103; inference.py:558-569,580,605-606)
 // g_loss = -(c_ll*g_ll + pw*dlogprior); optax.adam; also sum of log-prior.
 // =============================================================================
-__global__ void tick_kernel(int32_t* step_count) { *step_count += 1; }
+__global__ void tick_kernel(int32_t* step_count, int32_t* slot) {
+  *step_count += 1;
+  if (slot) *slot += 1;
+}
 
 __global__ void __launch_bounds__(256)
 map_adam_kernel(int P, float* __restrict__ params, float* __restrict__ am, float* __restrict__ av,
@@ -528,9 +608,12 @@ map_adam_kernel(int P, float* __restrict__ params, float* __restrict__ am, float
   }
 }
 
+// out row = (*slot - 1): the device-side step cursor keeps the launch arguments
+// identical for every step, so a whole step can be replayed as one CUDA graph.
 __global__ void map_loss_kernel(int n_net, const float* ll, const float* prior, float c_ll,
-                                float prior_weight, float* out) {
+                                float prior_weight, float* out, const int32_t* slot) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot) out += (size_t)(*slot - 1) * n_net;
   if (j < n_net) {
     out[j] = prior_weight == 0.f ? -(ll[j] * c_ll) : -(ll[j] * c_ll + prior[j] * prior_weight);
   }
@@ -775,6 +858,19 @@ template <typename T>
 void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* params,
                     const float* derived, const T* z, const T* h, const float* r, T* dU, int B,
                     float* grad, int n_net, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int G = m.W / VEC;
+  if (m.W % VEC == 0 && G <= 256 && 256 % G == 0) {
+    dim3 grid((B + kActVecRows - 1) / kActVecRows, n_net);
+    if (is_head) {
+      BNF_PROF("act_bwd", st);
+      act_bwd_vec_kernel<T, true><<<grid, 256, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+    } else {
+      BNF_PROF("act_bwd", st);
+      act_bwd_vec_kernel<T, false><<<grid, 256, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+    }
+    return;
+  }
   dim3 grid((m.W + 127) / 128, (B + kActRows - 1) / kActRows, n_net);
   if (is_head) {
     BNF_PROF("act_bwd", st);
@@ -816,9 +912,9 @@ template void launch_dgrad_simt_t<__nv_bfloat16, float>(const DevModel&, int, co
                                                         int, cudaStream_t);
 #undef BNF_INST
 
-void launch_tick(int32_t* step_count, cudaStream_t st) {
+void launch_tick(int32_t* step_count, int32_t* slot, cudaStream_t st) {
   BNF_PROF("tick", st);
-  tick_kernel<<<1, 1, 0, st>>>(step_count);
+  tick_kernel<<<1, 1, 0, st>>>(step_count, slot);
 }
 
 void launch_map_adam(int P, float* params, float* am, float* av, const float* g_ll,
@@ -831,9 +927,9 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
                                                    prior_weight, lr, prior_out);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
-                     float* out, cudaStream_t st) {
+                     float* out, const int32_t* slot, cudaStream_t st) {
   BNF_PROF("map_loss", st);
-  map_loss_kernel<<<(n_net + 127) / 128, 128, 0, st>>>(n_net, ll, prior, c_ll, prior_weight, out);
+  map_loss_kernel<<<(n_net + 127) / 128, 128, 0, st>>>(n_net, ll, prior, c_ll, prior_weight, out, slot);
 }
 
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,

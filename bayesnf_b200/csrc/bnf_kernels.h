@@ -35,12 +35,12 @@ template <typename T>
 void launch_wgrad_simt_t(const DevModel& m, int layer, const T* a_in, int Kin, int lda, const T* dU,
                          float* grad, int n_net, int B, cudaStream_t st);
 
-void launch_tick(int32_t* step_count, cudaStream_t st);
+void launch_tick(int32_t* step_count, int32_t* slot, cudaStream_t st);
 void launch_map_adam(int P, float* params, float* am, float* av, const float* g_ll,
                      const int32_t* step_count, float c_ll, float prior_weight, float lr,
                      float* prior_out, int n_net, cudaStream_t st);
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
-                     float* out, cudaStream_t st);
+                     float* out, const int32_t* slot, cudaStream_t st);
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,
                       float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st);
 void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float* av, const float* z,

@@ -51,4 +51,10 @@ struct bnf_plan {
   std::vector<bnf::Leaf> leaves;
   int n_groups;
   int sm_count;
+  // CUDA-graph replay of one full-batch MAP step (see bnf_map_steps); mutable
+  // cache, so graph mode is single-threaded per plan.
+  mutable void* graph_stream = nullptr;
+  mutable void* graph_exec = nullptr;
+  mutable void* ev_in = nullptr;
+  mutable void* ev_out = nullptr;
 };

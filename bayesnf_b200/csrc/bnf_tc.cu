@@ -164,13 +164,14 @@ struct TcArgs {
   long long out_batch; int ld_out; int grad_off;
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 template <int BLOCK_N> struct TcCfg {
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BLOCK_N * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
@@ -187,11 +188,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* sbias = (float*)(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][256]: s_l * bias of the tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -282,37 +284,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    // ===================== epilogue (warps 2..9) =====================
+    // warp%4 selects the TMEM lane quarter it may read; the two warps of a quarter
+    // take alternate 32-column chunks, so every SM sub-partition has two epilogue
+    // warps to hide tcgen05.ld / MUFU / store latency behind each other.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int net = t / tiles_per_net;
       int r = t % tiles_per_net;
       const int n_t = r % a.n_tiles; r /= a.n_tiles;
       const int m_t = r / a.k_splits;
+      const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
+      float c1 = a.isf, w_act = 0.f;
+      float* sb = sbias + acc * 256;
+      if (a.mode == TC_FWD) {
+        const float s_l = dv[kDvSLayer + a.layer];
+        c1 = s_l * a.isf;
+        w_act = dv[kDvActW];
+        if (epi_tid < BLOCK_N)
+          sb[epi_tid] = s_l * a.params[(size_t)net * a.P + a.off_bias + n_t * BLOCK_N + epi_tid];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m_t * 128 + q * 32 + lane;
       const bool row_ok = row < a.m_valid;
-      const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
-      float s_l = 1.f, w_act = 0.f;
-      if (a.mode == TC_FWD) { s_l = dv[kDvSLayer + a.layer]; w_act = dv[kDvActW]; }
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = half * 32; c < BLOCK_N; c += 64) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
         if (a.mode == TC_FWD) {
-          const float* bias = a.params + (size_t)net * a.P + a.off_bias + col0;
           uint32_t zp[16], hp[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float z0 = s_l * (__uint_as_float(v[j]) * a.isf + __ldg(bias + j));
-            float z1 = s_l * (__uint_as_float(v[j + 1]) * a.isf + __ldg(bias + j + 1));
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj += 2) {
+            float z0 = fmaf(__uint_as_float(v[j + jj]), c1, bb[jj]);
+            float z1 = fmaf(__uint_as_float(v[j + jj + 1]), c1, bb[jj + 1]);
             __nv_bfloat162 zz = __floats2bfloat162_rn(z0, z1);
-            __nv_bfloat162 hh = __floats2bfloat162_rn(act_f(z0, w_act), act_f(z1, w_act));
-            zp[j >> 1] = *reinterpret_cast<uint32_t*>(&zz);
-            hp[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            __nv_bfloat162 hh = __floats2bfloat162_rn(act_fast(z0, w_act), act_fast(z1, w_act));
+            zp[(j + jj) >> 1] = *reinterpret_cast<uint32_t*>(&zz);
+            hp[(j + jj) >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
           }
           if (row_ok) {
             const size_t o = (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0;
@@ -505,7 +524,7 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   const int sm = sm_count_of(p);
   long long base_tiles = (long long)n_net * a.m_tiles * a.n_tiles;
   int splits = 1;
-  if (base_tiles < 2LL * sm) splits = (int)((2LL * sm + base_tiles - 1) / base_tiles);
+  if (base_tiles < sm) splits = (int)(sm / base_tiles);   // fill one wave, never a ragged second one
   if (splits > a.k_blocks / 4) splits = a.k_blocks / 4;   // >= 4 k-blocks per split
   if (splits < 1) splits = 1;
   // every split must own at least one k-block
