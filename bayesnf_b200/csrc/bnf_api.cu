@@ -442,7 +442,9 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
     CU(cudaStreamWaitEvent(gs, (cudaEvent_t)p->ev_in, 0));
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long before = bnf_debug_launch_count();
     rc = one_step(gs, nullptr);
+    const unsigned long long per_step = bnf_debug_launch_count() - before;
     cudaError_t ce = cudaStreamEndCapture(gs, &graph);
     if (rc || ce != cudaSuccess || !graph) {
       if (graph) cudaGraphDestroy(graph);
@@ -455,6 +457,8 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
     if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
     p->graph_exec = exec;
     for (int s = 1; s < n_steps; ++s) CU(cudaGraphLaunch(exec, gs));
+    // the capture counted one step's kernels without launching them; replays launch them
+    prof_add_launches((long long)per_step * (n_steps - 1) - (long long)per_step);
     CU(cudaEventRecord((cudaEvent_t)p->ev_out, gs));
     CU(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_out, 0));
     return BNF_OK;

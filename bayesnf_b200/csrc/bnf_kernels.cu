@@ -496,7 +496,7 @@ act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __res
 // used when W is a multiple of the vector width and 256 % (W/VEC) == 0 so that a
 // thread keeps the same column group for every row it visits (column sums stay in
 // registers).  Same math as act_bwd_kernel.
-constexpr int kActVecRows = 128;
+constexpr int kActVecRows = 256;
 template <typename T, bool IS_HEAD>
 __global__ void __launch_bounds__(256)
 act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* __restrict__ params,
@@ -505,7 +505,10 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
   constexpr int VEC = 16 / sizeof(T);
   constexpr bool FAST = FastMath<T>::value;
   __shared__ float red[2][8];
+  extern __shared__ float colsum[];            // [W] bias grads (+ [W] Dense_L kernel grads at the head)
   const int net = blockIdx.y;
+  for (int i = threadIdx.x; i < (IS_HEAD ? 2 : 1) * m.W; i += blockDim.x) colsum[i] = 0.f;
+  __syncthreads();
   const int G = m.W / VEC;                     // column groups per row
   const int cg = threadIdx.x % G;
   const int rstep = 256 / G;                   // rows covered per pass
@@ -551,16 +554,21 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
     *reinterpret_cast<uint4*>(dU + o) = *reinterpret_cast<const uint4*>(out);
   }
   float* g = grad + (size_t)net * m.P;
+  // block-level column sums in shared memory first: one global atomic per column per block
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    atomicAdd(&g[m.off_bias[layer] + cg * VEC + k], g_b[k]);
-    if (IS_HEAD) atomicAdd(&g[m.off_kernel[m.L] + cg * VEC + k], g_ko[k] * dv[kDvSOut] * m.inv_sqrt_W);
+    atomicAdd(&colsum[cg * VEC + k], g_b[k]);
+    if (IS_HEAD) atomicAdd(&colsum[m.W + cg * VEC + k], g_ko[k]);
   }
   g_w = warp_sum(g_w);
   g_s = warp_sum(g_s);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { red[0][warp] = g_w; red[1][warp] = g_s; }
   __syncthreads();
+  for (int i = threadIdx.x; i < m.W; i += blockDim.x) {
+    atomicAdd(&g[m.off_bias[layer] + i], colsum[i]);
+    if (IS_HEAD) atomicAdd(&g[m.off_kernel[m.L] + i], colsum[m.W + i] * dv[kDvSOut] * m.inv_sqrt_W);
+  }
   if (threadIdx.x == 0) {
     float tw = 0.f, ts = 0.f;
     for (int i = 0; i < 8; ++i) { tw += red[0][i]; ts += red[1][i]; }
@@ -864,10 +872,10 @@ void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* par
     dim3 grid((B + kActVecRows - 1) / kActVecRows, n_net);
     if (is_head) {
       BNF_PROF("act_bwd", st);
-      act_bwd_vec_kernel<T, true><<<grid, 256, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+      act_bwd_vec_kernel<T, true><<<grid, 256, 2 * m.W * sizeof(float), st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
     } else {
       BNF_PROF("act_bwd", st);
-      act_bwd_vec_kernel<T, false><<<grid, 256, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+      act_bwd_vec_kernel<T, false><<<grid, 256, m.W * sizeof(float), st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
     }
     return;
   }

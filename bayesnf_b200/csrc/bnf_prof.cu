@@ -19,6 +19,7 @@ struct Rec { const char* name; cudaEvent_t a, b; };
 static std::vector<Rec> g_recs;
 
 void prof_count() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+void prof_add_launches(long long n) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
 
 void prof_begin(const char* name, cudaStream_t st, int* slot) {

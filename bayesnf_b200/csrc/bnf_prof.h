@@ -5,6 +5,7 @@
 namespace bnf {
 
 void prof_count();
+void prof_add_launches(long long n);
 bool prof_enabled();
 void prof_begin(const char* name, cudaStream_t st, int* slot);
 void prof_end(cudaStream_t st, int slot);

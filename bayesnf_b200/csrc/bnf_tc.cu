@@ -114,6 +114,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -171,24 +175,27 @@ template <int BLOCK_N> struct TcCfg {
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BLOCK_N * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
+  static constexpr int kStagingBytes = kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
 template <int BLOCK_N, bool MN_MAJOR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                const __grid_constant__ TcArgs a) {
   using Cfg = TcCfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = (uint64_t*)(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  float* sbias = (float*)(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][256]: s_l * bias of the tile's columns
+  float* sbias = (float*)(staging + Cfg::kStagingBytes + 256);  // [2][256]: s_l * bias of the tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -333,28 +340,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             hp[(j + jj) >> 1] = *reinterpret_cast<uint32_t*>(&hh);
             }
           }
-          if (row_ok) {
-            const size_t o = (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0;
-            uint4* hz = reinterpret_cast<uint4*>(a.out1 + o);
+          // registers -> 64B-swizzled smem tile (conflict-free 16B stores) -> TMA store:
+          // full 64-byte rows leave the SM as bulk writes instead of 32 scattered
+          // 16-byte stores per instruction; rows >= B are clipped by the tensor map.
+          uint8_t* stg = staging + (warp - 2) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hz[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-            if (a.out0) {
-              uint4* zz = reinterpret_cast<uint4*>(a.out0 + o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) zz[j] = make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int off = lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(stg + off) = make_uint4(hp[4 * k], hp[4 * k + 1], hp[4 * k + 2], hp[4 * k + 3]);
+            if (a.out0)
+              *reinterpret_cast<uint4*>(stg + 2048 + off) = make_uint4(zp[4 * k], zp[4 * k + 1], zp[4 * k + 2], zp[4 * k + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o1, stg, col0, m_t * 128 + q * 32, net);
+            if (a.out0) tma_store_3d(&map_o0, stg + 2048, col0, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else if (a.mode == TC_DGRAD_BF16) {
-          if (row_ok) {
-            uint32_t pk[16];
+          uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j]) * a.isf, __uint_as_float(v[j + 1]) * a.isf);
-              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
-            }
-            uint4* o4 = reinterpret_cast<uint4*>(a.out0 + (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0);
+          for (int j = 0; j < 32; j += 2) {
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j]) * a.isf, __uint_as_float(v[j + 1]) * a.isf);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          uint8_t* stg = staging + (warp - 2) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else if (a.mode == TC_DGRAD_F32 || a.mode == TC_PLAIN_F32) {
           if (row_ok) {
@@ -381,6 +405,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -430,8 +455,25 @@ static int make_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint64_t 
   return 0;
 }
 
+// bf16 output tensor [net][rows][cols]: 32x32 boxes, 64-byte swizzle (epilogue staging tiles)
+static int make_out_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint64_t rows, uint64_t nets) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return tc_fail(BNF_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {cols, rows, nets};
+  cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tc_fail(BNF_ERR_CUDA, "cuTensorMapEncodeTiled (output map) failed");
+  return 0;
+}
+
+struct OutMaps { CUtensorMap o0, o1; };
+
 template <int BLOCK_N, bool MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, int sm_count, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -443,17 +485,17 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs&
   int grid = (int)(total < sm_count ? total : sm_count);
   if (grid < 1) grid = 1;
   BNF_PROF(a.mode == TC_FWD ? "tc_gemm_fwd" : (a.mode == TC_WGRAD ? "tc_gemm_wgrad" : (a.mode == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
-  tc_gemm_kernel<BLOCK_N, MN><<<grid, kTcThreads, Cfg::kSmem, st>>>(ma, mb, a);
+  tc_gemm_kernel<BLOCK_N, MN><<<grid, kTcThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a);
   if (cudaGetLastError() != cudaSuccess) return tc_fail(BNF_ERR_CUDA, "tc_gemm_kernel launch failed");
   return 0;
 }
 
 template <bool MN>
-static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const TcArgs& a, int sm, cudaStream_t st) {
+static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm, cudaStream_t st) {
   switch (block_n) {
-    case 256: return launch_tc<256, MN>(ma, mb, a, sm, st);
-    case 128: return launch_tc<128, MN>(ma, mb, a, sm, st);
-    case 64: return launch_tc<64, MN>(ma, mb, a, sm, st);
+    case 256: return launch_tc<256, MN>(ma, mb, om, a, sm, st);
+    case 128: return launch_tc<128, MN>(ma, mb, om, a, sm, st);
+    case 64: return launch_tc<64, MN>(ma, mb, om, a, sm, st);
   }
   return tc_fail(BNF_ERR_INVALID, "bad BLOCK_N");
 }
@@ -484,7 +526,11 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.out0 = z; a.out1 = h; a.out_batch = (long long)B * m.W; a.ld_out = m.W;
-  return launch_tc_n<false>(bn, ma, mb, a, sm_count_of(p), st);
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if ((rc = make_out_map(&om.o1, h, m.W, B, n_net))) return rc;
+  if (z && (rc = make_out_map(&om.o0, z, m.W, B, n_net))) return rc;
+  return launch_tc_n<false>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
 
 int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16* out_bf, float* out_f32,
@@ -504,7 +550,10 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   a.m_valid = B; a.n_valid = Kp;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.out0 = out_bf; a.outf = out_f32; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
-  return launch_tc_n<false>(bn, ma, mb, a, sm_count_of(p), st);
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if (out_bf && (rc = make_out_map(&om.o0, out_bf, Kp, B, n_net))) return rc;
+  return launch_tc_n<false>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
 
 int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,
@@ -533,7 +582,9 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   a.m_valid = Kin; a.n_valid = m.W;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.outf = grad; a.out_batch = m.P; a.ld_out = m.W; a.grad_off = m.off_kernel[layer];
-  return launch_tc_n<true>(bn, ma, mb, a, sm, st);
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  return launch_tc_n<true>(bn, ma, mb, om, a, sm, st);
 }
 
 // debug / test entry: plain C[net][M][N] (f32) = A x B in either operand layout
@@ -548,15 +599,17 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
   a.mode = TC_PLAIN_F32; a.n_net = n_net; a.k_splits = 1; a.isf = 1.f;
   a.m_tiles = (M + 127) / 128; a.n_tiles = N / bn; a.k_blocks = (K + 63) / 64;
   a.m_valid = M; a.n_valid = N; a.outf = C; a.out_batch = (long long)M * N; a.ld_out = N;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
   if (!mn_major) {   // A [net][M][K], B [net][N][K]
     if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
     if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, bn))) return rc;
-    return launch_tc_n<false>(bn, ma, mb, a, sm_count, st);
+    return launch_tc_n<false>(bn, ma, mb, om, a, sm_count, st);
   }
   // A [net][K][M], B [net][K][N]
   if ((rc = make_map(&ma, A, M, K, n_net, M, (uint64_t)M * K, 64))) return rc;
   if ((rc = make_map(&mb, Bm, N, K, n_net, N, (uint64_t)N * K, 64))) return rc;
-  return launch_tc_n<true>(bn, ma, mb, a, sm_count, st);
+  return launch_tc_n<true>(bn, ma, mb, om, a, sm_count, st);
 }
 
 }  // namespace bnf
