@@ -287,15 +287,25 @@ int check_common(const bnf_plan* p, int prec, int n_net, int B) {
 template <typename T>
 int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
             const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
-            float* out_loc, float* ll, float* grad, cudaStream_t st) {
+            float* out_loc, float* ll, float* grad, cudaStream_t st, int32_t* tick_step = nullptr,
+            int32_t* tick_slot = nullptr) {
   const DevModel& m = p->m;
   const bool tc = prec == BNF_PREC_BF16;
-  launch_prep(m, params, w.derived, n_net, st);
-  launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
+  launch_prep(m, params, w.derived, n_net, tick_step, tick_slot, st);
+  // bf16 tensor-core mode: the feature encode is fused into the Dense_0 GEMM (the A tile is
+  // generated in shared memory); `feat` is only written as a by-product when the backward
+  // pass will need it (wgrad of Dense_0).  BNF_NO_FUSED_ENCODE=1 restores the two-kernel path.
+  static const bool fused_encode = getenv("BNF_NO_FUSED_ENCODE") == nullptr;
+  const bool fuse0 = tc && fused_encode;
+  if (!fuse0) launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
   if (tc) tc_cast_weights(m, params, w.wt, w.wn, n_net, st);
   for (int l = 0; l < m.L; ++l) {
     const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
-    if (tc) {
+    if (tc && l == 0 && fuse0) {
+      int rc = tc_fwd_layer0_fused(p, params, w.derived, x, idx, idx_stride, w.wt, grad ? (bf16*)w.feat : nullptr,
+                                   (bf16*)w.z[0], (bf16*)w.h[0], n_net, B, st);
+      if (rc) return fail(rc, "tc_fwd_layer0_fused failed: %s", tc_last_error());
+    } else if (tc) {
       int rc = tc_fwd_layer(p, l, params, w.derived, (const bf16*)a_in, w.wt, (bf16*)w.z[l], (bf16*)w.h[l], n_net, B, st);
       if (rc) return fail(rc, "tc_fwd_layer failed: %s", tc_last_error());
     } else {
@@ -346,10 +356,11 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
 
 int run_net_any(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
                 const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
-                float* out_loc, float* ll, float* grad, cudaStream_t st) {
+                float* out_loc, float* ll, float* grad, cudaStream_t st, int32_t* tick_step = nullptr,
+                int32_t* tick_slot = nullptr) {
   if (prec == BNF_PREC_FP32)
-    return run_net<float>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st);
-  return run_net<bf16>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st);
+    return run_net<float>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, tick_step, tick_slot);
+  return run_net<bf16>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, tick_step, tick_slot);
 }
 }  // namespace
 
@@ -406,11 +417,10 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   int32_t* slot = (int32_t*)(w.mm + 8);
   CU(cudaMemsetAsync(slot, 0, 4, st));
   auto one_step = [&](cudaStream_t s, const int32_t* idx_s) -> int {
-    launch_tick(step_count, slot, s);
     CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, s));
     CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, s));
     CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, s));
-    int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s);
+    int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, step_count, slot);
     if (r) return r;
     launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, s);
     launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss, slot, s);

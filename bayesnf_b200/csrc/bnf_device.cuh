@@ -110,6 +110,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- encode work items: (row, unit) ----------------------------------------
+struct UnitInfo { int kind, a, b; };  // kind 0:x 1:fourier(dim a, degree b) 2:seasonal(k=a) 3:inter(j=a)
+
+__device__ __forceinline__ int num_units(const DevModel& m) {
+  int u = m.D;
+  for (int i = 0; i < m.D; ++i) u += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+  return u + m.n_seasonal + m.n_inter;
+}
+__device__ __forceinline__ UnitInfo decode_unit(const DevModel& m, int u) {
+  if (u < m.D) return {0, u, 0};
+  u -= m.D;
+  for (int i = 0; i < m.D; ++i) {
+    int deg = m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+    if (u < deg) return {1, i, u};
+    u -= deg;
+  }
+  if (u < m.n_seasonal) return {2, u, 0};
+  return {3, u - m.n_seasonal, 0};
+}
+
+__device__ __forceinline__ const float* row_ptr(const float* x, const int32_t* idx, int64_t idx_stride,
+                                                int net, int b, int D) {
+  int64_t r = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
+  return x + r * D;
+}
+
+
 // ---- feature encode for one row (models.py:216-252) -------------------------
 // xr: the raw input row (D floats); dv: this network's derived scalars.
 // emit(col, value) is called once per feature column in [0, F).

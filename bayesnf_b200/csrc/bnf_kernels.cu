@@ -18,9 +18,14 @@ namespace bnf {
 // prep: per-network derived scalars
 // =============================================================================
 __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
-                            float* __restrict__ derived, int n_net) {
+                            float* __restrict__ derived, int n_net, int32_t* tick_step,
+                            int32_t* tick_slot) {
   int net = blockIdx.x;
   if (net >= n_net) return;
+  if (net == 0 && threadIdx.x == 0) {          // optional step tick (Adam count, loss row cursor)
+    if (tick_step) *tick_step += 1;
+    if (tick_slot) *tick_slot += 1;
+  }
   const float* p = params + (size_t)net * m.P;
   float* dv = derived + (size_t)net * kDerivedStride;
   int t = threadIdx.x;
@@ -46,31 +51,6 @@ __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* __r
 // work item = (row, unit); unit = one x column, one (dim,degree) sin/cos pair,
 // one seasonal sin/cos pair, or one interaction column.
 // =============================================================================
-struct UnitInfo { int kind, a, b; };  // kind 0:x 1:fourier(dim a, degree b) 2:seasonal(k=a) 3:inter(j=a)
-
-__device__ __forceinline__ int num_units(const DevModel& m) {
-  int u = m.D;
-  for (int i = 0; i < m.D; ++i) u += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
-  return u + m.n_seasonal + m.n_inter;
-}
-__device__ __forceinline__ UnitInfo decode_unit(const DevModel& m, int u) {
-  if (u < m.D) return {0, u, 0};
-  u -= m.D;
-  for (int i = 0; i < m.D; ++i) {
-    int deg = m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
-    if (u < deg) return {1, i, u};
-    u -= deg;
-  }
-  if (u < m.n_seasonal) return {2, u, 0};
-  return {3, u - m.n_seasonal, 0};
-}
-
-__device__ __forceinline__ const float* row_ptr(const float* x, const int32_t* idx, int64_t idx_stride,
-                                                int net, int b, int D) {
-  int64_t r = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
-  return x + r * D;
-}
-
 constexpr int kEncRows = 32;
 
 template <typename T>
@@ -341,6 +321,7 @@ void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int
 // head: o = s_out*(h.Ko/sqrt(W) + bo) ; likelihood ; r = dlogp/do  (models.py:269-273,157-191)
 // one warp per row.  Accumulates loglik and the scalar-head gradients.
 // =============================================================================
+constexpr int kHeadRows = 128;
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
@@ -355,14 +336,24 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
   const float* Ko = p + m.off_kernel[m.L];
   const float bo = p[m.off_bias[m.L]];
   const float s_out = dv[kDvSOut];
-  const int rows_per_block = 64;
+  const int rows_per_block = kHeadRows;
   float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
   for (int rr = warp; rr < rows_per_block; rr += 8) {
     const int b = blockIdx.x * rows_per_block + rr;
     if (b >= B) break;
     const T* hr = h + ((size_t)net * B + b) * m.W;
     float dot = 0.f;
-    for (int n = lane; n < m.W; n += 32) dot = fmaf(to_f<T>(hr[n]), Ko[n], dot);
+    constexpr int VEC = 16 / sizeof(T);
+    if (m.W % VEC == 0) {                       // 16-byte loads: one row of W=256 bf16 per warp pass
+      for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
+        alignas(16) T hv[VEC];
+        *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) dot = fmaf(to_f<T>(hv[k]), Ko[n + k], dot);
+      }
+    } else {
+      for (int n = lane; n < m.W; n += 32) dot = fmaf(to_f<T>(hr[n]), Ko[n], dot);
+    }
     dot = warp_sum(dot);
     if (lane == 0) {
       const float opre = dot * m.inv_sqrt_W + bo;
@@ -413,8 +404,23 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
       }
     }
   }
-  if (r_out && lane == 0) atomicAdd(&ll[net], a_ll);
-  if (r_out && grad && lane == 0) {
+  // lane 0 of each warp holds its partial sums: combine the 8 warps in shared memory so the
+  // block issues one atomic per quantity (the targets are 6 addresses per network)
+  __shared__ float hred[6][8];
+  if (lane == 0) {
+    hred[0][warp] = a_ll; hred[1][warp] = a_g0; hred[2][warp] = a_g1;
+    hred[3][warp] = a_g2; hred[4][warp] = a_gs; hred[5][warp] = a_gb;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a_ll = a_g0 = a_g1 = a_g2 = a_gs = a_gb = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      a_ll += hred[0][i]; a_g0 += hred[1][i]; a_g1 += hred[2][i];
+      a_g2 += hred[3][i]; a_gs += hred[4][i]; a_gb += hred[5][i];
+    }
+  }
+  if (r_out && threadIdx.x == 0) atomicAdd(&ll[net], a_ll);
+  if (r_out && grad && threadIdx.x == 0) {
     float* g = grad + (size_t)net * m.P;
     if (m.likelihood == BNF_NORMAL) {
       atomicAdd(&g[0], a_g0 * expf(p[0]));                // dsigma/dlns = exp(lns)
@@ -611,8 +617,15 @@ map_adam_kernel(int P, float* __restrict__ params, float* __restrict__ am, float
     params[o] = th + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + eps));
   }
   if (prior_weight != 0.f) {
+    __shared__ float pred[8];
     lp = warp_sum(lp);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&prior_out[net], lp);
+    if ((threadIdx.x & 31) == 0) pred[threadIdx.x >> 5] = lp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 8; ++i) tot += pred[i];
+      atomicAdd(&prior_out[net], tot);       // one atomic per block (8 addresses in total)
+    }
   }
 }
 
@@ -827,9 +840,10 @@ quantile_approx_kernel(const float* __restrict__ means, const float* __restrict_
 // =============================================================================
 // host-side launch wrappers
 // =============================================================================
-void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, cudaStream_t st) {
+void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, int32_t* tick_step,
+                 int32_t* tick_slot, cudaStream_t st) {
   BNF_PROF("prep", st);
-  prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net);
+  prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net, tick_step, tick_slot);
 }
 
 template <typename T>
@@ -855,7 +869,7 @@ template <typename T>
 void launch_head(const DevModel& m, const float* params, const float* derived, const T* h,
                  const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
                  float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st) {
-  dim3 grid((B + 63) / 64, n_net);
+  dim3 grid((B + kHeadRows - 1) / kHeadRows, n_net);
   BNF_PROF("head", st);
   head_kernel<T><<<grid, 256, 0, st>>>(m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
 }

@@ -7,7 +7,8 @@
 
 namespace bnf {
 
-void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, cudaStream_t st);
+void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, int32_t* tick_step,
+                 int32_t* tick_slot, cudaStream_t st);
 
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,

@@ -114,6 +114,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -166,26 +170,36 @@ struct TcArgs {
   const float* params; const float* derived; int P, off_bias, layer; float isf;
   bf16* out0; bf16* out1; float* outf;
   long long out_batch; int ld_out; int grad_off;
+  // A_MODE 2 (fused encode + Dense_0): raw inputs instead of a feature matrix
+  const float* x; const int32_t* idx; long long idx_stride; int x_tma; int write_feat;
 };
 
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
+constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-template <int BLOCK_N> struct TcCfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+constexpr int kXTileBytes = 128 * kMaxD * 4;
+// A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
+// encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major.
+template <int BLOCK_N, int A_MODE = 0> struct TcCfg {
+  static constexpr int kStages = A_MODE == 2 ? 2 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int kThreads = kTcThreads + (A_MODE == 2 ? 32 * kEncWarps : 0);
+  static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = BLOCK_N * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, bool MN_MAJOR>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BLOCK_N, int A_MODE>
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
-               const __grid_constant__ TcArgs a) {
-  using Cfg = TcCfg<BLOCK_N>;
+               const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
+  using Cfg = TcCfg<BLOCK_N, A_MODE>;
+  constexpr bool MN_MAJOR = A_MODE == 1;
+  constexpr bool ENCODE = A_MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -195,11 +209,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* xfull = tempty + 3;                      // A_MODE 2: raw input tile landed
   float* sbias = (float*)(staging + Cfg::kStagingBytes + 256);  // [2][256]: s_l * bias of the tile's columns
+  float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], ENCODE ? 1 + 32 * kEncWarps : 1);
+      mbar_init(&empty[s], 1);
+      if (ENCODE) mbar_init(&xfull[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,6 +227,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (ENCODE && warp >= 2 + kEpiWarps) {
+    // zero the A slots once: pad columns [F, Fp) are never written again
+    const int et = threadIdx.x - kTcThreads;
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      uint4* pz = reinterpret_cast<uint4*>(smem + s * Cfg::kStageBytes);
+      for (int i = et; i < Cfg::kABytes / 16; i += 32 * kEncWarps) pz[i] = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -233,11 +262,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          if (!MN_MAJOR) {
+          if (ENCODE) {
+            // B by TMA; the raw input rows of this tile as one bulk copy for the encoder warps
+            mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
+            tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
+            if (a.x_tma && m_t * 128 + 128 <= a.m_valid) {
+              const uint32_t xb = 128u * (uint32_t)dm.D * 4u;
+              mbar_arrive_expect_tx(&xfull[stage], xb);
+              bulk_load_1d(xtile + stage * 128 * kMaxD, a.x + (size_t)m_t * 128 * dm.D, xb, &xfull[stage]);
+            } else {
+              mbar_arrive(&xfull[stage]);
+            }
+          } else if (!MN_MAJOR) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
             tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
             tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
           } else {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
             // MN-major: boxes of [64 reduction rows][64 MN elements]
             for (int j = 0; j < 2; ++j)
               tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
@@ -290,7 +331,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue (warps 2..9) =====================
     // warp%4 selects the TMEM lane quarter it may read; the two warps of a quarter
     // take alternate 32-column chunks, so every SM sub-partition has two epilogue
@@ -406,6 +447,84 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (ENCODE) {
+    // ===================== feature encoder (warps 10..13, A_MODE 2) =====================
+    // work item = (unit, row): 128 rows of one unit per pass -> warp-uniform unit kind.
+    // Each item writes its one or two bf16 feature values straight into the 128B-swizzled
+    // K-major A tile the MMA reads; the finished tile is also TMA-stored as `feat` (wgrad
+    // of Dense_0 needs it) by one elected thread.
+    const int et = threadIdx.x - kTcThreads;
+    const int U = num_units(dm);
+    const float two_pi = 6.283185307179586f;
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int net = t / tiles_per_net;
+      int r0 = t % tiles_per_net;
+      const int n_t = r0 % a.n_tiles; r0 /= a.n_tiles;
+      const int m_t = r0 / a.k_splits;
+      const float* dv = a.derived + (size_t)net * kDerivedStride;
+      const bool x_in_smem = a.x_tma && m_t * 128 + 128 <= a.m_valid;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");
+        mbar_wait(&xfull[stage], phase);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        const float* xs = xtile + stage * 128 * kMaxD;
+        auto put = [&](int r, int c, float v) {
+          if ((c >> 6) != kb) return;
+          const int cc = c & 63;
+          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((((cc >> 3) ^ (r & 7)) & 7) << 4) + (cc & 7) * 2;
+          *reinterpret_cast<__nv_bfloat16*>(sa + off) = __float2bfloat16_rn(v);
+        };
+        for (int w = et; w < 128 * U; w += 32 * kEncWarps) {
+          const int u = w >> 7, r = w & 127;
+          const int row = m_t * 128 + r;
+          if (row >= a.m_valid) continue;
+          const UnitInfo ui = decode_unit(dm, u);
+          const float* xr = x_in_smem ? xs + r * dm.D
+                                      : a.x + (a.idx ? (size_t)a.idx[(size_t)net * a.idx_stride + row] : (size_t)row) * dm.D;
+          if (ui.kind == 0) {
+            put(r, dm.col_x + ui.a, (xr[ui.a] / dv[kDvDenom + ui.a]) * dv[kDvSX]);
+          } else if (ui.kind == 1) {
+            const int i = ui.a, d = ui.b, deg = dm.fourier_deg[i];
+            const int c0 = dm.fourier_col[i] + d, c1i = c0 + deg;
+            if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
+            const float sx = xr[i] / dv[kDvDenom + i];
+            float sn, cs;
+            sincosf((two_pi * (float)(1 << d)) * sx, &sn, &cs);
+            const float den = (float)(d + 1), sc = dv[kDvSFourier + i];
+            put(r, c0, (cs / den) * sc);
+            put(r, c1i, (sn / den) * sc);
+          } else if (ui.kind == 2) {
+            const int k = ui.a;
+            const int c0 = dm.col_seasonal + k, c1i = c0 + dm.n_seasonal;
+            if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
+            float sn, cs;
+            sincosf(dm.seasonal_w[k] * xr[0], &sn, &cs);
+            const float sc = dv[kDvSSeas], hk = dm.seasonal_h[k];
+            put(r, c0, (cs / hk) * sc);
+            put(r, c1i, (sn / hk) * sc);
+          } else {
+            const int j = ui.a;
+            const float sa_ = xr[dm.inter_a[j]] / dv[kDvDenom + dm.inter_a[j]];
+            const float sb_ = xr[dm.inter_b[j]] / dv[kDvDenom + dm.inter_b[j]];
+            put(r, dm.col_inter + j, (sa_ * sb_) * dv[kDvSInter]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (a.write_feat && n_t == 0) {
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");
+          if (et == 0) {
+            tma_store_3d(&map_a, sa, kb * 64, m_t * 128, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        mbar_arrive(&full[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -472,9 +591,11 @@ static int make_out_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint6
 
 struct OutMaps { CUtensorMap o0, o1; };
 
-template <int BLOCK_N, bool MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
+template <int BLOCK_N, int MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
+                     const DevModel* dm = nullptr) {
+  using Cfg = TcCfg<BLOCK_N, MN>;
+  static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
@@ -484,18 +605,19 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
   long long total = (long long)a.n_net * a.m_tiles * a.n_tiles * a.k_splits;
   int grid = (int)(total < sm_count ? total : sm_count);
   if (grid < 1) grid = 1;
-  BNF_PROF(a.mode == TC_FWD ? "tc_gemm_fwd" : (a.mode == TC_WGRAD ? "tc_gemm_wgrad" : (a.mode == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
-  tc_gemm_kernel<BLOCK_N, MN><<<grid, kTcThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a);
+  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : a.mode == TC_FWD ? "tc_gemm_fwd" : (a.mode == TC_WGRAD ? "tc_gemm_wgrad" : (a.mode == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  tc_gemm_kernel<BLOCK_N, MN><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a, dm ? *dm : dm_zero);
   if (cudaGetLastError() != cudaSuccess) return tc_fail(BNF_ERR_CUDA, "tc_gemm_kernel launch failed");
   return 0;
 }
 
-template <bool MN>
-static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm, cudaStream_t st) {
+template <int MN>
+static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm, cudaStream_t st,
+                       const DevModel* dm = nullptr) {
   switch (block_n) {
-    case 256: return launch_tc<256, MN>(ma, mb, om, a, sm, st);
-    case 128: return launch_tc<128, MN>(ma, mb, om, a, sm, st);
-    case 64: return launch_tc<64, MN>(ma, mb, om, a, sm, st);
+    case 256: return launch_tc<256, MN>(ma, mb, om, a, sm, st, dm);
+    case 128: return launch_tc<128, MN>(ma, mb, om, a, sm, st, dm);
+    case 64: return launch_tc<64, MN>(ma, mb, om, a, sm, st, dm);
   }
   return tc_fail(BNF_ERR_INVALID, "bad BLOCK_N");
 }
@@ -530,7 +652,38 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   memset(&om, 0, sizeof(om));
   if ((rc = make_out_map(&om.o1, h, m.W, B, n_net))) return rc;
   if (z && (rc = make_out_map(&om.o0, z, m.W, B, n_net))) return rc;
-  return launch_tc_n<false>(bn, ma, mb, om, a, sm_count_of(p), st);
+  return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
+}
+
+// Fused feature encode + Dense_0 (models.py:216-268 for the first layer): the A operand is
+// generated on-chip from (x, idx) by encoder warps; `feat` (may be NULL) receives the tile
+// as a by-product for the Dense_0 wgrad.
+int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
+                        const int32_t* idx, int64_t idx_stride, const bf16* wt, bf16* feat, bf16* z, bf16* h,
+                        int n_net, int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = m.Fp, bn = pick_block_n(m.W);
+  CUtensorMap ma, mb;
+  int rc;
+  memset(&ma, 0, sizeof(ma));
+  if (feat && (rc = make_map(&ma, feat, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128))) return rc;
+  if ((rc = make_map(&mb, wt, Kp, m.W, n_net, Kp, tc_weight_elems(m), bn))) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_FWD; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1; a.k_blocks = Kp / 64;
+  a.m_valid = B; a.n_valid = m.W;
+  a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[0]; a.layer = 0;
+  a.isf = m.inv_sqrt_F;
+  a.out0 = z; a.out1 = h; a.out_batch = (long long)B * m.W; a.ld_out = m.W;
+  a.x = x; a.idx = idx; a.idx_stride = idx_stride;
+  a.x_tma = (idx == nullptr && ((uintptr_t)x & 15) == 0) ? 1 : 0;
+  a.write_feat = feat ? 1 : 0;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if ((rc = make_out_map(&om.o1, h, m.W, B, n_net))) return rc;
+  if (z && (rc = make_out_map(&om.o0, z, m.W, B, n_net))) return rc;
+  return launch_tc_n<2>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
 int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16* out_bf, float* out_f32,
@@ -553,7 +706,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   OutMaps om;
   memset(&om, 0, sizeof(om));
   if (out_bf && (rc = make_out_map(&om.o0, out_bf, Kp, B, n_net))) return rc;
-  return launch_tc_n<false>(bn, ma, mb, om, a, sm_count_of(p), st);
+  return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
 
 int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,
@@ -584,7 +737,7 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   a.outf = grad; a.out_batch = m.P; a.ld_out = m.W; a.grad_off = m.off_kernel[layer];
   OutMaps om;
   memset(&om, 0, sizeof(om));
-  return launch_tc_n<true>(bn, ma, mb, om, a, sm, st);
+  return launch_tc_n<1>(bn, ma, mb, om, a, sm, st);
 }
 
 // debug / test entry: plain C[net][M][N] (f32) = A x B in either operand layout
@@ -604,12 +757,12 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
   if (!mn_major) {   // A [net][M][K], B [net][N][K]
     if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
     if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, bn))) return rc;
-    return launch_tc_n<false>(bn, ma, mb, om, a, sm_count, st);
+    return launch_tc_n<0>(bn, ma, mb, om, a, sm_count, st);
   }
   // A [net][K][M], B [net][K][N]
   if ((rc = make_map(&ma, A, M, K, n_net, M, (uint64_t)M * K, 64))) return rc;
   if ((rc = make_map(&mb, Bm, N, K, n_net, N, (uint64_t)N * K, 64))) return rc;
-  return launch_tc_n<true>(bn, ma, mb, om, a, sm_count, st);
+  return launch_tc_n<1>(bn, ma, mb, om, a, sm_count, st);
 }
 
 }  // namespace bnf

@@ -19,6 +19,10 @@ void tc_cast_weights(const DevModel& m, const float* params, __nv_bfloat16* wt, 
 int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived,
                  const __nv_bfloat16* a_in, const __nv_bfloat16* wt, __nv_bfloat16* z,
                  __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
+int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
+                        const int32_t* idx, int64_t idx_stride, const __nv_bfloat16* wt,
+                        __nv_bfloat16* feat, __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B,
+                        cudaStream_t st);
 // out_bf (hidden layers) or out_f32 (layer 0 -> dfeat [n_net,B,Fp]) receives isf * dU @ K^T
 int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_bfloat16* dU,
              __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st);
