@@ -63,6 +63,8 @@ SIGNATURES = {
     'bnf_mixture_quantiles': (C.c_int, [_P, _P, _I32, _I32, C.POINTER(C.c_double), _I32, _I32,
                                         _P, _P, _SZ, _P]),
     'bnf_quantile_workspace_bytes': (_SZ, [_I32, _I32]),
+    'bnf_nb_mixture_quantiles': (C.c_int, [_P, _P, _P, _I32, _I32, C.POINTER(C.c_double), _I32, _P, _P,
+                                           _P, _SZ, _P]),
     'bnf_debug_gemm': (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     'bnf_debug_launch_count': (C.c_uint64, []),
     'bnf_debug_profile': (C.c_int, [_I32]),

@@ -292,11 +292,12 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
   const DevModel& m = p->m;
   const bool tc = prec == BNF_PREC_BF16;
   launch_prep(m, params, w.derived, n_net, tick_step, tick_slot, st);
-  // bf16 tensor-core mode: the feature encode is fused into the Dense_0 GEMM (the A tile is
-  // generated in shared memory); `feat` is only written as a by-product when the backward
-  // pass will need it (wgrad of Dense_0).  BNF_NO_FUSED_ENCODE=1 restores the two-kernel path.
-  static const bool fused_encode = getenv("BNF_NO_FUSED_ENCODE") == nullptr;
-  const bool fuse0 = tc && fused_encode;
+  // bf16 tensor-core mode, BNF_FUSED_ENCODE=1: the feature encode is fused into the Dense_0
+  // GEMM (encoder warps generate the A tile in shared memory; `feat` is written as a
+  // by-product only when the backward pass needs it).  Correct and tested, but with 4 encoder
+  // warps per SM it is latency-bound (profiles/README.md), so the two-kernel path is the default.
+  const char* fe = getenv("BNF_FUSED_ENCODE");
+  const bool fuse0 = tc && fe && fe[0] == '1';
   if (!fuse0) launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
   if (tc) tc_cast_weights(m, params, w.wt, w.wn, n_net, st);
   for (int l = 0; l < m.L; ++l) {
@@ -331,14 +332,22 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
       launch_wgrad_simt_t<T>(m, l, a_in, Kin, lda, (const T*)w.dU[cur], grad, n_net, B, st);
     }
     if (l > 0) {
-      if (tc) {
-        int rc = tc_dgrad(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], nullptr, n_net, B, st);
-        if (rc) return fail(rc, "tc_dgrad failed: %s", tc_last_error());
+      const char* nf = getenv("BNF_NO_FUSED_ACT_BWD");
+      if (tc && !(nf && nf[0] == '1')) {
+        // dgrad + activation backward of layer l-1 in one kernel (epilogue fusion)
+        int rc = tc_dgrad(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], nullptr, n_net, B, st,
+                          (const bf16*)w.z[l - 1], params, w.derived, grad);
+        if (rc) return fail(rc, "tc_dgrad (fused) failed: %s", tc_last_error());
       } else {
-        launch_dgrad_simt_t<T, T>(m, l, params, (const T*)w.dU[cur], (T*)w.dU[cur ^ 1], m.W, m.W, n_net, B, st);
+        if (tc) {
+          int rc = tc_dgrad(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], nullptr, n_net, B, st);
+          if (rc) return fail(rc, "tc_dgrad failed: %s", tc_last_error());
+        } else {
+          launch_dgrad_simt_t<T, T>(m, l, params, (const T*)w.dU[cur], (T*)w.dU[cur ^ 1], m.W, m.W, n_net, B, st);
+        }
+        launch_act_bwd<T>(m, l - 1, false, params, w.derived, (const T*)w.z[l - 1], (const T*)nullptr,
+                          nullptr, (T*)w.dU[cur ^ 1], B, grad, n_net, st);
       }
-      launch_act_bwd<T>(m, l - 1, false, params, w.derived, (const T*)w.z[l - 1], (const T*)nullptr,
-                        nullptr, (T*)w.dU[cur ^ 1], B, grad, n_net, st);
       cur ^= 1;
     } else {
       if (tc) {
@@ -347,7 +356,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
       } else {
         launch_dgrad_simt_t<T, float>(m, 0, params, (const T*)w.dU[cur], w.dfeat, m.F, m.Fp, n_net, B, st);
       }
-      launch_encode_bwd(m, params, w.derived, x, idx, idx_stride, B, w.dfeat, grad, n_net, st);
+      launch_encode_bwd(m, params, w.derived, x, idx, idx_stride, B, w.dfeat, grad, n_net, tc, st);
     }
   }
   CUK();
@@ -584,5 +593,18 @@ extern "C" int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, fl
   CU(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
   int rc = tc_debug_gemm(mn_major, (const bf16*)a, (const bf16*)b, c, n_net, m, n, k, sm, (cudaStream_t)stream);
   if (rc) return fail(rc, "tc_debug_gemm: %s", tc_last_error());
+  return BNF_OK;
+}
+
+extern "C" int bnf_nb_mixture_quantiles(const float* loc, const float* shape_raw, const float* pi_logit,
+                                        int32_t M, int32_t N, const double* q, int32_t nq, float* out_means,
+                                        float* out_q, void* ws, size_t ws_bytes, void* stream) {
+  if (!loc || !shape_raw || !q || !out_means || !out_q || M < 1 || N < 1 || nq < 1)
+    return fail(BNF_ERR_INVALID, "bad argument");
+  if (!ws || ws_bytes < 64) return fail(BNF_ERR_WORKSPACE, "workspace too small");
+  for (int i = 0; i < nq; ++i)
+    if (!(q[i] > 0.0 && q[i] < 1.0)) return fail(BNF_ERR_INVALID, "quantile must be in (0,1)");
+  launch_nb_quantiles(loc, shape_raw, pi_logit, M, N, q, nq, out_means, out_q, (float*)ws, (cudaStream_t)stream);
+  CUK();
   return BNF_OK;
 }

@@ -75,6 +75,16 @@ __device__ __forceinline__ float act_grad_fast(float z, float w, float* diff) {
   const float dt = fmaf(-t, t, 1.f);
   return fmaf(w, delu - dt, dt);
 }
+// sin/cos for the bf16 path with arguments up to ~1e5 rad (seasonal features): one exact
+// f32 range reduction to [-pi, pi] (two-constant Cody-Waite) and the MUFU approximations.
+// Absolute error ~1e-6 + |x|*6e-8 (the latter is the rounding of the f32 argument itself,
+// which the reference shares), far below the bf16 rounding of the stored feature.
+__device__ __forceinline__ void sincos_reduced(float x, float* sn, float* cs) {
+  const float k = rintf(x * 0.15915494309189535f);          // x / 2pi
+  float r = fmaf(-k, 6.28318548202514648f, x);              // hi part of 2pi (f32)
+  r = fmaf(-k, -1.74845553e-7f, r);                         // lo part: 2pi - f32(2pi)
+  __sincosf(r, sn, cs);
+}
 template <bool FAST> __device__ __forceinline__ float act_sel(float z, float w) {
   return FAST ? act_fast(z, w) : act_f(z, w);
 }

@@ -81,14 +81,14 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
       float sx = xr[i] / dv[kDvDenom + i];
       float c = two_pi * (float)(1 << d);
       float sn, cs;
-      sincosf(c * sx, &sn, &cs);
+      if (FastMath<T>::value) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
       const float den = (float)(d + 1), s = dv[kDvSFourier + i];
       trow[m.fourier_col[i] + d] = (cs / den) * s;
       trow[m.fourier_col[i] + deg + d] = (sn / den) * s;
     } else if (ui.kind == 2) {
       const int k = ui.a;
       float sn, cs;
-      sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
+      if (FastMath<T>::value) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
       const float s = dv[kDvSSeas], hk = m.seasonal_h[k];
       trow[m.col_seasonal + k] = (cs / hk) * s;
       trow[m.col_seasonal + m.n_seasonal + k] = (sn / hk) * s;
@@ -110,6 +110,7 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
 
 // encode backward: dfeat [n_net,B,Fp] f32 -> grads of
 // feature_inv_sp_scale{g} and log_scale_adjustment, accumulated into grad[n_net,P].
+template <bool FAST>
 __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                                   const float* __restrict__ derived, const float* __restrict__ x,
                                   const int32_t* __restrict__ idx, int64_t idx_stride, int B,
@@ -150,7 +151,7 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
         float sx = xr[i] / dv[kDvDenom + i];
         float c = two_pi * (float)(1 << d);
         float sn, cs;
-        sincosf(c * sx, &sn, &cs);
+        if (FAST) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
         const float den = (float)(d + 1);
         float Gc = g[m.fourier_col[i] + d], Gs = g[m.fourier_col[i] + deg + d];
         gs = Gc * (cs / den) + Gs * (sn / den);
@@ -159,7 +160,7 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
       } else if (ui.kind == 2) {
         const int k = ui.a;
         float sn, cs;
-        sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
+        if (FAST) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
         float hk = m.seasonal_h[k];
         gs = g[m.col_seasonal + k] * (cs / hk) + g[m.col_seasonal + m.n_seasonal + k] * (sn / hk);
       } else {
@@ -321,7 +322,7 @@ void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int
 // head: o = s_out*(h.Ko/sqrt(W) + bo) ; likelihood ; r = dlogp/do  (models.py:269-273,157-191)
 // one warp per row.  Accumulates loglik and the scalar-head gradients.
 // =============================================================================
-constexpr int kHeadRows = 128;
+constexpr int kHeadRows = 256;
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
@@ -336,27 +337,43 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
   const float* Ko = p + m.off_kernel[m.L];
   const float bo = p[m.off_bias[m.L]];
   const float s_out = dv[kDvSOut];
-  const int rows_per_block = kHeadRows;
   float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
-  for (int rr = warp; rr < rows_per_block; rr += 8) {
-    const int b = blockIdx.x * rows_per_block + rr;
-    if (b >= B) break;
-    const T* hr = h + ((size_t)net * B + b) * m.W;
-    float dot = 0.f;
+  // Each warp takes 32 rows at a time: the row dot products are computed cooperatively
+  // (coalesced 16-byte loads), lane j keeps row j's result, then all 32 lanes run the
+  // per-row likelihood math in parallel and write r / o_pre coalesced.
+  const int blk0 = blockIdx.x * kHeadRows;
+  for (int base = blk0 + warp * 32; base < min(B, blk0 + kHeadRows); base += 8 * 32) {
+    float mydot = 0.f;
     constexpr int VEC = 16 / sizeof(T);
-    if (m.W % VEC == 0) {                       // 16-byte loads: one row of W=256 bf16 per warp pass
-      for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
-        alignas(16) T hv[VEC];
-        *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+    for (int j0 = 0; j0 < 32; j0 += 4) {       // 4 rows in flight: independent loads, then reduce
+      if (base + j0 >= B) break;                // warp-uniform
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) dot = fmaf(to_f<T>(hv[k]), Ko[n + k], dot);
+      for (int u = 0; u < 4; ++u) {
+        const int b = base + j0 + u;
+        if (b < B) {
+          const T* hr = h + ((size_t)net * B + b) * m.W;
+          if (m.W % VEC == 0) {
+            for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
+              alignas(16) T hv[VEC];
+              *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), Ko[n + k], dot[u]);
+            }
+          } else {
+            for (int n = lane; n < m.W; n += 32) dot[u] = fmaf(to_f<T>(hr[n]), Ko[n], dot[u]);
+          }
+        }
       }
-    } else {
-      for (int n = lane; n < m.W; n += 32) dot = fmaf(to_f<T>(hr[n]), Ko[n], dot);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d = warp_sum(dot[u]);
+        if (lane == j0 + u) mydot = d;
+      }
     }
-    dot = warp_sum(dot);
-    if (lane == 0) {
-      const float opre = dot * m.inv_sqrt_W + bo;
+    const int b = base + lane;
+    if (b < B) {
+      const float opre = mydot * m.inv_sqrt_W + bo;
       const float o = s_out * opre;
       if (out_loc) out_loc[(size_t)net * B + b] = o;
       if (r_out) {
@@ -404,6 +421,8 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
       }
     }
   }
+  a_ll = warp_sum(a_ll); a_g0 = warp_sum(a_g0); a_g1 = warp_sum(a_g1);
+  a_g2 = warp_sum(a_g2); a_gs = warp_sum(a_gs); a_gb = warp_sum(a_gb);
   // lane 0 of each warp holds its partial sums: combine the 8 warps in shared memory so the
   // block issues one atomic per quantity (the targets are 6 addresses per network)
   __shared__ float hred[6][8];
@@ -838,6 +857,117 @@ quantile_approx_kernel(const float* __restrict__ means, const float* __restrict_
 }
 
 // =============================================================================
+// NB / ZINB predictive mean and mixture quantiles (inference.py:271-333)
+// CDF of NegativeBinomial(total_count=r, logits=l) at integer k: I_{sigmoid(-l)}(r, 1+k)
+// (TFP NegativeBinomial._cdf), evaluated in double (continued fraction, modified Lentz).
+// =============================================================================
+__device__ double betacf_d(double a, double b, double x) {
+  const double FPMIN = 1e-300, EPS = 1e-12;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < FPMIN) d = FPMIN;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 2000; ++m) {
+    const double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+// I_x(a, b) with x given as (log x, log(1-x)) to stay accurate when x -> 0 or 1
+__device__ double betainc_d(double a, double b, double logx, double log1mx) {
+  const double x = exp(logx), y = exp(log1mx);
+  if (x <= 0.0) return 0.0;
+  if (y <= 0.0) return 1.0;
+  const double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * logx + b * log1mx);
+  if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf_d(a, b, x) / a;
+  return 1.0 - bt * betacf_d(b, a, y) / b;
+}
+__device__ __forceinline__ double log_sigmoid_d(double v) { return v < 0 ? v - log1p(exp(v)) : -log1p(exp(-v)); }
+
+struct NbComp { double r, logits, pi; };
+__device__ __forceinline__ NbComp nb_component(float loc, float shape_raw, const float* pi_logit, int c) {
+  // models.py:166-191 literally: mean=softplus(loc), shape=softplus(p1), r=1/shape,
+  // logits=-log(shape)-log(mean), pi=sigmoid(p2)
+  const double a = log1p(exp(-fabs((double)shape_raw))) + fmax((double)shape_raw, 0.0);
+  const double mean_net = log1p(exp(-fabs((double)loc))) + fmax((double)loc, 0.0);
+  NbComp o;
+  o.r = 1.0 / a;
+  o.logits = -log(a) - log(mean_net);
+  o.pi = pi_logit ? 1.0 / (1.0 + exp(-(double)pi_logit[c])) : 0.0;
+  return o;
+}
+
+// means[c,n] = distribution mean; ws[0] / ws[1] = global max of mean / stddev (ordered-int floats)
+__global__ void __launch_bounds__(256)
+nb_stats_kernel(const float* __restrict__ loc, const float* __restrict__ shape_raw,
+                const float* __restrict__ pi_logit, int M, int N, float* __restrict__ means,
+                float* __restrict__ ws) {
+  float mx_mean = -FLT_MAX, mx_sd = -FLT_MAX;
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i / N);
+    const NbComp k = nb_component(loc[i], shape_raw[c], pi_logit, c);
+    const double nb_mean = k.r * exp(k.logits);
+    const double nb_var = nb_mean / exp(log_sigmoid_d(-k.logits));
+    const double mean = (1.0 - k.pi) * nb_mean;
+    const double var = (1.0 - k.pi) * (nb_var + nb_mean * nb_mean) - mean * mean;
+    means[i] = (float)mean;
+    mx_mean = fmaxf(mx_mean, (float)mean);
+    mx_sd = fmaxf(mx_sd, (float)sqrt(fmax(var, 0.0)));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx_mean = fmaxf(mx_mean, __shfl_xor_sync(0xffffffffu, mx_mean, o));
+    mx_sd = fmaxf(mx_sd, __shfl_xor_sync(0xffffffffu, mx_sd, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    auto enc = [](float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; };
+    atomicMax((int*)&ws[0], enc(mx_mean));
+    atomicMax((int*)&ws[1], enc(mx_sd));
+  }
+}
+__global__ void nb_stats_init_kernel(float* ws) { ((int*)ws)[0] = (int)0x80000000; ((int*)ws)[1] = (int)0x80000000; }
+
+__device__ double nb_mix_cdf(const float* __restrict__ loc, const float* __restrict__ shape_raw,
+                             const float* __restrict__ pi_logit, int M, int N, int n, double kk) {
+  double acc = 0.0;
+  for (int c = 0; c < M; ++c) {
+    const NbComp k = nb_component(loc[(size_t)c * N + n], shape_raw[c], pi_logit, c);
+    const double cdf = betainc_d(k.r, 1.0 + kk, log_sigmoid_d(-k.logits), log_sigmoid_d(k.logits));
+    acc += k.pi + (1.0 - k.pi) * cdf;
+  }
+  return acc / (double)M;
+}
+
+// exact discrete quantile min{k>=0 : meanCDF(k) >= q} on [0, ceil(high)], high as inference.py:319-324
+__global__ void __launch_bounds__(128)
+nb_quantile_kernel(const float* __restrict__ loc, const float* __restrict__ shape_raw,
+                   const float* __restrict__ pi_logit, int M, int N, const float* __restrict__ ws,
+                   float q, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float high = dec_ordered(ws[0]) + 1.1f * rsqrtf(1.f - q) * dec_ordered(ws[1]);
+  double lo = -1.0, hi = ceil((double)high);
+  if (!(hi >= 0.0)) hi = 0.0;
+  while (hi - lo > 1.0) {
+    const double mid = floor(0.5 * (lo + hi));
+    if (nb_mix_cdf(loc, shape_raw, pi_logit, M, N, n, mid) >= (double)q) hi = mid; else lo = mid;
+  }
+  out[n] = (float)hi;
+}
+
+// =============================================================================
 // host-side launch wrappers
 // =============================================================================
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, int32_t* tick_step,
@@ -859,10 +989,13 @@ template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const 
 
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
-                       int n_net, cudaStream_t st) {
+                       int n_net, bool fast_trig, cudaStream_t st) {
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
   BNF_PROF("encode_bwd", st);
-  encode_bwd_kernel<<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+  if (fast_trig)
+    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+  else
+    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
 }
 
 template <typename T>
@@ -1002,6 +1135,24 @@ void launch_quantiles(const float* means, const float* scales, int M, int N, con
       BNF_PROF("quantile_root", st);
       quantile_root_kernel<<<(N + 127) / 128, 128, 0, st>>>(means, scales, M, N, mm, (float)q[i], out + (size_t)i * N);
     }
+  }
+}
+
+void launch_nb_quantiles(const float* loc, const float* shape_raw, const float* pi_logit, int M, int N,
+                         const double* q, int nq, float* means, float* out, float* ws, cudaStream_t st) {
+  {
+    BNF_PROF("nb_stats_init", st);
+    nb_stats_init_kernel<<<1, 1, 0, st>>>(ws);
+  }
+  {
+    size_t total = (size_t)M * N;
+    int blocks = (int)((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+    BNF_PROF("nb_stats", st);
+    nb_stats_kernel<<<blocks, 256, 0, st>>>(loc, shape_raw, pi_logit, M, N, means, ws);
+  }
+  for (int i = 0; i < nq; ++i) {
+    BNF_PROF("nb_quantile", st);
+    nb_quantile_kernel<<<(N + 127) / 128, 128, 0, st>>>(loc, shape_raw, pi_logit, M, N, ws, (float)q[i], out + (size_t)i * N);
   }
 }
 

@@ -15,7 +15,7 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st);
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
-                       int n_net, cudaStream_t st);
+                       int n_net, bool fast_trig, cudaStream_t st);
 template <typename T>
 void launch_head(const DevModel& m, const float* params, const float* derived, const T* h,
                  const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
@@ -52,5 +52,8 @@ void launch_init_params(const DevModel& m, float lns_init, uint64_t seed, int64_
                         int n_net, float* params, cudaStream_t st);
 void launch_quantiles(const float* means, const float* scales, int M, int N, const double* q, int nq,
                       bool approximate, const float* ndtri_q, float* out, float* mm, cudaStream_t st);
+
+void launch_nb_quantiles(const float* loc, const float* shape_raw, const float* pi_logit, int M, int N,
+                         const double* q, int nq, float* means, float* out, float* ws, cudaStream_t st);
 
 }  // namespace bnf

@@ -160,7 +160,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // -----------------------------------------------------------------------------
 // the GEMM kernel
 // -----------------------------------------------------------------------------
-enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4 };
+enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4, TC_DGRAD_ACT = 5 };
 
 struct TcArgs {
   int mode, n_net;
@@ -172,6 +172,8 @@ struct TcArgs {
   long long out_batch; int ld_out; int grad_off;
   // A_MODE 2 (fused encode + Dense_0): raw inputs instead of a feature matrix
   const float* x; const int32_t* idx; long long idx_stride; int x_tma; int write_feat;
+  // TC_DGRAD_ACT (dgrad fused with the activation backward of the previous layer)
+  const bf16* zin; float* gradp; int off_bias_prev, off_ls_prev, off_actw, layer_prev;
 };
 
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
@@ -356,10 +358,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           sb[epi_tid] = s_l * a.params[(size_t)net * a.P + a.off_bias + n_t * BLOCK_N + epi_tid];
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const int row = m_t * 128 + q * 32 + lane;
       const bool row_ok = row < a.m_valid;
+      // TC_DGRAD_ACT: this row's z of the previous layer, register-prefetched one chunk ahead
+      float s_prev = 0.f, g_w = 0.f, g_s = 0.f;
+      uint4 zq[4];
+      const bf16* zrow = nullptr;
+      if (a.mode == TC_DGRAD_ACT) {
+        w_act = dv[kDvActW];
+        s_prev = dv[kDvSLayer + a.layer_prev];
+        zrow = a.zin + (size_t)net * a.out_batch + (size_t)min(row, a.m_valid - 1) * a.ld_out + n_t * BLOCK_N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) zq[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32) + k);
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = half * 32; c < BLOCK_N; c += 64) {
         uint32_t v[32];
@@ -401,6 +414,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (a.out0) tma_store_3d(&map_o0, stg + 2048, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+        } else if (a.mode == TC_DGRAD_ACT) {
+          // dh = acc/sqrt(fan_in); dz = dh*act'(z); dU = s*dz; plus the reductions that the
+          // separate act_bwd kernel used to do (bias column sums, activation-mix and
+          // layer-scale scalars).  models.py:255-268 backward.
+          uint32_t zw[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { zw[4 * k] = zq[k].x; zw[4 * k + 1] = zq[k].y; zw[4 * k + 2] = zq[k].z; zw[4 * k + 3] = zq[k].w; }
+          if (c + 64 < BLOCK_N) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) zq[k] = __ldg(reinterpret_cast<const uint4*>(zrow + c + 64) + k);
+          }
+          float du[32];
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&zw[j >> 1]);
+            const float z0 = __low2float(z2), z1 = __high2float(z2);
+            float d0, d1;
+            const float dh0 = row_ok ? __uint_as_float(v[j]) * a.isf : 0.f;
+            const float dh1 = row_ok ? __uint_as_float(v[j + 1]) * a.isf : 0.f;
+            const float da0 = act_grad_fast(z0, w_act, &d0), da1 = act_grad_fast(z1, w_act, &d1);
+            const float dz0 = dh0 * da0, dz1 = dh1 * da1;
+            g_w = fmaf(dh0, d0, fmaf(dh1, d1, g_w));
+            g_s = fmaf(dz0, z0, fmaf(dz1, z1, g_s));
+            du[j] = dz0 * s_prev;
+            du[j + 1] = dz1 * s_prev;
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(du[j], du[j + 1]);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          uint8_t* stg = staging + (warp - 2) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          // bias gradient: column sums over this warp's 32 rows by a transpose-reduce
+          // (31 shuffles); lane L ends up with column L, one coalesced atomic per chunk.
+#pragma unroll
+          for (int hh = 16; hh >= 1; hh >>= 1) {
+            const bool up = (lane & hh) != 0;
+#pragma unroll
+            for (int i = 0; i < hh; ++i) {
+              const float send = up ? du[i] : du[i + hh];
+              const float keep = up ? du[i + hh] : du[i];
+              du[i] = keep + __shfl_xor_sync(0xffffffffu, send, hh);
+            }
+          }
+          atomicAdd(a.gradp + (size_t)net * a.P + a.off_bias_prev + col0 + lane, du[0]);
         } else if (a.mode == TC_DGRAD_BF16) {
           uint32_t pk[16];
 #pragma unroll
@@ -445,6 +513,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (a.mode == TC_DGRAD_ACT) {
+        g_w = warp_sum(g_w);
+        g_s = warp_sum(g_s);
+        if (lane == 0) {
+          float* g = a.gradp + (size_t)net * a.P;
+          atomicAdd(g + a.off_actw, g_w * w_act * (1.f - w_act));
+          atomicAdd(g + a.off_ls_prev, (g_s / s_prev) * sigmoid_f(a.params[(size_t)net * a.P + a.off_ls_prev]));
+        }
+      }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (ENCODE) {
@@ -492,7 +569,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
             const float sx = xr[i] / dv[kDvDenom + i];
             float sn, cs;
-            sincosf((two_pi * (float)(1 << d)) * sx, &sn, &cs);
+            sincos_reduced((two_pi * (float)(1 << d)) * sx, &sn, &cs);   // MUFU: bf16 rounding dominates
             const float den = (float)(d + 1), sc = dv[kDvSFourier + i];
             put(r, c0, (cs / den) * sc);
             put(r, c1i, (sn / den) * sc);
@@ -501,7 +578,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int c0 = dm.col_seasonal + k, c1i = c0 + dm.n_seasonal;
             if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
             float sn, cs;
-            sincosf(dm.seasonal_w[k] * xr[0], &sn, &cs);
+            sincos_reduced(dm.seasonal_w[k] * xr[0], &sn, &cs);
             const float sc = dv[kDvSSeas], hk = dm.seasonal_h[k];
             put(r, c0, (cs / hk) * sc);
             put(r, c1i, (sn / hk) * sc);
@@ -687,7 +764,8 @@ int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* der
 }
 
 int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16* out_bf, float* out_f32,
-             int n_net, int B, cudaStream_t st) {
+             int n_net, int B, cudaStream_t st, const bf16* z_prev, const float* params,
+             const float* derived, float* grad) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer);          // output columns (in-features, padded)
   const int bn = pick_block_n(Kp);
@@ -698,7 +776,12 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
-  a.mode = out_bf ? TC_DGRAD_BF16 : TC_DGRAD_F32; a.n_net = n_net;
+  a.mode = out_bf ? (z_prev ? TC_DGRAD_ACT : TC_DGRAD_BF16) : TC_DGRAD_F32; a.n_net = n_net;
+  if (z_prev) {
+    a.zin = z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
+    a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
+    a.off_ls_prev = m.off_layer_scale[layer - 1]; a.off_actw = m.off_actw;
+  }
   a.m_tiles = (B + 127) / 128; a.n_tiles = Kp / bn; a.k_splits = 1; a.k_blocks = m.W / 64;
   a.m_valid = B; a.n_valid = Kp;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;

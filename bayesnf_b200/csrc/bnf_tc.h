@@ -24,8 +24,12 @@ int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* der
                         __nv_bfloat16* feat, __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B,
                         cudaStream_t st);
 // out_bf (hidden layers) or out_f32 (layer 0 -> dfeat [n_net,B,Fp]) receives isf * dU @ K^T
+// z_prev != NULL (hidden layers): fuse the activation backward of layer-1 into the epilogue
+// (out_bf receives dU of layer-1; bias / activation-mix / layer-scale grads go to `grad`).
 int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_bfloat16* dU,
-             __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st);
+             __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st,
+             const __nv_bfloat16* z_prev = nullptr, const float* params = nullptr,
+             const float* derived = nullptr, float* grad = nullptr);
 int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
              float* grad, int n_net, int B, cudaStream_t st);
 

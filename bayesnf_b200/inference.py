@@ -196,6 +196,21 @@ def mixture_quantiles(means: torch.Tensor, scales: torch.Tensor, quantiles: Sequ
   return out
 
 
+def nb_mixture_quantiles(loc: torch.Tensor, shape_raw: torch.Tensor, pi_logit: torch.Tensor | None,
+                         quantiles: Sequence[float]) -> tuple[torch.Tensor, torch.Tensor]:
+  """loc [M,N], shape_raw [M], pi_logit [M]|None -> (means [M,N], quantiles [len(q),N])."""
+  M, N = loc.shape
+  q = (C.c_double * len(quantiles))(*[float(v) for v in quantiles])
+  means = torch.empty((M, N), dtype=torch.float32, device=loc.device)
+  out = torch.empty((len(quantiles), N), dtype=torch.float32, device=loc.device)
+  ws = torch.empty(256, dtype=torch.uint8, device=loc.device)
+  _lib.check(_lib.lib.bnf_nb_mixture_quantiles(
+      _ptr(loc.contiguous()), _ptr(shape_raw.contiguous()),
+      _ptr(pi_logit.contiguous() if pi_logit is not None else None), M, N, q, len(quantiles),
+      _ptr(means), _ptr(out), _ptr(ws), ws.numel(), _stream()))
+  return means, out
+
+
 def _to_device_data(features, target=None):
   dev = _device()
   # jnp.array(...) with x64 disabled: float64 pandas values -> float32 (inference.py:553-554)
@@ -427,8 +442,14 @@ def predict_bnf(
                           list(quantiles), approximate_quantiles)
     means = loc_all.reshape((world,) + tuple(lead[1:]) + (loc.shape[1],)).cpu().numpy()
     return means, [q[i].cpu().numpy() for i in range(len(quantiles))]
-  # NB / ZINB predictive quantiles (inference.py:271-333: betainc CDF root find) are
-  # SURVEY.md section 8f item 1 ("next"), not built yet.
-  raise NotImplementedError(
-      'predict_bnf for NB/ZINB observation models is not implemented yet; training '
-      '(fit_map / fit_vi) and Engine.forward support them.')
+  # NB / ZINB (inference.py:271-333): distribution means + mixture quantiles from the gathered
+  # network outputs and the per-member shape / zero-inflation parameters.
+  loc_all = parallel.all_gather_leading(loc)
+  shape_all = parallel.all_gather_leading(nets[:, 1].contiguous())
+  pi_all = parallel.all_gather_leading(nets[:, 2].contiguous())
+  world, n_pts = loc_all.shape[0], loc.shape[1]
+  means_t, q = nb_mixture_quantiles(
+      loc_all.reshape(-1, n_pts), shape_all.reshape(-1),
+      pi_all.reshape(-1) if dist == models.LikelihoodDist.ZINB else None, list(quantiles))
+  means = means_t.reshape((world,) + tuple(lead[1:]) + (n_pts,)).cpu().numpy()
+  return means, [q[i].cpu().numpy() for i in range(len(quantiles))]

@@ -41,6 +41,10 @@ WORKLOADS = {
     'wind_map_e16': dict(width=1024, depth=6, members_per_gpu=16, sites=128, times=512, batch=65536,
                          periods=[7, 365.25 / 12, 365.25], harmonics=[3, 10, 10], objective='map'),
     # BASELINE.json configs[3]-shaped dense stack (W512 L4) with Normal obs, 8 members
+    # BASELINE.json configs[2] per-GPU shard: 1M-row field, VI, W512 L4, 64 members / 8 GPUs,
+    # S=5 Monte-Carlo draws, batch 65536 (one shared random sub-batch per step)
+    'synthetic_vi_e8': dict(width=512, depth=4, members_per_gpu=8, sites=1000, times=1000, batch=65536,
+                            periods=[24, 168], harmonics=[4, 4], objective='vi', mc_samples=5),
     'air_quality_map_e8': dict(width=512, depth=4, members_per_gpu=8, sites=64, times=512, batch=None,
                                periods=[24, 168], harmonics=[4, 4], objective='map'),
 }
@@ -234,17 +238,40 @@ def main():
   B = wl['batch'] or n_total
   xd, yd = inference._to_device_data(x, y)
   lns = float(np.log(np.nanstd(y) / 2))
-  p = eng.init_params(lns, 1234, rank * E, E)
-  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  is_vi = wl['objective'] == 'vi'
+  S = wl.get('mc_samples', 1)
+  p = eng.init_params(0.0 if is_vi else lns, 1234, rank * E, E)
   sc = torch.zeros(1, dtype=torch.int32, device=dev)
   idx = None
-  if B < n_total:
-    gen = torch.Generator(device=dev).manual_seed(rank)
-    idx = inference._per_member_permutations(E, n_total, gen, dev)[:, :B].contiguous()
+  gen = torch.Generator(device=dev).manual_seed(rank)
+  if is_vi:
+    import math
+    rho = torch.full_like(p, math.log(math.expm1(0.3)))
+    m = torch.zeros((E, 2, spec.num_params), dtype=torch.float32, device=dev)
+    v = torch.zeros_like(m)
+    if B < n_total:
+      idx = torch.randperm(n_total, generator=gen, device=dev)[:B].to(torch.int32).contiguous()[None]
+  else:
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    if B < n_total:
+      idx = inference._per_member_permutations(E, n_total, gen, dev)[:, :B].contiguous()
+  vi_losses = torch.zeros((1, E), dtype=torch.float32, device=dev)
+  step_id = [0]
 
-  def run(k):
-    return eng.map_steps(p, m, v, sc, xd, yd, idx, B, n_total, k, 0.005, 1.0) if idx is None else \
-        torch.cat([eng.map_steps(p, m, v, sc, xd, yd, idx, B, n_total, 1, 0.005, 1.0) for _ in range(k)])
+  def run(k, xx=None, yy=None):
+    xx = xd if xx is None else xx
+    yy = yd if yy is None else yy
+    if is_vi:     # one tfp.vi step per call: S reparameterised draws per member (device Philox)
+      out = []
+      for _ in range(k):
+        step_id[0] += 1
+        eng.vi_step(p, rho, m, v, sc, S, None, 977 * step_id[0] + rank, xx, yy, idx, B, n_total, 0.01, 0.1,
+                    vi_losses[0])
+        out.append(vi_losses.clone())
+      return torch.cat(out)
+    if idx is None:
+      return eng.map_steps(p, m, v, sc, xx, yy, None, B, n_total, k, 0.005, 1.0)
+    return torch.cat([eng.map_steps(p, m, v, sc, xx, yy, idx, B, n_total, 1, 0.005, 1.0) for _ in range(k)])
 
   def barrier():
     if world > 1:
@@ -270,7 +297,7 @@ def main():
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
   ms = float(t_ms[0])
   assert torch.isfinite(losses).all(), 'non-finite loss in the timed region'
-  value = world * E * B * args.steps / (ms * 1e-3)
+  value = world * E * S * B * args.steps / (ms * 1e-3)   # network-rows per second (VI: x S draws)
 
   # ---- end to end through the public API, host buffers ------------------------
   xh = torch.tensor(x.astype(np.float32)).pin_memory()
@@ -281,7 +308,7 @@ def main():
   def e2e_step():
     xe.copy_(xh, non_blocking=True)
     ye.copy_(yh, non_blocking=True)
-    ls = eng.map_steps(p, m, v, sc, xe, ye, idx, B, n_total, 1, 0.005, 1.0)
+    ls = run(1, xe, ye)
     return ls.cpu()
 
   for _ in range(3):
@@ -295,7 +322,7 @@ def main():
   t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-  e2e_val = world * E * B * k_e2e / float(t_e[0])
+  e2e_val = world * E * S * B * k_e2e / float(t_e[0])
 
   # ---- per-kernel CUDA-event timing (separate short run; not the headline) ----
   prof, roof = {}, None
@@ -312,7 +339,7 @@ def main():
       prof[name] = {'launches_per_step': int(cnt) / k_prof, 'ms_per_step': float(tot) / k_prof}
     F, W, L = spec.num_features, wl['width'], wl['depth']
     Fp = spec.padded_features
-    rows = E * B
+    rows = E * S * B
     gemm_flops = {   # algorithmic FLOPs per step of each GEMM class (true F, not padded)
         'fwd': 2.0 * rows * (F * W + (L - 1) * W * W),
         'dgrad': 2.0 * rows * (F * W + (L - 1) * W * W),
@@ -343,7 +370,7 @@ def main():
 
   if rank == 0:
     fps = flops_per_sample(spec.num_features, wl['width'], wl['depth'])
-    act_bytes = E * B * wl['width'] * (2 if args.precision != 'fp32' else 4) * (2 * wl['depth'] + 2)
+    act_bytes = E * S * B * wl['width'] * (2 if args.precision != 'fp32' else 4) * (2 * wl['depth'] + 2)
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -352,6 +379,7 @@ def main():
         'data': 'synthetic',
         'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
                    'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
+                   'mc_samples': S,
                    'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'],
                    'parallelism': f'members sharded x{world}, no collective in training',
                    'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
@@ -360,6 +388,7 @@ def main():
                          'are data-dependent so no flush is inserted)'},
         'per_gpu_samples_per_s': value / world,
         'algorithmic_tflops_per_gpu': value / world * fps / 1e12,
+        'samples_definition': 'members x MC draws x batch rows per second' if is_vi else 'members x batch rows per second',
         'e2e': {'value': e2e_val, 'unit': 'samples/s', 'steps': k_e2e,
                 'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4),
                 'd2h_bytes_per_step': int(E * 4)},

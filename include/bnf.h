@@ -192,6 +192,19 @@ int bnf_mixture_quantiles(const float* means, const float* scales,
                           void* workspace, size_t workspace_bytes, void* stream);
 size_t bnf_quantile_workspace_bytes(int32_t n_components, int32_t n_points);
 
+/* NB / ZINB predictive mean and quantiles of the ensemble mixture
+ * (_build_observation_distribution + _get_nb_quantiles_root, inference.py:271-333).
+ * loc [n_components, n_points] = network outputs (bnf_forward); shape_raw /
+ * pi_logit [n_components] = params[1] / params[2] (pi_logit NULL -> plain NB).
+ * out_means [n_components, n_points] = distribution mean (obs_d.mean()); out_q
+ * [n_q, n_points] = min{k >= 0 integer : mean-CDF(k) >= q} capped at ceil(high), high =
+ * max(mean) + 1.1*rsqrt(1-q)*max(stddev) -- the integer the reference's
+ * ceil(Chandrupatla root) lands on.  CDF = regularised incomplete beta, in f64.  */
+int bnf_nb_mixture_quantiles(const float* loc, const float* shape_raw, const float* pi_logit,
+                             int32_t n_components, int32_t n_points, const double* q, int32_t n_q,
+                             float* out_means, float* out_q, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* ---- test / profiling hooks (not part of the reference seam) ----------------
  * bnf_debug_gemm: run the tcgen05 GEMM kernel alone, C[net][M][N] (f32) =
  *   mn_major == 0: A[net][M][K] x B[net][N][K]^T   (both K-major, as fwd/dgrad use it)

@@ -435,3 +435,55 @@ def normal_quantile_via_root(means, scales, q, value_tol=1e-5, max_iter=60):
     t = torch.minimum(torch.maximum(t, tl), 1 - tl)
     t = torch.where(torch.isfinite(t), t, torch.full_like(t, 0.5))
   return best
+
+
+# --------------------------------------------------------------------------
+# inference.py:271-333 NB / ZINB predictive mean and quantiles
+# --------------------------------------------------------------------------
+def nb_predictive(loc, shape_raw, pi_logit, distribution):
+  """loc (M, N) network outputs, shape_raw / pi_logit (M,) -> dict of float64 numpy arrays
+  (total_count (M,1), logits (M,N), pi (M,1), mean, stddev, prob0), following
+  models.py:166-191 literally and the TFP NegativeBinomial / mixture moments."""
+  import scipy.special as sp
+  loc = np.asarray(loc, np.float64)
+  a = np.logaddexp(np.asarray(shape_raw, np.float64), 0.0)[:, None]        # softplus(params[1])
+  mean_net = np.logaddexp(loc, 0.0)
+  r = 1.0 / a
+  logits = -np.log(a) - np.log(mean_net)
+  nb_mean = r * np.exp(logits)                        # tfd.NegativeBinomial.mean
+  nb_var = nb_mean / sp.expit(-logits)                # tfd.NegativeBinomial.variance
+  nb_p0 = sp.expit(-logits) ** r                      # exp(log_prob(0))
+  if distribution == NB:
+    pi = np.zeros_like(a)
+  else:
+    pi = 1.0 / (1.0 + np.exp(-np.asarray(pi_logit, np.float64)))[:, None]
+  mean = (1 - pi) * nb_mean
+  var = (1 - pi) * (nb_var + nb_mean ** 2) - mean ** 2      # mixture of delta_0 and NB
+  return dict(r=r, logits=logits, pi=pi, mean=mean, stddev=np.sqrt(var), prob0=pi + (1 - pi) * nb_p0)
+
+
+def nb_mixture_cdf(k, pred):
+  """Mean over components of the (ZI)NB CDF at integer(s) k >= 0 -> (N,)."""
+  import scipy.special as sp
+  k = np.floor(np.asarray(k, np.float64))
+  cdf = sp.betainc(pred['r'], 1.0 + k, sp.expit(-pred['logits']))    # TFP NegativeBinomial._cdf
+  return (pred['pi'] + (1 - pred['pi']) * cdf).mean(0)
+
+
+def nb_quantiles(pred, q):
+  """inference.py:298-333: ceil(root of mean-CDF(x) - q on [0, high]) with the
+  zero-mass override, evaluated as the exact discrete quantile
+  min{k >= 0 integer : mean-CDF(k) >= q}, capped at ceil(high); the reference's
+  Chandrupatla root + ceil lands on the same integer unless a CDF plateau lies
+  within its 1e-5 value tolerance of q."""
+  high = pred['mean'].max() + 1.1 / math.sqrt(1 - q) * pred['stddev'].max()
+  n = pred['logits'].shape[1]
+  lo = np.full(n, -1.0)
+  hi = np.full(n, math.ceil(high))
+  while np.any(hi - lo > 1):
+    mid = np.floor((lo + hi) / 2)
+    ge = nb_mixture_cdf(mid, pred) >= q
+    act = hi - lo > 1
+    hi = np.where(act & ge, mid, hi)
+    lo = np.where(act & ~ge, mid, lo)
+  return hi

@@ -357,3 +357,42 @@ def test_training_reduces_loss_full_size(cuda):
   assert losses.shape == (1, 8, 60) and np.isfinite(losses).all()
   assert (losses[0, :, -1] < losses[0, :, 0]).all()
   assert (np.diff(losses[0], axis=1) < 0).mean() > 0.9
+
+
+@pytest.mark.parametrize('dist', ['NB', 'ZINB'])
+def test_nb_predictive_quantiles(cuda, dist):
+  """predict_bnf for count models (inference.py:271-333): distribution means and the discrete
+  mixture quantiles vs the scipy-based oracle (f64 betainc on both sides -> exact integers)."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  n = 120
+  x, y = _data(cfg, n, counts=True)
+  om = O.OracleModel(**cfg)
+  P = _random_params(om, 5, y, seed=21)
+  spec = models.ModelSpec(**cfg, observation_model=dist)
+  params = spec.unflatten(P.numpy()[None])
+  qs = (0.5, 0.025, 0.975)
+  means, quantiles = inference.predict_bnf(x, dist, params, cfg, qs, precision='fp32')
+  assert means.shape == (1, 5, n) and len(quantiles) == 3
+  xd, _ = inference._to_device_data(x, y)
+  loc = torch.stack([om.forward(om.unflatten(P[j]), xd.cpu()) for j in range(5)]).numpy()
+  pred = O.nb_predictive(loc, P[:, 1].numpy(), P[:, 2].numpy(), dist)
+  np.testing.assert_allclose(means[0], pred['mean'], rtol=2e-4)
+  for q, got in zip(qs, quantiles):
+    want = O.nb_quantiles(pred, q)
+    # identical integers except where the f32 network output moves a CDF value across q
+    assert np.mean(got == want) >= 0.97, (q, got[:10], want[:10])
+    assert np.abs(got - want).max() <= max(2.0, 0.02 * want.max())
+  assert np.all(quantiles[1] <= quantiles[0]) and np.all(quantiles[0] <= quantiles[2])
+
+
+def test_nb_estimator_predict_api(cuda):
+  """End to end: ZINB estimator fit + predict through the public API."""
+  import bayesnf_b200
+  train, test = _chickenpox_tables()
+  est = _chickenpox_estimator(bayesnf_b200.BayesianNeuralFieldMAP, precision='fp32')
+  est.observation_model = 'ZINB'
+  est.fit(train, seed=3, ensemble_size=3, learning_rate=0.005, num_epochs=8)
+  means, q = est.predict(train, quantiles=(0.5, 0.9))
+  assert means.shape == (1, 3, 100) and np.isfinite(means).all()
+  assert q[0].shape == (100,) and np.all(q[0] <= q[1]) and np.all(q[0] == np.floor(q[0]))

@@ -134,3 +134,28 @@ def test_bf16_training_tracks_fp32(cuda):
   rel = np.abs(res['bf16'] - res['fp32']) / np.abs(res['fp32'])
   assert rel.max() < 2e-2, rel.max()
   assert (res['bf16'][:, -1] < res['bf16'][:, 0]).all()
+
+
+@pytest.mark.parametrize('flag', ['BNF_FUSED_ENCODE', 'BNF_NO_FUSED_ACT_BWD'])
+def test_alternative_kernel_paths_agree(cuda, flag, monkeypatch):
+  """The opt-in fused encode+Dense_0 kernel and the unfused dgrad/act_bwd pair compute the
+  same thing as the default path (same bf16 storage; only reduction order differs)."""
+  from bayesnf_b200 import inference
+  n = 700
+  cfg = _cfg(256, 3, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3)
+  eng = inference.Engine(spec, 'bf16')
+  monkeypatch.delenv(flag, raising=False)
+  loc0 = eng.forward(P.cuda(), xd).cpu()
+  ll0, g0 = eng.loglik_grad(P.cuda(), xd, yd)
+  monkeypatch.setenv(flag, '1')
+  loc1 = eng.forward(P.cuda(), xd).cpu()
+  ll1, g1 = eng.loglik_grad(P.cuda(), xd, yd)
+  assert float((loc0 - loc1).abs().max()) <= 1e-2 * float(loc0.abs().max())
+  assert float(((ll0 - ll1) / ll0).abs().max()) <= 5e-3
+  g0, g1 = g0.cpu(), g1.cpu()
+  for j in range(3):
+    for lo, hi in [(0, 3)] + [(o, o + (int(np.prod(s)) if s else 1))
+                              for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]:
+      scale = float(g0[j, lo:hi].abs().max()) + 1e-3 * float(g0[j].abs().max())
+      assert float((g0[j, lo:hi] - g1[j, lo:hi]).abs().max()) <= 3e-2 * scale, (flag, lo, hi)
