@@ -194,7 +194,7 @@ template <int BLOCK_N, int A_MODE = 0> struct TcCfg {
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, int A_MODE>
+template <int BLOCK_N, int A_MODE, int MODE>
 __global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
@@ -350,7 +350,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
       float c1 = a.isf, w_act = 0.f;
       float* sb = sbias + acc * 256;
-      if (a.mode == TC_FWD) {
+      if (MODE == TC_FWD) {
         const float s_l = dv[kDvSLayer + a.layer];
         c1 = s_l * a.isf;
         w_act = dv[kDvActW];
@@ -361,15 +361,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int row = m_t * 128 + q * 32 + lane;
       const bool row_ok = row < a.m_valid;
       // TC_DGRAD_ACT: this row's z of the previous layer, register-prefetched one chunk ahead
+      // (two chunks ahead, so the DRAM latency of the strided z rows hides behind the math of
+      // the chunks in between; the chunk loop itself stays rolled to keep the code in I-cache)
       float s_prev = 0.f, g_w = 0.f, g_s = 0.f;
-      uint4 zq[4];
+      uint4 zq0[4], zq1[4];
       const bf16* zrow = nullptr;
-      if (a.mode == TC_DGRAD_ACT) {
+      if (MODE == TC_DGRAD_ACT) {
         w_act = dv[kDvActW];
         s_prev = dv[kDvSLayer + a.layer_prev];
         zrow = a.zin + (size_t)net * a.out_batch + (size_t)min(row, a.m_valid - 1) * a.ld_out + n_t * BLOCK_N;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) zq[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32) + k);
+        for (int k = 0; k < 4; ++k) {
+          zq0[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32) + k);
+          if (BLOCK_N > 64) zq1[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32 + 64) + k);
+        }
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -378,7 +383,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
-        if (a.mode == TC_FWD) {
+        if (MODE == TC_FWD) {
           uint32_t zp[16], hp[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -414,16 +419,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (a.out0) tma_store_3d(&map_o0, stg + 2048, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        } else if (a.mode == TC_DGRAD_ACT) {
+        } else if (MODE == TC_DGRAD_ACT) {
           // dh = acc/sqrt(fan_in); dz = dh*act'(z); dU = s*dz; plus the reductions that the
           // separate act_bwd kernel used to do (bias column sums, activation-mix and
           // layer-scale scalars).  models.py:255-268 backward.
           uint32_t zw[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { zw[4 * k] = zq[k].x; zw[4 * k + 1] = zq[k].y; zw[4 * k + 2] = zq[k].z; zw[4 * k + 3] = zq[k].w; }
-          if (c + 64 < BLOCK_N) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) zq[k] = __ldg(reinterpret_cast<const uint4*>(zrow + c + 64) + k);
+          for (int k = 0; k < 4; ++k) {
+            zw[4 * k] = zq0[k].x; zw[4 * k + 1] = zq0[k].y; zw[4 * k + 2] = zq0[k].z; zw[4 * k + 3] = zq0[k].w;
+            zq0[k] = zq1[k];
+            if (c + 128 < BLOCK_N) zq1[k] = __ldg(reinterpret_cast<const uint4*>(zrow + c + 128) + k);
           }
           float du[32];
           uint32_t pk[16];
@@ -469,7 +474,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
           atomicAdd(a.gradp + (size_t)net * a.P + a.off_bias_prev + col0 + lane, du[0]);
-        } else if (a.mode == TC_DGRAD_BF16) {
+        } else if (MODE == TC_DGRAD_BF16) {
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -489,7 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        } else if (a.mode == TC_DGRAD_F32 || a.mode == TC_PLAIN_F32) {
+        } else if (MODE == TC_DGRAD_F32 || MODE == TC_PLAIN_F32) {
           if (row_ok) {
             float4* o4 = reinterpret_cast<float4*>(a.outf + (size_t)net * a.out_batch + (size_t)row * a.ld_out + col0);
 #pragma unroll
@@ -513,7 +518,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (a.mode == TC_DGRAD_ACT) {
+      if (MODE == TC_DGRAD_ACT) {
         g_w = warp_sum(g_w);
         g_s = warp_sum(g_s);
         if (lane == 0) {
@@ -668,24 +673,45 @@ static int make_out_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint6
 
 struct OutMaps { CUtensorMap o0, o1; };
 
-template <int BLOCK_N, int MN>
-static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
-                     const DevModel* dm = nullptr) {
+template <int BLOCK_N, int MN, int MODE>
+static int launch_tc_m(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
+                       const DevModel* dm = nullptr) {
   using Cfg = TcCfg<BLOCK_N, MN>;
   static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
       return tc_fail(BNF_ERR_CUDA, "cudaFuncSetAttribute(smem) failed");
     attr_set = true;
   }
   long long total = (long long)a.n_net * a.m_tiles * a.n_tiles * a.k_splits;
   int grid = (int)(total < sm_count ? total : sm_count);
   if (grid < 1) grid = 1;
-  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : a.mode == TC_FWD ? "tc_gemm_fwd" : (a.mode == TC_WGRAD ? "tc_gemm_wgrad" : (a.mode == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
-  tc_gemm_kernel<BLOCK_N, MN><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a, dm ? *dm : dm_zero);
+  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  tc_gemm_kernel<BLOCK_N, MN, MODE><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a, dm ? *dm : dm_zero);
   if (cudaGetLastError() != cudaSuccess) return tc_fail(BNF_ERR_CUDA, "tc_gemm_kernel launch failed");
   return 0;
+}
+
+// one kernel instantiation per (tile width, operand mode, epilogue): each carries only its own
+// epilogue code (the whole hot loop stays resident in the instruction cache)
+template <int BLOCK_N, int MN>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm, cudaStream_t st,
+                     const DevModel* dm = nullptr) {
+  if constexpr (MN == 2) {
+    return launch_tc_m<BLOCK_N, 2, TC_FWD>(ma, mb, om, a, sm, st, dm);
+  } else if constexpr (MN == 1) {
+    if (a.mode == TC_WGRAD) return launch_tc_m<BLOCK_N, 1, TC_WGRAD>(ma, mb, om, a, sm, st, dm);
+    return launch_tc_m<BLOCK_N, 1, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
+  } else {
+    switch (a.mode) {
+      case TC_FWD: return launch_tc_m<BLOCK_N, 0, TC_FWD>(ma, mb, om, a, sm, st, dm);
+      case TC_DGRAD_ACT: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ACT>(ma, mb, om, a, sm, st, dm);
+      case TC_DGRAD_BF16: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_BF16>(ma, mb, om, a, sm, st, dm);
+      case TC_DGRAD_F32: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_F32>(ma, mb, om, a, sm, st, dm);
+      default: return launch_tc_m<BLOCK_N, 0, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
+    }
+  }
 }
 
 template <int MN>
