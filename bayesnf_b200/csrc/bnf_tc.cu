@@ -122,6 +122,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// one lane of a converged warp (PTX elect.sync): keeps the surrounding loop warp-uniform so
+// the uniform-datapath tcgen05 / TMA instructions need no per-instruction election
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, %1;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -177,6 +184,10 @@ struct TcArgs {
 };
 
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
+// Warp roles.  The SM's issue arbiter favours the highest warp id, so the single-thread MMA
+// issuer and the TMA producer are the LAST two warps of the CTA: the eight epilogue warps
+// (ids 0..7) can never starve the tensor-core feed.  (A_MODE 2 adds encoder warps after them.)
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kXTileBytes = 128 * kMaxD * 4;
@@ -225,12 +236,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                  ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (ENCODE && warp >= 2 + kEpiWarps) {
+  if (ENCODE && warp > kMmaWarp) {
     // zero the A slots once: pad columns [F, Fp) are never written again
     const int et = threadIdx.x - kTcThreads;
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -248,9 +259,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int total_tiles = a.n_net * tiles_per_net;
   const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp == kProducerWarp) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int net = t / tiles_per_net;
@@ -262,42 +273,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          if (ENCODE) {
-            // B by TMA; the raw input rows of this tile as one bulk copy for the encoder warps
-            mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
-            tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
-            if (a.x_tma && m_t * 128 + 128 <= a.m_valid) {
-              const uint32_t xb = 128u * (uint32_t)dm.D * 4u;
-              mbar_arrive_expect_tx(&xfull[stage], xb);
-              bulk_load_1d(xtile + stage * 128 * kMaxD, a.x + (size_t)m_t * 128 * dm.D, xb, &xfull[stage]);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            if (ENCODE) {
+              // B by TMA; the raw input rows of this tile as one bulk copy for the encoder warps
+              mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
+              tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
+              if (a.x_tma && m_t * 128 + 128 <= a.m_valid) {
+                const uint32_t xb = 128u * (uint32_t)dm.D * 4u;
+                mbar_arrive_expect_tx(&xfull[stage], xb);
+                bulk_load_1d(xtile + stage * 128 * kMaxD, a.x + (size_t)m_t * 128 * dm.D, xb, &xfull[stage]);
+              } else {
+                mbar_arrive(&xfull[stage]);
+              }
+            } else if (!MN_MAJOR) {
+              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+              tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+              tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
             } else {
-              mbar_arrive(&xfull[stage]);
+              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+              // MN-major: boxes of [64 reduction rows][64 MN elements]
+              for (int j = 0; j < 2; ++j)
+                tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
             }
-          } else if (!MN_MAJOR) {
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
-            tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
-          } else {
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            // MN-major: boxes of [64 reduction rows][64 MN elements]
-            for (int j = 0; j < 2; ++j)
-              tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
           }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accum, bf16 x bf16
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
                              ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
+      // smem descriptors differ only in the 14-bit start address: build them once and add offsets
+      const uint64_t adesc0 = MN_MAJOR ? make_smem_desc(smem_u32(smem), 8192, 1024)
+                                       : make_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = adesc0 + (uint64_t)(Cfg::kABytes >> 4);
+      constexpr uint32_t kStep = (MN_MAJOR ? 2048 : 32) >> 4;      // one UMMA_K=16 slice
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -312,35 +331,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad, bd;
-            if (!MN_MAJOR) {
-              ad = make_smem_desc(sa + k * 32, 16, 1024);
-              bd = make_smem_desc(sb + k * 32, 16, 1024);
-            } else {
-              ad = make_smem_desc(sa + k * 2048, 8192, 1024);
-              bd = make_smem_desc(sb + k * 2048, 8192, 1024);
-            }
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
-    // ===================== epilogue (warps 2..9) =====================
+  } else if (warp < kEpiWarps) {
+    // ===================== epilogue (warps 0..7) =====================
     // warp%4 selects the TMEM lane quarter it may read; the two warps of a quarter
     // take alternate 32-column chunks, so every SM sub-partition has two epilogue
     // warps to hide tcgen05.ld / MUFU / store latency behind each other.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int epi_tid = threadIdx.x - 64;
+    const int half = warp >> 2;
+    const int epi_tid = threadIdx.x;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int net = t / tiles_per_net;
@@ -402,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // registers -> 64B-swizzled smem tile (conflict-free 16B stores) -> TMA store:
           // full 64-byte rows leave the SM as bulk writes instead of 32 scattered
           // 16-byte stores per instruction; rows >= B are clipped by the tensor map.
-          uint8_t* stg = staging + (warp - 2) * 4096;
+          uint8_t* stg = staging + warp * 4096;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -448,7 +461,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __nv_bfloat162 t2 = __floats2bfloat162_rn(du[j], du[j + 1]);
             pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
           }
-          uint8_t* stg = staging + (warp - 2) * 4096;
+          uint8_t* stg = staging + warp * 4096;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -481,7 +494,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j]) * a.isf, __uint_as_float(v[j + 1]) * a.isf);
             pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
           }
-          uint8_t* stg = staging + (warp - 2) * 4096;
+          uint8_t* stg = staging + warp * 4096;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -610,7 +623,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
