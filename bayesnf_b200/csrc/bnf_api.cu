@@ -315,13 +315,21 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
     }
   }
   const bool g = grad != nullptr;
-  launch_head<T>(m, params, w.derived, (const T*)w.h[m.L - 1], y, idx, idx_stride, B, out_loc,
-                 ll ? w.opre : nullptr, ll ? w.r : nullptr, ll, g ? grad : nullptr, n_net, st);
-  CUK();
-  if (!g) return BNF_OK;
   int cur = 0;
-  launch_act_bwd<T>(m, m.L - 1, true, params, w.derived, (const T*)w.z[m.L - 1], (const T*)w.h[m.L - 1],
-                    w.r, (T*)w.dU[cur], B, grad, n_net, st);
+  // training: head + activation backward of the last layer in one kernel when the shape allows
+  const char* nh = getenv("BNF_NO_FUSED_HEAD");
+  bool head_done = false;
+  if (g && ll && !(nh && nh[0] == '1'))
+    head_done = launch_head_fused<T>(m, params, w.derived, (const T*)w.h[m.L - 1], (const T*)w.z[m.L - 1], y, idx,
+                                     idx_stride, B, (T*)w.dU[cur], ll, grad, n_net, st);
+  if (!head_done) {
+    launch_head<T>(m, params, w.derived, (const T*)w.h[m.L - 1], y, idx, idx_stride, B, out_loc,
+                   ll ? w.opre : nullptr, ll ? w.r : nullptr, ll, g ? grad : nullptr, n_net, st);
+    CUK();
+    if (!g) return BNF_OK;
+    launch_act_bwd<T>(m, m.L - 1, true, params, w.derived, (const T*)w.z[m.L - 1], (const T*)w.h[m.L - 1],
+                      w.r, (T*)w.dU[cur], B, grad, n_net, st);
+  }
   for (int l = m.L - 1; l >= 0; --l) {
     const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
     const int Kin = l == 0 ? m.F : m.W, lda = l == 0 ? m.Fp : m.W;

@@ -110,6 +110,7 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
 
 // encode backward: dfeat [n_net,B,Fp] f32 -> grads of
 // feature_inv_sp_scale{g} and log_scale_adjustment, accumulated into grad[n_net,P].
+constexpr int kEncBwdRows = 128;   // more rows per block: fewer block reductions / atomics
 template <bool FAST>
 __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                                   const float* __restrict__ derived, const float* __restrict__ x,
@@ -117,7 +118,7 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
                                   const float* __restrict__ dfeat, float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
   const int net = blockIdx.y;
-  const int row0 = blockIdx.x * kEncRows;
+  const int row0 = blockIdx.x * kEncBwdRows;
   const float* dv = derived + (size_t)net * kDerivedStride;
   const int nacc = m.D + 3 + m.D;
   for (int e = threadIdx.x; e < nacc; e += blockDim.x) acc[e] = 0.f;
@@ -126,9 +127,9 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
   const float two_pi = 6.283185307179586f;
   const int lane = threadIdx.x & 31;
   // every warp processes whole (unit, 32 rows) items -> warp-uniform unit
-  const int items = (kEncRows * U + 31) / 32 * 32;
+  const int items = (kEncBwdRows * U + 31) / 32 * 32;
   for (int w = threadIdx.x; w < items; w += blockDim.x) {
-    const int u = w / kEncRows, r = w % kEncRows;
+    const int u = w / kEncBwdRows, r = w % kEncBwdRows;
     const int b = row0 + r;
     const bool live = (u < U) && (b < B);
     float gs = 0.f, gl_a = 0.f, gl_b = 0.f;
@@ -547,6 +548,7 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
     g_b[k] = 0.f; g_ko[k] = 0.f;
     head_c[k] = IS_HEAD ? dv[kDvSOut] * m.inv_sqrt_W * p[m.off_kernel[m.L] + cg * VEC + k] : 0.f;
   }
+#pragma unroll 4
   for (int b = b0 + threadIdx.x / G; b < b1; b += rstep) {
     const size_t o = ((size_t)net * B + b) * m.W + (size_t)cg * VEC;
     alignas(16) T zv[VEC];
@@ -599,6 +601,185 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
     for (int i = 0; i < 8; ++i) { tw += red[0][i]; ts += red[1][i]; }
     atomicAdd(&g[m.off_actw], tw * w * (1.f - w));
     atomicAdd(&g[m.off_layer_scale[layer]], (ts / s_l) * sigmoid_f(p[m.off_layer_scale[layer]]));
+  }
+}
+
+// =============================================================================
+// head + activation backward of the last hidden layer in ONE kernel (training path).
+// A block owns 256 rows: (A) each warp forms the h.Ko dots of 32 rows (coalesced 16-byte
+// loads, 4 rows in flight), all lanes evaluate their row's likelihood and r = dlogp/do
+// into shared memory; (B) the block runs the elementwise backward of the same rows
+// (h re-read while it is still L2/L1-resident, z from HBM), so r never leaves the SM and
+// the bias / Dense_L column sums are flushed once per 256 rows.
+// Same math as head_kernel + act_bwd_vec_kernel<.., true>.
+// =============================================================================
+constexpr int kHeadFusedRows = 256;
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                  const float* __restrict__ derived, const T* __restrict__ h, const T* __restrict__ z,
+                  const float* __restrict__ y_all, const int32_t* __restrict__ idx, int64_t idx_stride,
+                  int B, T* __restrict__ dU, float* __restrict__ ll, float* __restrict__ grad) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr bool FAST = FastMath<T>::value;
+  extern __shared__ float fsm[];
+  float* rs = fsm;                              // [256] r = dlogp/do of this block's rows
+  float* colsum = fsm + kHeadFusedRows;         // [2W] bias / Dense_L kernel column sums
+  __shared__ float hred[8][8];
+  const int net = blockIdx.y;
+  const int b0 = blockIdx.x * kHeadFusedRows, b1 = min(B, b0 + kHeadFusedRows);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* p = params + (size_t)net * m.P;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const float* Ko = p + m.off_kernel[m.L];
+  const float bo = p[m.off_bias[m.L]], s_out = dv[kDvSOut];
+  for (int i = threadIdx.x; i < 2 * m.W; i += 256) colsum[i] = 0.f;
+  // ---- (A) row dots + likelihood: warp w owns rows b0 + 32w .. +31
+  float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
+  {
+    const int base = b0 + warp * 32;
+    float mydot = 0.f;
+    for (int j0 = 0; j0 < 32; j0 += 4) {
+      if (base + j0 >= b1) break;               // warp-uniform
+      float dot[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = base + j0 + u;
+        if (b < b1) {
+          const T* hr = h + ((size_t)net * B + b) * m.W;
+          for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
+            alignas(16) T hv[VEC];
+            *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), Ko[n + k], dot[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d = warp_sum(dot[u]);
+        if (lane == j0 + u) mydot = d;
+      }
+    }
+    const int b = base + lane;
+    if (b < b1) {
+      const float opre = mydot * m.inv_sqrt_W + bo;
+      const float o = s_out * opre;
+      int64_t row = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
+      const float yv = y_all[row];
+      float logp, rr;
+      if (m.likelihood == BNF_NORMAL) {
+        const float sg = dv[kDvSigma];
+        const float d = yv / sg - o / sg;
+        logp = -0.5f * d * d - (0.9189385332046727f + logf(sg));
+        rr = d / sg;
+        a_g0 += (d * d - 1.f) / sg;
+      } else {
+        const float mean = softplus_f(o);
+        const float shp = dv[kDvShape];
+        const float rc = 1.f / shp;
+        const float lg = -logf(shp) - logf(mean);
+        const float sig_l = sigmoid_f(lg);
+        float nb = rc * log_sigmoid_f(-lg) + yv * log_sigmoid_f(lg)
+                   - (lgammaf(1.f + yv) + lgammaf(rc) - lgammaf(1.f + yv + rc)) - logf(rc + yv);
+        float dnb_dl = yv * (1.f - sig_l) - rc * sig_l;
+        float dnb_dr = log_sigmoid_f(-lg) - digamma_f(rc) + digamma_f(1.f + yv + rc) - 1.f / (rc + yv);
+        float wnb = 1.f;
+        logp = nb;
+        if (m.likelihood == BNF_ZINB) {
+          const float pi = dv[kDvPi];
+          if (yv == 0.f) {
+            const float A = (1.f - pi) * expf(nb), tot = A + pi;
+            logp = logf(tot);
+            wnb = A / tot;
+            a_g2 += (1.f - expf(nb)) / tot;
+          } else {
+            logp = log1pf(-pi) + nb;
+            a_g2 += -1.f / (1.f - pi);
+          }
+        }
+        rr = wnb * dnb_dl * (-sigmoid_f(o) / mean);
+        a_g1 += wnb * (dnb_dl * (-1.f / shp) + dnb_dr * (-1.f / (shp * shp)));
+      }
+      a_ll += logp;
+      a_gs += rr * opre;
+      a_gb += rr * s_out;
+      rs[b - b0] = rr;
+    }
+  }
+  __syncthreads();
+  // ---- (B) activation backward of layer L-1 for these rows (thread keeps one column group)
+  const int layer = m.L - 1;
+  const float w = dv[kDvActW], s_l = dv[kDvSLayer + layer];
+  float g_w = 0.f, g_s = 0.f;
+  {
+    const int G = m.W / VEC;
+    const int cg = threadIdx.x % G, rstep = 256 / G;
+    float g_b[VEC], g_ko[VEC], head_c[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      g_b[k] = 0.f; g_ko[k] = 0.f;
+      head_c[k] = s_out * m.inv_sqrt_W * Ko[cg * VEC + k];
+    }
+    // 4 independent row iterations in flight: the loop is latency-bound otherwise
+#pragma unroll 4
+    for (int b = b0 + threadIdx.x / G; b < b1; b += rstep) {
+      const size_t o = ((size_t)net * B + b) * m.W + (size_t)cg * VEC;
+      alignas(16) T zv[VEC];
+      alignas(16) T hv[VEC];
+      alignas(16) T out[VEC];
+      *reinterpret_cast<uint4*>(zv) = *reinterpret_cast<const uint4*>(z + o);
+      *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(h + o);
+      const float rb = rs[b - b0];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float zz = to_f<T>(zv[k]);
+        const float dh = rb * head_c[k];
+        g_ko[k] += rb * to_f<T>(hv[k]);
+        float diff;
+        const float da = act_grad_sel<FAST>(zz, w, &diff);
+        const float dz = dh * da;
+        g_w += dh * diff;
+        g_s += dz * zz;
+        const float du = dz * s_l;
+        g_b[k] += du;
+        out[k] = from_f<T>(du);
+      }
+      *reinterpret_cast<uint4*>(dU + o) = *reinterpret_cast<const uint4*>(out);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      atomicAdd(&colsum[cg * VEC + k], g_b[k]);
+      atomicAdd(&colsum[m.W + cg * VEC + k], g_ko[k]);
+    }
+  }
+  // ---- block reductions -> global atomics
+  a_ll = warp_sum(a_ll); a_g0 = warp_sum(a_g0); a_g1 = warp_sum(a_g1); a_g2 = warp_sum(a_g2);
+  a_gs = warp_sum(a_gs); a_gb = warp_sum(a_gb); g_w = warp_sum(g_w); g_s = warp_sum(g_s);
+  if (lane == 0) {
+    hred[0][warp] = a_ll; hred[1][warp] = a_g0; hred[2][warp] = a_g1; hred[3][warp] = a_g2;
+    hred[4][warp] = a_gs; hred[5][warp] = a_gb; hred[6][warp] = g_w; hred[7][warp] = g_s;
+  }
+  __syncthreads();
+  float* g = grad + (size_t)net * m.P;
+  for (int i = threadIdx.x; i < m.W; i += 256) {
+    atomicAdd(&g[m.off_bias[layer] + i], colsum[i]);
+    atomicAdd(&g[m.off_kernel[m.L] + i], colsum[m.W + i] * s_out * m.inv_sqrt_W);
+  }
+  if (threadIdx.x == 0) {
+    float t[8];
+    for (int k = 0; k < 8; ++k) { t[k] = 0.f; for (int i = 0; i < 8; ++i) t[k] += hred[k][i]; }
+    atomicAdd(&ll[net], t[0]);
+    if (m.likelihood == BNF_NORMAL) {
+      atomicAdd(&g[0], t[1] * expf(p[0]));
+    } else {
+      atomicAdd(&g[1], t[2] * sigmoid_f(p[1]));
+      if (m.likelihood == BNF_ZINB) { const float pi = dv[kDvPi]; atomicAdd(&g[2], t[3] * pi * (1.f - pi)); }
+    }
+    atomicAdd(&g[m.off_out_scale], t[4] * sigmoid_f(p[m.off_out_scale]));
+    atomicAdd(&g[m.off_bias[m.L]], t[5]);
+    atomicAdd(&g[m.off_actw], t[6] * w * (1.f - w));
+    atomicAdd(&g[m.off_layer_scale[layer]], (t[7] / s_l) * sigmoid_f(p[m.off_layer_scale[layer]]));
   }
 }
 
@@ -990,7 +1171,7 @@ template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const 
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
                        int n_net, bool fast_trig, cudaStream_t st) {
-  dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
+  dim3 grid((B + kEncBwdRows - 1) / kEncBwdRows, n_net);
   BNF_PROF("encode_bwd", st);
   if (fast_trig)
     encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
@@ -1008,6 +1189,24 @@ void launch_head(const DevModel& m, const float* params, const float* derived, c
 }
 template void launch_head<float>(const DevModel&, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 template void launch_head<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
+
+// returns false when the shape does not fit the fused kernel (caller uses head + act_bwd)
+template <typename T>
+bool launch_head_fused(const DevModel& m, const float* params, const float* derived, const T* h, const T* z,
+                       const float* y, const int32_t* idx, int64_t idx_stride, int B, T* dU, float* ll,
+                       float* grad, int n_net, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (m.W % VEC != 0) return false;
+  const int G = m.W / VEC;
+  if (G > 256 || 256 % G != 0) return false;
+  const size_t smem = (size_t)(kHeadFusedRows + 2 * m.W) * sizeof(float);
+  dim3 grid((B + kHeadFusedRows - 1) / kHeadFusedRows, n_net);
+  BNF_PROF("head_fused", st);
+  head_fused_kernel<T><<<grid, 256, smem, st>>>(m, params, derived, h, z, y, idx, idx_stride, B, dU, ll, grad);
+  return true;
+}
+template bool launch_head_fused<float>(const DevModel&, const float*, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, int, cudaStream_t);
+template bool launch_head_fused<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, __nv_bfloat16*, float*, float*, int, cudaStream_t);
 
 template <typename T>
 void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* params,

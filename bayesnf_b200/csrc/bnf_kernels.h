@@ -21,6 +21,10 @@ void launch_head(const DevModel& m, const float* params, const float* derived, c
                  const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
                  float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st);
 template <typename T>
+bool launch_head_fused(const DevModel& m, const float* params, const float* derived, const T* h, const T* z,
+                       const float* y, const int32_t* idx, int64_t idx_stride, int B, T* dU, float* ll,
+                       float* grad, int n_net, cudaStream_t st);
+template <typename T>
 void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* params,
                     const float* derived, const T* z, const T* h, const float* r, T* dU, int B,
                     float* grad, int n_net, cudaStream_t st);

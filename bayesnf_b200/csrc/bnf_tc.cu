@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bnf_device.cuh"
@@ -122,6 +123,41 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+// 2-SM TMA load: completion bytes are credited to the LEADER CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on both CTAs' barrier
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // one lane of a converged warp (PTX elect.sync): keeps the surrounding loop warp-uniform so
 // the uniform-datapath tcgen05 / TMA instructions need no per-instruction election
 __device__ __forceinline__ bool elect_one() {
@@ -193,26 +229,31 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kXTileBytes = 128 * kMaxD * 4;
 // A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
 // encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major.
-template <int BLOCK_N, int A_MODE = 0> struct TcCfg {
-  static constexpr int kStages = A_MODE == 2 ? 2 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+// CTA2: a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
+// each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
+// from L2 drops by a third and the ring gets deeper (32 KB stages).
+template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false> struct TcCfg {
+  static constexpr int kStages = A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8)));
   static constexpr int kThreads = kTcThreads + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
   static constexpr int kABytes = 128 * 64 * 2;
-  static constexpr int kBBytes = BLOCK_N * 64 * 2;
+  static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, int A_MODE, int MODE>
-__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE>::kThreads), 1)
+template <int BLOCK_N, int A_MODE, int MODE, bool CTA2>
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE, CTA2>::kThreads), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
-  using Cfg = TcCfg<BLOCK_N, A_MODE>;
+  using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2>;
   constexpr bool MN_MAJOR = A_MODE == 1;
   constexpr bool ENCODE = A_MODE == 2;
+  static_assert(!(CTA2 && ENCODE), "the fused encode kernel is single-CTA");
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -229,17 +270,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], ENCODE ? 1 + 32 * kEncWarps : 1);
+      mbar_init(&full[s], ENCODE ? 1 + 32 * kEncWarps : (CTA2 ? 2 : 1));
       mbar_init(&empty[s], 1);
       if (ENCODE) mbar_init(&xfull[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 32 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (CTA2 ? 2 : 1) * 32 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (ENCODE && warp > kMmaWarp) {
     // zero the A slots once: pad columns [F, Fp) are never written again
@@ -252,23 +299,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();        // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_net = a.m_tiles * a.n_tiles * a.k_splits;
+  // work items: (net, m unit, split, n tile); a unit is one 128-row tile, or a PAIR of them for
+  // a CTA pair (this CTA takes rows of tile 2*unit + cta_rank)
+  const int m_units = CTA2 ? (a.m_tiles + 1) / 2 : a.m_tiles;
+  const int tiles_per_net = m_units * a.n_tiles * a.k_splits;
   const int total_tiles = a.n_net * tiles_per_net;
   const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < total_tiles; t += tile_step) {
         const int net = t / tiles_per_net;
         int r = t % tiles_per_net;
         const int n_t = r % a.n_tiles; r /= a.n_tiles;
         const int split = r % a.k_splits;
-        const int m_t = r / a.k_splits;
+        const int m_t = CTA2 ? 2 * (r / a.k_splits) + (int)cta_rank : r / a.k_splits;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -286,6 +339,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 bulk_load_1d(xtile + stage * 128 * kMaxD, a.x + (size_t)m_t * 128 * dm.D, xb, &xfull[stage]);
               } else {
                 mbar_arrive(&xfull[stage]);
+              }
+            } else if (CTA2) {
+              // the LEADER's full barrier collects both CTAs' bytes (count 2: its own
+              // arrive.expect_tx + the peer's remote arrive)
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+              else mbar_arrive_remote(&full[stage], 0);
+              const int nb = n_t * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);   // this CTA's half of B
+              if (!MN_MAJOR) {
+                tma_load_3d_2sm(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+                tma_load_3d_2sm(sb, &map_b, &full[stage], kb * 64, nb, net);
+              } else {
+                for (int j = 0; j < 2; ++j)
+                  tma_load_3d_2sm(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+                for (int j = 0; j < BLOCK_N / 128; ++j)
+                  tma_load_3d_2sm(sb + j * 8192, &map_b, &full[stage], nb + j * 64, kb * 64, net);
               }
             } else if (!MN_MAJOR) {
               mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -307,11 +375,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
-    {
+    if (!CTA2 || cta_rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accum, bf16 x bf16
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
                              ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)((CTA2 ? 256 : 128) >> 4) << 24);
       // smem descriptors differ only in the 14-bit start address: build them once and add offsets
       const uint64_t adesc0 = MN_MAJOR ? make_smem_desc(smem_u32(smem), 8192, 1024)
                                        : make_smem_desc(smem_u32(smem), 16, 1024);
@@ -319,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t kStep = (MN_MAJOR ? 2048 : 32) >> 4;      // one UMMA_K=16 slice
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < total_tiles; t += tile_step) {
         int r = t % tiles_per_net;
         r /= a.n_tiles;
         const int split = r % a.k_splits;
@@ -334,14 +402,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (elect_one()) {
             const uint64_t so = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+            for (int k = 0; k < 4; ++k) {
+              if (CTA2) umma_bf16_2sm(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CTA2) umma_commit_2sm(&empty[stage]);   // frees the slot in BOTH CTAs
+            else umma_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
           }
           __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);   // accumulator complete -> epilogue
+        if (elect_one()) {                            // accumulator complete -> epilogue(s)
+          if (CTA2) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
+        }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -355,11 +428,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = warp >> 2;
     const int epi_tid = threadIdx.x;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = tile0; t < total_tiles; t += tile_step) {
       const int net = t / tiles_per_net;
       int r = t % tiles_per_net;
       const int n_t = r % a.n_tiles; r /= a.n_tiles;
-      const int m_t = r / a.k_splits;
+      const int m_t = CTA2 ? 2 * (r / a.k_splits) + (int)cta_rank : r / a.k_splits;
       const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
       float c1 = a.isf, w_act = 0.f;
       float* sb = sbias + acc * 256;
@@ -529,7 +602,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (CTA2) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns both TMEMs' reuse
+      else mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (MODE == TC_DGRAD_ACT) {
         g_w = warp_sum(g_w);
@@ -552,7 +626,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int U = num_units(dm);
     const float two_pi = 6.283185307179586f;
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = tile0; t < total_tiles; t += tile_step) {
       const int net = t / tiles_per_net;
       int r0 = t % tiles_per_net;
       const int n_t = r0 % a.n_tiles; r0 /= a.n_tiles;
@@ -623,10 +697,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();        // the peer's smem / TMEM stay alive until both CTAs are done
   if (warp == kMmaWarp) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    if (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -686,24 +764,59 @@ static int make_out_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint6
 
 struct OutMaps { CUtensorMap o0, o1; };
 
-template <int BLOCK_N, int MN, int MODE>
-static int launch_tc_m(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
-                       const DevModel* dm = nullptr) {
-  using Cfg = TcCfg<BLOCK_N, MN>;
+template <int BLOCK_N, int MN, int MODE, bool CTA2>
+static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
+                       const DevModel* dm) {
+  using Cfg = TcCfg<BLOCK_N, MN, CTA2>;
   static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
       return tc_fail(BNF_ERR_CUDA, "cudaFuncSetAttribute(smem) failed");
     attr_set = true;
   }
-  long long total = (long long)a.n_net * a.m_tiles * a.n_tiles * a.k_splits;
-  int grid = (int)(total < sm_count ? total : sm_count);
+  const int m_units = CTA2 ? (a.m_tiles + 1) / 2 : a.m_tiles;
+  long long total = (long long)a.n_net * m_units * a.n_tiles * a.k_splits;
+  const int slots = CTA2 ? sm_count / 2 : sm_count;
+  int grid = (int)(total < slots ? total : slots);
   if (grid < 1) grid = 1;
+  if (CTA2) grid *= 2;
   BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
-  tc_gemm_kernel<BLOCK_N, MN, MODE><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(ma, mb, om.o0, om.o1, a, dm ? *dm : dm_zero);
-  if (cudaGetLastError() != cudaSuccess) return tc_fail(BNF_ERR_CUDA, "tc_gemm_kernel launch failed");
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const DevModel& dmr = dm ? *dm : dm_zero;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, ma, mb, om.o0, om.o1, a, dmr);
+  if (e != cudaSuccess) {
+    snprintf(g_tc_err, sizeof(g_tc_err), "tc_gemm_kernel launch failed: %s", cudaGetErrorString(e));
+    return BNF_ERR_CUDA;
+  }
   return 0;
+}
+
+// CTA pairs (cta_group::2) serve the big 256-wide GEMMs; opt-in with BNF_CTA2=1 for now
+static bool want_cta2(const TcArgs& a, int block_n) {
+  const char* e = getenv("BNF_CTA2");
+  return e && e[0] == '1' && block_n == 256 && a.m_tiles >= 2;
+}
+
+template <int BLOCK_N, int MN, int MODE>
+static int launch_tc_m(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
+                       const DevModel* dm = nullptr) {
+  if constexpr (BLOCK_N == 256 && MN != 2 && (MODE == TC_FWD || MODE == TC_DGRAD_ACT || MODE == TC_WGRAD || MODE == TC_PLAIN_F32)) {
+    if (want_cta2(a, BLOCK_N)) return launch_tc_k<BLOCK_N, MN, MODE, true>(ma, mb, om, a, sm_count, st, dm);
+  }
+  return launch_tc_k<BLOCK_N, MN, MODE, false>(ma, mb, om, a, sm_count, st, dm);
 }
 
 // one kernel instantiation per (tile width, operand mode, epilogue): each carries only its own
@@ -754,12 +867,13 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
   if (rc) return rc;
-  rc = make_map(&mb, wt + layer_off(m, layer), Kp, m.W, n_net, Kp, tc_weight_elems(m), bn);
-  if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_FWD; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1; a.k_blocks = Kp / 64;
+  // a CTA pair loads the B tile in two halves (one per CTA)
+  rc = make_map(&mb, wt + layer_off(m, layer), Kp, m.W, n_net, Kp, tc_weight_elems(m), want_cta2(a, bn) ? bn / 2 : bn);
+  if (rc) return rc;
   a.m_valid = B; a.n_valid = m.W;
   a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
@@ -811,11 +925,13 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 128);
   if (rc) return rc;
-  rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m), bn);
-  if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
+  a.m_tiles = (B + 127) / 128;
   a.mode = out_bf ? (z_prev ? TC_DGRAD_ACT : TC_DGRAD_BF16) : TC_DGRAD_F32; a.n_net = n_net;
+  rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m),
+                (a.mode == TC_DGRAD_ACT && want_cta2(a, bn)) ? bn / 2 : bn);
+  if (rc) return rc;
   if (z_prev) {
     a.zin = z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
     a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
@@ -846,9 +962,11 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   a.mode = TC_WGRAD; a.n_net = n_net;
   a.m_tiles = (Kp + 127) / 128; a.n_tiles = m.W / bn; a.k_blocks = (B + 63) / 64;
   const int sm = sm_count_of(p);
-  long long base_tiles = (long long)n_net * a.m_tiles * a.n_tiles;
+  const bool pair = want_cta2(a, bn);
+  const int slots = pair ? sm / 2 : sm;
+  long long base_tiles = (long long)n_net * (pair ? (a.m_tiles + 1) / 2 : a.m_tiles) * a.n_tiles;
   int splits = 1;
-  if (base_tiles < sm) splits = (int)(sm / base_tiles);   // fill one wave, never a ragged second one
+  if (base_tiles < slots) splits = (int)(slots / base_tiles);   // fill one wave, never a ragged second one
   if (splits > a.k_blocks / 4) splits = a.k_blocks / 4;   // >= 4 k-blocks per split
   if (splits < 1) splits = 1;
   // every split must own at least one k-block
@@ -878,7 +996,7 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
   memset(&om, 0, sizeof(om));
   if (!mn_major) {   // A [net][M][K], B [net][N][K]
     if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
-    if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, bn))) return rc;
+    if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, want_cta2(a, bn) ? bn / 2 : bn))) return rc;
     return launch_tc_n<0>(bn, ma, mb, om, a, sm_count, st);
   }
   // A [net][K][M], B [net][K][N]

@@ -132,8 +132,7 @@ def cpu_oracle_rate(x, y, margs, budget_s, threads=None):
   full batch, all host threads, for ~budget_s seconds.  Returns samples/s."""
   import torch
   from oracle import bnf_oracle as O
-  if threads:
-    torch.set_num_threads(threads)
+  torch.set_num_threads(threads or os.cpu_count() or 1)
   om = O.OracleModel(**margs)
   g = torch.Generator().manual_seed(0)
   p = om.flatten(O.init_map_params(om, y, g))
@@ -167,6 +166,7 @@ def run_reference(args, wl, x, y, margs):
     return
   import torch
   from oracle import bnf_oracle as O
+  torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: undo it
   om = O.OracleModel(**margs)
   g = torch.Generator().manual_seed(0)
   p = om.flatten(O.init_map_params(om, y, g))
@@ -399,7 +399,7 @@ def main():
         'cpu_baseline': cpu,
         'final_loss_mean': float(losses[-1].mean()),
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
   if world > 1:
     dist.destroy_process_group()
 

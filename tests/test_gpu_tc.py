@@ -159,3 +159,55 @@ def test_alternative_kernel_paths_agree(cuda, flag, monkeypatch):
                               for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]:
       scale = float(g0[j, lo:hi].abs().max()) + 1e-3 * float(g0[j].abs().max())
       assert float((g0[j, lo:hi] - g1[j, lo:hi]).abs().max()) <= 3e-2 * scale, (flag, lo, hi)
+
+
+def test_fused_head_matches_two_kernel_path(cuda, monkeypatch):
+  """head_fused_kernel == head_kernel + act_bwd (fp32 mode: tight tolerance)."""
+  from bayesnf_b200 import inference
+  for dist in ('NORMAL', 'ZINB'):
+    n = 333
+    cfg = _cfg(128, 2, n)
+    om, spec, P, xd, yd = _setup(cfg, n, 3, dist)
+    eng = inference.Engine(spec, 'fp32')
+    monkeypatch.delenv('BNF_NO_FUSED_HEAD', raising=False)
+    ll0, g0 = eng.loglik_grad(P.cuda(), xd, yd)
+    monkeypatch.setenv('BNF_NO_FUSED_HEAD', '1')
+    ll1, g1 = eng.loglik_grad(P.cuda(), xd, yd)
+    assert float(((ll0 - ll1) / ll1).abs().max()) <= 1e-5
+    assert float((g0 - g1).abs().max()) <= 2e-4 * float(g1.abs().max())
+
+
+@pytest.mark.parametrize('mn_major,nets,m,n,k', [
+    (0, 1, 256, 256, 64), (0, 1, 256, 256, 256), (0, 2, 1000, 512, 1024), (0, 1, 130, 256, 128),
+    (0, 3, 4096, 1024, 1024), (1, 1, 256, 256, 128), (1, 2, 512, 256, 1000), (1, 2, 1024, 1024, 4096)])
+def test_gemm_cta_pair(cuda, monkeypatch, mn_major, nets, m, n, k):
+  """cta_group::2 variant (BNF_CTA2=1): a CTA pair computes 256-row tiles, each CTA staging
+  half of the B tile; same results as the single-CTA kernel."""
+  monkeypatch.setenv('BNF_CTA2', '1')
+  g = torch.Generator(device='cuda').manual_seed(m + n + k)
+  if mn_major:
+    a = torch.randn(nets, k, m, generator=g, device=cuda).to(torch.bfloat16)
+    b = torch.randn(nets, k, n, generator=g, device=cuda).to(torch.bfloat16)
+    want = torch.bmm(a.float().transpose(1, 2), b.float())
+  else:
+    a = torch.randn(nets, m, k, generator=g, device=cuda).to(torch.bfloat16)
+    b = torch.randn(nets, n, k, generator=g, device=cuda).to(torch.bfloat16)
+    want = torch.bmm(a.float(), b.float().transpose(1, 2))
+  c = _gemm(mn_major, a, b, nets, m, n, k)
+  err = float((c - want).abs().max())
+  assert err <= 2e-3 * float(want.abs().max()), err
+
+
+def test_cta_pair_training_path(cuda, monkeypatch):
+  """Whole bf16 step with CTA pairs == single-CTA path (width 256 so every GEMM qualifies)."""
+  from bayesnf_b200 import inference
+  n = 1000
+  cfg = _cfg(256, 3, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3)
+  eng = inference.Engine(spec, 'bf16')
+  monkeypatch.delenv('BNF_CTA2', raising=False)
+  ll0, g0 = eng.loglik_grad(P.cuda(), xd, yd)
+  monkeypatch.setenv('BNF_CTA2', '1')
+  ll1, g1 = eng.loglik_grad(P.cuda(), xd, yd)
+  assert float(((ll0 - ll1) / ll0).abs().max()) <= 1e-3
+  assert float((g0 - g1).abs().max()) <= 1e-2 * float(g0.abs().max())
