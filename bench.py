@@ -118,6 +118,26 @@ class ClockSampler(threading.Thread):
             'reasons': sorted(self.reasons)}
 
 
+NCU_SUMMARY = {'chickenpox_map_e8': 'ncu_chickenpox_r1L_summary.csv', 'wind_map_e16': 'ncu_wind_tc_gemm_r1L_summary.csv'}
+NCU_PATTERN = {'tc_gemm_fwd': ', 0, 0, ', 'tc_gemm_dgrad': ', 0, 5, ', 'tc_gemm_wgrad': ', 1, 3, '}
+
+
+def ncu_traffic_gb(workload, kernel):
+  """DRAM bytes (read+write) per launch of `kernel` from the committed `ncu --set full` summary
+  of the same workload (profiles/), or None."""
+  import csv
+  path = os.path.join(ROOT, 'profiles', NCU_SUMMARY.get(workload, ''))
+  if not os.path.isfile(path) or kernel not in NCU_PATTERN:
+    return None
+  rows = list(csv.reader(open(path)))
+  hdr, units = rows[0], rows[1]
+  ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+  scale = {'Gbyte': 1.0, 'Mbyte': 1e-3, 'Kbyte': 1e-6, 'byte': 1e-9}[units[ir]]
+  vals = [(float(r[ir]) + float(r[iw])) * scale for r in rows[2:]
+          if NCU_PATTERN[kernel] in r[ik] and r[ik].startswith('void tc_gemm_kernel<256')]
+  return max(vals) if vals else None      # the widest launch of that class (hidden layers)
+
+
 def peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -127,33 +147,56 @@ def peaks():
   return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def cpu_oracle_rate(x, y, margs, budget_s, threads=None):
-  """The CPU baseline: oracle MAP steps (value_and_grad + Adam) of ONE member on the
-  full batch, all host threads, for ~budget_s seconds.  Returns samples/s."""
+def _oracle_stepper(x, y, margs):
+  """One oracle MAP step (value_and_grad + Adam) of ONE member on the full batch."""
   import torch
   from oracle import bnf_oracle as O
-  torch.set_num_threads(threads or os.cpu_count() or 1)
   om = O.OracleModel(**margs)
   g = torch.Generator().manual_seed(0)
-  p = om.flatten(O.init_map_params(om, y, g))
-  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  state = {'p': om.flatten(O.init_map_params(om, y, g)), 't': 0}
+  state['m'], state['v'] = torch.zeros_like(state['p']), torch.zeros_like(state['p'])
   B = margs['init_x'][0]
   xt = torch.tensor(x[:B], dtype=torch.float32)
   yt = torch.tensor(y[:B], dtype=torch.float32)
   n_total = len(y)
-  steps, t0 = 0, None
+
+  def step():
+    state['t'] += 1
+    loss, gr = O.map_loss_and_grad(om, state['p'], xt, yt, n_total, 1.0, 'NORMAL')
+    state['p'], state['m'], state['v'] = O.adam_update(state['p'], gr, state['m'], state['v'], state['t'], 0.005)
+  return step, B
+
+
+def _best_thread_count(step):
+  """The CPU arm may use every host thread, but torch's intra-op pool gets SLOWER past a point
+  on these GEMM sizes: time one step at a few pool sizes and keep the fastest."""
+  import torch
+  ncpu = os.cpu_count() or 1
+  best, best_t = ncpu, float('inf')
+  for n in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+    torch.set_num_threads(n)
+    step()                                   # warm the pool
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    if dt < best_t:
+      best, best_t = n, dt
+  torch.set_num_threads(best)
+  return best
+
+
+def cpu_oracle_rate(x, y, margs, budget_s):
+  """The CPU baseline: oracle MAP steps for ~budget_s seconds.  Returns samples/s."""
+  step, B = _oracle_stepper(x, y, margs)
+  threads = _best_thread_count(step)
+  steps, t0 = 0, time.perf_counter()
   while True:
-    loss, gr = O.map_loss_and_grad(om, p, xt, yt, n_total, 1.0, 'NORMAL')
-    p, m, v = O.adam_update(p, gr, m, v, steps + 1, 0.005)
+    step()
     steps += 1
-    if steps == 1:                 # first step = warm-up (thread pools, allocator)
-      t0 = time.perf_counter()
-      continue
     el = time.perf_counter() - t0
-    if el > budget_s and steps >= 4:
+    if el > budget_s and steps >= 3:
       break
-  timed = steps - 1
-  return B * timed / el, timed, torch.get_num_threads()
+  return B * steps / el, steps, threads
 
 
 def run_reference(args, wl, x, y, margs):
@@ -165,24 +208,13 @@ def run_reference(args, wl, x, y, margs):
   if rank != 0:
     return
   import torch
-  from oracle import bnf_oracle as O
-  torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: undo it
-  om = O.OracleModel(**margs)
-  g = torch.Generator().manual_seed(0)
-  p = om.flatten(O.init_map_params(om, y, g))
-  m, v = torch.zeros_like(p), torch.zeros_like(p)
-  B = margs['init_x'][0]
-  xt, yt = torch.tensor(x[:B], dtype=torch.float32), torch.tensor(y[:B], dtype=torch.float32)
-  t = 0
+  step, B = _oracle_stepper(x, y, margs)
+  _best_thread_count(step)                   # torchrun exports OMP_NUM_THREADS=1: undo it
   for _ in range(args.warmup):
-    t += 1
-    loss, gr = O.map_loss_and_grad(om, p, xt, yt, len(y), 1.0, 'NORMAL')
-    p, m, v = O.adam_update(p, gr, m, v, t, 0.005)
+    step()
   t0 = time.perf_counter()
   for _ in range(args.steps):
-    t += 1
-    loss, gr = O.map_loss_and_grad(om, p, xt, yt, len(y), 1.0, 'NORMAL')
-    p, m, v = O.adam_update(p, gr, m, v, t, 0.005)
+    step()
   el = time.perf_counter() - t0
   val = B * args.steps / el
   cores = torch.get_num_threads()
@@ -194,7 +226,8 @@ def run_reference(args, wl, x, y, margs):
       'data': 'synthetic',
       'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
                  'batch_rows': B, 'objective': wl['objective']},
-      'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+      'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'cores_available': os.cpu_count(),
+                       'kind': 'port', 'sample': sample},
       'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }))
 
@@ -356,16 +389,20 @@ def main():
     if best:
       d = prof[best]
       peak = pk['tflops_sustained'] if args.precision == 'bf16' else None
+      traffic = ncu_traffic_gb(args.workload, best) if args.precision == 'bf16' else None
+      avg_ms = d['ms_per_step'] / d['launches_per_step']
       roof = {'bound': 'tensor', 'kernel': best, 'achieved': d['tflops'], 'peak': peak,
-              'unit': 'TFLOP/s', 'frac': (d['tflops'] / peak) if peak else None, 'traffic': None,
-              'peak_source': pk['source'] + ', sustained bf16',
-              'avg_launch_ms': d['ms_per_step'] / d['launches_per_step']}
+              'unit': 'TFLOP/s', 'frac': (d['tflops'] / peak) if peak else None,
+              'traffic': traffic, 'traffic_unit': 'GB per launch (ncu dram read+write, hidden-layer launch)',
+              'hbm_frac_of_measured': (traffic / (avg_ms * 1e-3) / pk['hbm_gbs']) if traffic else None,
+              'peak_source': pk['source'] + ', sustained bf16', 'avg_launch_ms': avg_ms,
+              'note': 'small shapes (chickenpox) are latency-bound: both fractions are low'}
 
   # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     val, timed, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget)
-    cpu = {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+    cpu = {'value': val, 'unit': 'samples/s', 'cores': cores, 'cores_available': os.cpu_count(), 'kind': 'port',
            'sample': f'1 member x {margs["init_x"][0]} rows x {timed} MAP steps (torch-CPU oracle, f32)'}
 
   if rank == 0:

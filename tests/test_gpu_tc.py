@@ -35,8 +35,9 @@ SHAPES = [(1, 128, 64, 64), (1, 128, 128, 128), (1, 128, 256, 256), (2, 256, 256
 
 
 @pytest.mark.parametrize('nets,m,n,k', SHAPES)
-def test_gemm_k_major(cuda, nets, m, n, k):
-  """C = A[M,K] . B[N,K]^T  (operand layout of the forward and dgrad GEMMs)."""
+def test_gemm_k_major(cuda, monkeypatch, nets, m, n, k):
+  """C = A[M,K] . B[N,K]^T  (operand layout of the forward and dgrad GEMMs), single-CTA tiles."""
+  monkeypatch.setenv('BNF_CTA2', '0')
   g = torch.Generator(device='cuda').manual_seed(m * 7 + n)
   a = torch.randn(nets, m, k, generator=g, device=cuda).to(torch.bfloat16)
   b = torch.randn(nets, n, k, generator=g, device=cuda).to(torch.bfloat16)
@@ -49,8 +50,9 @@ def test_gemm_k_major(cuda, nets, m, n, k):
 @pytest.mark.parametrize('nets,m,n,k', [(1, 128, 64, 64), (1, 128, 128, 128), (1, 256, 256, 256),
                                         (2, 128, 256, 1000), (1, 64, 64, 200), (3, 64, 128, 77),
                                         (2, 1024, 1024, 4096), (8, 256, 256, 10440)])
-def test_gemm_mn_major(cuda, nets, m, n, k):
+def test_gemm_mn_major(cuda, monkeypatch, nets, m, n, k):
   """C = A[K,M]^T . B[K,N]  (wgrad: reduction over batch rows, ragged K zero-filled by TMA)."""
+  monkeypatch.setenv('BNF_CTA2', '0')
   g = torch.Generator(device='cuda').manual_seed(m * 3 + k)
   a = torch.randn(nets, k, m, generator=g, device=cuda).to(torch.bfloat16)
   b = torch.randn(nets, k, n, generator=g, device=cuda).to(torch.bfloat16)
@@ -181,8 +183,8 @@ def test_fused_head_matches_two_kernel_path(cuda, monkeypatch):
     (0, 1, 256, 256, 64), (0, 1, 256, 256, 256), (0, 2, 1000, 512, 1024), (0, 1, 130, 256, 128),
     (0, 3, 4096, 1024, 1024), (1, 1, 256, 256, 128), (1, 2, 512, 256, 1000), (1, 2, 1024, 1024, 4096)])
 def test_gemm_cta_pair(cuda, monkeypatch, mn_major, nets, m, n, k):
-  """cta_group::2 variant (BNF_CTA2=1): a CTA pair computes 256-row tiles, each CTA staging
-  half of the B tile; same results as the single-CTA kernel."""
+  """cta_group::2 variant (default for 256-wide tiles; BNF_CTA2=0 disables): a CTA pair computes
+  256-row tiles, each CTA staging half of the B tile; both variants against a f32 matmul."""
   monkeypatch.setenv('BNF_CTA2', '1')
   g = torch.Generator(device='cuda').manual_seed(m + n + k)
   if mn_major:
@@ -205,9 +207,41 @@ def test_cta_pair_training_path(cuda, monkeypatch):
   cfg = _cfg(256, 3, n)
   om, spec, P, xd, yd = _setup(cfg, n, 3)
   eng = inference.Engine(spec, 'bf16')
-  monkeypatch.delenv('BNF_CTA2', raising=False)
+  monkeypatch.setenv('BNF_CTA2', '0')
   ll0, g0 = eng.loglik_grad(P.cuda(), xd, yd)
   monkeypatch.setenv('BNF_CTA2', '1')
   ll1, g1 = eng.loglik_grad(P.cuda(), xd, yd)
   assert float(((ll0 - ll1) / ll0).abs().max()) <= 1e-3
   assert float((g0 - g1).abs().max()) <= 1e-2 * float(g0.abs().max())
+
+
+def test_estimators_bf16_end_to_end(cuda):
+  """Public API in tensor-core mode: MAP with minibatches + per-member permutations, MLE full
+  batch (CUDA-graph replay), VI with sub-batches, predict with quantiles."""
+  import pandas as pd
+  import bayesnf_b200
+  rng = np.random.default_rng(0)
+  T, S = 120, 12
+  dates = pd.date_range('2021-01-04', periods=T, freq='W-MON')
+  rows = []
+  for s in range(S):
+    lat, lon = rng.normal(), rng.normal()
+    for t, d in enumerate(dates):
+      rows.append((d, lat, lon, 5 * np.sin(2 * np.pi * t / 52.0) + lat + rng.normal(scale=0.3)))
+  df = pd.DataFrame(rows, columns=['datetime', 'latitude', 'longitude', 'y'])
+  kw = dict(feature_cols=['datetime', 'latitude', 'longitude'], target_col='y', freq='W',
+            seasonality_periods=['Y'], num_seasonal_harmonics=[4], width=128, depth=2,
+            standardize=['latitude', 'longitude'], precision='bf16')
+  est = bayesnf_b200.BayesianNeuralFieldMAP(**kw).fit(df, seed=1, ensemble_size=4, num_epochs=6,
+                                                     batch_size=256, learning_rate=0.01)
+  assert est.losses_.shape == (1, 4, 6) and np.isfinite(est.losses_).all()
+  assert est.losses_[0, :, -1].mean() < est.losses_[0, :, 0].mean()
+  means, q = est.predict(df.iloc[:200], quantiles=(0.1, 0.5, 0.9))
+  assert means.shape == (1, 4, 200) and np.all(q[0] <= q[1]) and np.all(q[1] <= q[2])
+  est = bayesnf_b200.BayesianNeuralFieldMLE(**kw).fit(df, seed=2, ensemble_size=2, num_epochs=40)
+  assert est.losses_.shape == (1, 2, 40) and (est.losses_[0, :, -1] < est.losses_[0, :, 0]).all()
+  est = bayesnf_b200.BayesianNeuralFieldVI(**kw).fit(df, seed=3, ensemble_size=2, num_epochs=2,
+                                                    batch_size=480, sample_size_posterior=3)
+  assert est.losses_.shape == (1, 2, 2 * (len(df) // 480)) and np.isfinite(est.losses_).all()
+  means, q = est.predict(df.iloc[:50])
+  assert means.shape == (1, 3, 2, 50) and np.isfinite(q[0]).all()
