@@ -51,7 +51,7 @@ __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* __r
 // work item = (row, unit); unit = one x column, one (dim,degree) sin/cos pair,
 // one seasonal sin/cos pair, or one interaction column.
 // =============================================================================
-constexpr int kEncRows = 64;
+constexpr int kEncRows = 32;
 
 template <typename T>
 __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* __restrict__ derived,
@@ -117,14 +117,8 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
                                   const int32_t* __restrict__ idx, int64_t idx_stride, int B,
                                   const float* __restrict__ dfeat, float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
-  extern __shared__ float gtile[];           // [rows][Fp+1]: this block's dfeat rows, coalesced load
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * kEncBwdRows;
-  {
-    const int ldg = m.Fp + 1, rows = min(kEncBwdRows, B - row0);
-    const float* src = dfeat + ((size_t)net * B + row0) * m.Fp;
-    for (int e = threadIdx.x; e < rows * m.Fp; e += blockDim.x) gtile[(e / m.Fp) * ldg + (e % m.Fp)] = src[e];
-  }
   const float* dv = derived + (size_t)net * kDerivedStride;
   const int nacc = m.D + 3 + m.D;
   for (int e = threadIdx.x; e < nacc; e += blockDim.x) acc[e] = 0.f;
@@ -147,7 +141,7 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
     else { slot = 2; dim_a = m.inter_a[ui.a]; dim_b = m.inter_b[ui.a]; }
     if (live) {
       const float* xr = row_ptr(x, idx, idx_stride, net, b, m.D);
-      const float* g = gtile + r * (m.Fp + 1);
+      const float* g = dfeat + ((size_t)net * B + b) * m.Fp;
       if (ui.kind == 0) {
         float sx = xr[ui.a] / dv[kDvDenom + ui.a];
         float G = g[m.col_x + ui.a];
@@ -619,7 +613,7 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
 // the bias / Dense_L column sums are flushed once per 256 rows.
 // Same math as head_kernel + act_bwd_vec_kernel<.., true>.
 // =============================================================================
-constexpr int kHeadFusedRows = 128;   // 4+ blocks per SM at the chickenpox shape (balance + latency hiding)
+constexpr int kHeadFusedRows = 256;
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
@@ -640,13 +634,12 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
   const float* Ko = p + m.off_kernel[m.L];
   const float bo = p[m.off_bias[m.L]], s_out = dv[kDvSOut];
   for (int i = threadIdx.x; i < 2 * m.W; i += 256) colsum[i] = 0.f;
-  // ---- (A) row dots + likelihood: warp w owns rows b0 + RW*w .. + RW-1 (RW = rows / 8 warps)
+  // ---- (A) row dots + likelihood: warp w owns rows b0 + 32w .. +31
   float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
   {
-    constexpr int RW = kHeadFusedRows / 8;
-    const int base = b0 + warp * RW;
+    const int base = b0 + warp * 32;
     float mydot = 0.f;
-    for (int j0 = 0; j0 < RW; j0 += 4) {
+    for (int j0 = 0; j0 < 32; j0 += 4) {
       if (base + j0 >= b1) break;               // warp-uniform
       float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -669,7 +662,7 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
       }
     }
     const int b = base + lane;
-    if (lane < RW && b < b1) {
+    if (b < b1) {
       const float opre = mydot * m.inv_sqrt_W + bo;
       const float o = s_out * opre;
       int64_t row = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
@@ -1180,17 +1173,10 @@ void launch_encode_bwd(const DevModel& m, const float* params, const float* deri
                        int n_net, bool fast_trig, cudaStream_t st) {
   dim3 grid((B + kEncBwdRows - 1) / kEncBwdRows, n_net);
   BNF_PROF("encode_bwd", st);
-  const size_t smem = (size_t)kEncBwdRows * (m.Fp + 1) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(encode_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(encode_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
-  }
   if (fast_trig)
-    encode_bwd_kernel<true><<<grid, 256, smem, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
   else
-    encode_bwd_kernel<false><<<grid, 256, smem, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
 }
 
 template <typename T>

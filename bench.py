@@ -259,6 +259,8 @@ def main():
   local = int(os.environ.get('LOCAL_RANK', '0'))
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+      os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the single JSON line
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
   torch.cuda.set_device(local)
