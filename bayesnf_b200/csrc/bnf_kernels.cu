@@ -110,43 +110,44 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
 
 // encode backward: dfeat [n_net,B,Fp] f32 -> grads of
 // feature_inv_sp_scale{g} and log_scale_adjustment, accumulated into grad[n_net,P].
-constexpr int kEncBwdRows = 128;   // more rows per block: fewer block reductions / atomics
+// A warp owns whole units (one x column / one sin-cos pair / one interaction column): its
+// lanes stride over the block's rows and keep the three partial sums in registers, so there is
+// one warp reduction per (unit, block) instead of one per 32 rows; rows per block are chosen at
+// launch so the grid is a whole number of waves.
+constexpr int kEncBwdMaxRows = 1024;
 template <bool FAST>
-__global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
-                                  const float* __restrict__ derived, const float* __restrict__ x,
-                                  const int32_t* __restrict__ idx, int64_t idx_stride, int B,
-                                  const float* __restrict__ dfeat, float* __restrict__ grad) {
+__global__ void __launch_bounds__(256)
+encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                  const float* __restrict__ derived, const float* __restrict__ x,
+                  const int32_t* __restrict__ idx, int64_t idx_stride, int B, int R /* rows per block */,
+                  const float* __restrict__ dfeat, float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
   const int net = blockIdx.y;
-  const int row0 = blockIdx.x * kEncBwdRows;
+  const int row0 = blockIdx.x * R, row1 = min(B, row0 + R);
   const float* dv = derived + (size_t)net * kDerivedStride;
   const int nacc = m.D + 3 + m.D;
   for (int e = threadIdx.x; e < nacc; e += blockDim.x) acc[e] = 0.f;
   __syncthreads();
   const int U = num_units(m);
   const float two_pi = 6.283185307179586f;
-  const int lane = threadIdx.x & 31;
-  // every warp processes whole (unit, 32 rows) items -> warp-uniform unit
-  const int items = (kEncBwdRows * U + 31) / 32 * 32;
-  for (int w = threadIdx.x; w < items; w += blockDim.x) {
-    const int u = w / kEncBwdRows, r = w % kEncBwdRows;
-    const int b = row0 + r;
-    const bool live = (u < U) && (b < B);
-    float gs = 0.f, gl_a = 0.f, gl_b = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int u = warp; u < U; u += 8) {
+    const UnitInfo ui = decode_unit(m, u);
     int slot = 0, dim_a = 0, dim_b = -1;
-    UnitInfo ui = decode_unit(m, u < U ? u : 0);
     if (ui.kind == 0) { slot = 0; dim_a = ui.a; }
     else if (ui.kind == 1) { slot = 3 + ui.a; dim_a = ui.a; }
     else if (ui.kind == 2) { slot = 1; dim_a = -1; }
     else { slot = 2; dim_a = m.inter_a[ui.a]; dim_b = m.inter_b[ui.a]; }
-    if (live) {
+    float gs = 0.f, gl_a = 0.f, gl_b = 0.f;
+#pragma unroll 2
+    for (int b = row0 + lane; b < row1; b += 32) {
       const float* xr = row_ptr(x, idx, idx_stride, net, b, m.D);
       const float* g = dfeat + ((size_t)net * B + b) * m.Fp;
       if (ui.kind == 0) {
         float sx = xr[ui.a] / dv[kDvDenom + ui.a];
         float G = g[m.col_x + ui.a];
-        gs = G * sx;
-        gl_a = dv[kDvSX] * G * (-sx);
+        gs = fmaf(G, sx, gs);
+        gl_a = fmaf(dv[kDvSX] * G, -sx, gl_a);
       } else if (ui.kind == 1) {
         const int i = ui.a, d = ui.b, deg = m.fourier_deg[i];
         float sx = xr[i] / dv[kDvDenom + i];
@@ -155,30 +156,30 @@ __global__ void encode_bwd_kernel(const __grid_constant__ DevModel m, const floa
         if (FAST) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
         const float den = (float)(d + 1);
         float Gc = g[m.fourier_col[i] + d], Gs = g[m.fourier_col[i] + deg + d];
-        gs = Gc * (cs / den) + Gs * (sn / den);
+        gs += Gc * (cs / den) + Gs * (sn / den);
         float dsx = dv[kDvSFourier + i] * (c / den) * (-sn * Gc + cs * Gs);
-        gl_a = dsx * (-sx);
+        gl_a = fmaf(dsx, -sx, gl_a);
       } else if (ui.kind == 2) {
         const int k = ui.a;
         float sn, cs;
         if (FAST) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
         float hk = m.seasonal_h[k];
-        gs = g[m.col_seasonal + k] * (cs / hk) + g[m.col_seasonal + m.n_seasonal + k] * (sn / hk);
+        gs += g[m.col_seasonal + k] * (cs / hk) + g[m.col_seasonal + m.n_seasonal + k] * (sn / hk);
       } else {
         const int j = ui.a;
         float sa = xr[dim_a] / dv[kDvDenom + dim_a];
         float sb = xr[dim_b] / dv[kDvDenom + dim_b];
         float G = g[m.col_inter + j];
-        gs = G * sa * sb;
+        gs = fmaf(G, sa * sb, gs);
         // d(sa*sb)/d lsa_a = -sa*sb, same for b
-        gl_a = dv[kDvSInter] * G * (-sa * sb);
-        gl_b = gl_a;
+        gl_a = fmaf(dv[kDvSInter] * G, -sa * sb, gl_a);
       }
     }
+    if (ui.kind == 3) gl_b = gl_a;
     gs = warp_sum(gs);
     gl_a = warp_sum(gl_a);
     gl_b = warp_sum(gl_b);
-    if (lane == 0 && u < U) {
+    if (lane == 0) {
       atomicAdd(&acc[m.D + slot], gs);
       if (dim_a >= 0) atomicAdd(&acc[dim_a], gl_a);
       if (dim_b >= 0) atomicAdd(&acc[dim_b], gl_b);
@@ -610,34 +611,38 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
 // loads, 4 rows in flight), all lanes evaluate their row's likelihood and r = dlogp/do
 // into shared memory; (B) the block runs the elementwise backward of the same rows
 // (h re-read while it is still L2/L1-resident, z from HBM), so r never leaves the SM and
-// the bias / Dense_L column sums are flushed once per 256 rows.
+// the bias / Dense_L column sums are flushed once per block; the rows per block are picked at
+// launch so that the grid is a whole number of waves of resident blocks (no ragged tail).
 // Same math as head_kernel + act_bwd_vec_kernel<.., true>.
 // =============================================================================
-constexpr int kHeadFusedRows = 256;
+constexpr int kHeadFusedMaxRows = 512;   // rows per block are chosen at launch so the grid is whole waves
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                   const float* __restrict__ derived, const T* __restrict__ h, const T* __restrict__ z,
                   const float* __restrict__ y_all, const int32_t* __restrict__ idx, int64_t idx_stride,
-                  int B, T* __restrict__ dU, float* __restrict__ ll, float* __restrict__ grad) {
+                  int B, int R /* rows per block */, T* __restrict__ dU, float* __restrict__ ll,
+                  float* __restrict__ grad) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr bool FAST = FastMath<T>::value;
   extern __shared__ float fsm[];
-  float* rs = fsm;                              // [256] r = dlogp/do of this block's rows
-  float* colsum = fsm + kHeadFusedRows;         // [2W] bias / Dense_L kernel column sums
+  float* rs = fsm;                              // [R] r = dlogp/do of this block's rows
+  float* colsum = fsm + kHeadFusedMaxRows;      // [2W] bias / Dense_L kernel column sums
+  float* kos = colsum + 2 * m.W;                // [W] Dense_L kernel
   __shared__ float hred[8][8];
   const int net = blockIdx.y;
-  const int b0 = blockIdx.x * kHeadFusedRows, b1 = min(B, b0 + kHeadFusedRows);
+  const int b0 = blockIdx.x * R, b1 = min(B, b0 + R);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* p = params + (size_t)net * m.P;
   const float* dv = derived + (size_t)net * kDerivedStride;
   const float* Ko = p + m.off_kernel[m.L];
   const float bo = p[m.off_bias[m.L]], s_out = dv[kDvSOut];
   for (int i = threadIdx.x; i < 2 * m.W; i += 256) colsum[i] = 0.f;
-  // ---- (A) row dots + likelihood: warp w owns rows b0 + 32w .. +31
+  for (int i = threadIdx.x; i < m.W; i += 256) kos[i] = Ko[i];
+  __syncthreads();
+  // ---- (A) row dots + likelihood: groups of 32 rows round-robin over the 8 warps
   float a_ll = 0.f, a_g0 = 0.f, a_g1 = 0.f, a_g2 = 0.f, a_gs = 0.f, a_gb = 0.f;
-  {
-    const int base = b0 + warp * 32;
+  for (int base = b0 + warp * 32; base < b1; base += 256) {
     float mydot = 0.f;
     for (int j0 = 0; j0 < 32; j0 += 4) {
       if (base + j0 >= b1) break;               // warp-uniform
@@ -649,9 +654,12 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
           const T* hr = h + ((size_t)net * B + b) * m.W;
           for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
             alignas(16) T hv[VEC];
+            alignas(16) float kk[VEC];
             *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), Ko[n + k], dot[u]);
+            for (int k = 0; k < VEC; k += 4) *reinterpret_cast<float4*>(kk + k) = *reinterpret_cast<const float4*>(kos + n + k);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), kk[k], dot[u]);
           }
         }
       }
@@ -1157,6 +1165,26 @@ void launch_prep(const DevModel& m, const float* params, float* derived, int n_n
   prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net, tick_step, tick_slot);
 }
 
+// rows per block such that n_net * ceil(B / R) blocks fill a whole number of waves of
+// (SM count * blocks_per_sm) resident blocks, with min_rows <= R <= max_rows
+static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int max_rows) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long slots = (long long)sms * blocks_per_sm;
+  for (int w = 1; w <= 1024; ++w) {
+    const int nb = (int)(slots * w / n_net);     // blocks per network in w waves
+    if (nb < 1) continue;
+    const int r = (B + nb - 1) / nb;
+    if (r <= max_rows) return r < min_rows ? min_rows : r;
+  }
+  return max_rows;
+}
+
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st) {
@@ -1171,12 +1199,20 @@ template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const 
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
                        int n_net, bool fast_trig, cudaStream_t st) {
-  dim3 grid((B + kEncBwdRows - 1) / kEncBwdRows, n_net);
+  static int occ[2] = {0, 0};
+  int& oc = occ[fast_trig ? 1 : 0];
+  if (!oc) {
+    if (fast_trig) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, encode_bwd_kernel<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, encode_bwd_kernel<false>, 256, 0);
+    if (oc < 1) oc = 1;
+  }
+  const int R = balanced_rows(B, n_net, oc, 64, kEncBwdMaxRows);
+  dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("encode_bwd", st);
   if (fast_trig)
-    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, grad);
   else
-    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, dfeat, grad);
+    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, grad);
 }
 
 template <typename T>
@@ -1199,10 +1235,21 @@ bool launch_head_fused(const DevModel& m, const float* params, const float* deri
   if (m.W % VEC != 0) return false;
   const int G = m.W / VEC;
   if (G > 256 || 256 % G != 0) return false;
-  const size_t smem = (size_t)(kHeadFusedRows + 2 * m.W) * sizeof(float);
-  dim3 grid((B + kHeadFusedRows - 1) / kHeadFusedRows, n_net);
+  const size_t smem = (size_t)(kHeadFusedMaxRows + 3 * m.W) * sizeof(float);
+  // rows per block: the smallest whole number of waves of resident blocks that keeps R <= max
+  static int occ_cache[2] = {0, 0}, w_cache[2] = {0, 0};
+  int& occ = occ_cache[sizeof(T) == 4 ? 0 : 1];
+  int& w_of = w_cache[sizeof(T) == 4 ? 0 : 1];
+  if (!occ || w_of != m.W) {
+    w_of = m.W;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(head_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel<T>, 256, smem);
+    if (occ < 1) occ = 1;
+  }
+  const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
+  dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("head_fused", st);
-  head_fused_kernel<T><<<grid, 256, smem, st>>>(m, params, derived, h, z, y, idx, idx_stride, B, dU, ll, grad);
+  head_fused_kernel<T><<<grid, 256, smem, st>>>(m, params, derived, h, z, y, idx, idx_stride, B, R, dU, ll, grad);
   return true;
 }
 template bool launch_head_fused<float>(const DevModel&, const float*, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, int, cudaStream_t);
