@@ -603,14 +603,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                   __uint_as_float(v[4 * j + 2]) * a.isf, __uint_as_float(v[4 * j + 3]) * a.isf);
           }
         } else {  // TC_WGRAD: grad[net*P + off + row*ld + col] += acc*isf  (split-K partial sums)
-          if (row_ok) {
-            float* o = a.outf + (size_t)net * a.out_batch + a.grad_off + (size_t)row * a.ld_out + col0;
+          // The 32x32 f32 chunk is transposed through this warp's staging tile so that every
+          // store / atomic instruction covers 32 CONSECUTIVE floats of one output row (one or
+          // two 128-byte lines) instead of one float in each of 32 rows: 32x fewer L2 requests,
+          // which is what bounds the split-K reduction at small shapes.  (Parameter leaves sit
+          // at arbitrary 4-byte offsets of the flat vector, so no 16-byte vector atomics.)
+          float* st32 = reinterpret_cast<float*>(staging + warp * 4096);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(st32 + lane * 32 + ((k ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(v[4 * k]) * a.isf, __uint_as_float(v[4 * k + 1]) * a.isf,
+                            __uint_as_float(v[4 * k + 2]) * a.isf, __uint_as_float(v[4 * k + 3]) * a.isf);
+          __syncwarp();
+          const int row_base = m_t * 128 + q * 32;
+          float* o = a.outf + (size_t)net * a.out_batch + a.grad_off + (size_t)row_base * a.ld_out + col0 + lane;
+          const bool col_ok = col0 + lane < a.n_valid;
+          const int rows_here = min(32, a.m_valid - row_base);
+          if (col_ok) {
             if (a.k_splits == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < a.n_valid) o[j] = __uint_as_float(v[j]) * a.isf;
+#pragma unroll 8
+              for (int r = 0; r < rows_here; ++r)
+                o[(size_t)r * a.ld_out] = st32[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
             } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < a.n_valid) atomicAdd(o + j, __uint_as_float(v[j]) * a.isf);
+#pragma unroll 8
+              for (int r = 0; r < rows_here; ++r)
+                atomicAdd(o + (size_t)r * a.ld_out, st32[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))]);
             }
           }
         }
