@@ -364,7 +364,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
       } else {
         launch_dgrad_simt_t<T, float>(m, 0, params, (const T*)w.dU[cur], w.dfeat, m.F, m.Fp, n_net, B, st);
       }
-      launch_encode_bwd(m, params, w.derived, x, idx, idx_stride, B, w.dfeat, grad, n_net, tc, st);
+      launch_encode_bwd(m, params, w.derived, x, idx, idx_stride, B, w.dfeat, grad, n_net, tc, /*col_major=*/tc, st);
     }
   }
   CUK();

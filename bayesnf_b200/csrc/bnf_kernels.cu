@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256)
 encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                   const float* __restrict__ derived, const float* __restrict__ x,
                   const int32_t* __restrict__ idx, int64_t idx_stride, int B, int R /* rows per block */,
-                  const float* __restrict__ dfeat, float* __restrict__ grad) {
+                  const float* __restrict__ dfeat, int64_t g_row, int64_t g_col /* element strides */,
+                  float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * R, row1 = min(B, row0 + R);
@@ -142,10 +143,10 @@ encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
 #pragma unroll 2
     for (int b = row0 + lane; b < row1; b += 32) {
       const float* xr = row_ptr(x, idx, idx_stride, net, b, m.D);
-      const float* g = dfeat + ((size_t)net * B + b) * m.Fp;
+      const float* g = dfeat + (size_t)net * B * m.Fp + (size_t)b * g_row;
       if (ui.kind == 0) {
         float sx = xr[ui.a] / dv[kDvDenom + ui.a];
-        float G = g[m.col_x + ui.a];
+        float G = g[(m.col_x + ui.a) * g_col];
         gs = fmaf(G, sx, gs);
         gl_a = fmaf(dv[kDvSX] * G, -sx, gl_a);
       } else if (ui.kind == 1) {
@@ -155,7 +156,7 @@ encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
         float sn, cs;
         if (FAST) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
         const float den = (float)(d + 1);
-        float Gc = g[m.fourier_col[i] + d], Gs = g[m.fourier_col[i] + deg + d];
+        float Gc = g[(m.fourier_col[i] + d) * g_col], Gs = g[(m.fourier_col[i] + deg + d) * g_col];
         gs += Gc * (cs / den) + Gs * (sn / den);
         float dsx = dv[kDvSFourier + i] * (c / den) * (-sn * Gc + cs * Gs);
         gl_a = fmaf(dsx, -sx, gl_a);
@@ -164,12 +165,12 @@ encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
         float sn, cs;
         if (FAST) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
         float hk = m.seasonal_h[k];
-        gs += g[m.col_seasonal + k] * (cs / hk) + g[m.col_seasonal + m.n_seasonal + k] * (sn / hk);
+        gs += g[(m.col_seasonal + k) * g_col] * (cs / hk) + g[(m.col_seasonal + m.n_seasonal + k) * g_col] * (sn / hk);
       } else {
         const int j = ui.a;
         float sa = xr[dim_a] / dv[kDvDenom + dim_a];
         float sb = xr[dim_b] / dv[kDvDenom + dim_b];
-        float G = g[m.col_inter + j];
+        float G = g[(m.col_inter + j) * g_col];
         gs = fmaf(G, sa * sb, gs);
         // d(sa*sb)/d lsa_a = -sa*sb, same for b
         gl_a = fmaf(dv[kDvSInter] * G, -sa * sb, gl_a);
@@ -1198,7 +1199,10 @@ template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const 
 
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
-                       int n_net, bool fast_trig, cudaStream_t st) {
+                       int n_net, bool fast_trig, bool col_major, cudaStream_t st) {
+  // dfeat element (net, b, c) sits at net*B*Fp + b*g_row + c*g_col: row-major from the SIMT
+  // dgrad, column-major from the tensor-core dgrad epilogue
+  const int64_t g_row = col_major ? 1 : m.Fp, g_col = col_major ? B : 1;
   static int occ[2] = {0, 0};
   int& oc = occ[fast_trig ? 1 : 0];
   if (!oc) {
@@ -1210,9 +1214,9 @@ void launch_encode_bwd(const DevModel& m, const float* params, const float* deri
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("encode_bwd", st);
   if (fast_trig)
-    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, grad);
+    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
   else
-    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, grad);
+    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
 }
 
 template <typename T>

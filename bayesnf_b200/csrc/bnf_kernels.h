@@ -15,7 +15,7 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st);
 void launch_encode_bwd(const DevModel& m, const float* params, const float* derived, const float* x,
                        const int32_t* idx, int64_t idx_stride, int B, const float* dfeat, float* grad,
-                       int n_net, bool fast_trig, cudaStream_t st);
+                       int n_net, bool fast_trig, bool col_major, cudaStream_t st);
 template <typename T>
 void launch_head(const DevModel& m, const float* params, const float* derived, const T* h,
                  const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,

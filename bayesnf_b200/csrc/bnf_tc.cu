@@ -217,6 +217,7 @@ struct TcArgs {
   const float* x; const int32_t* idx; long long idx_stride; int x_tma; int write_feat;
   // TC_DGRAD_ACT (dgrad fused with the activation backward of the previous layer)
   const bf16* zin; float* gradp; int off_bias_prev, off_ls_prev, off_actw, layer_prev;
+  int out_cm; // TC_DGRAD_F32: write outf column-major [net][col][row]
   int dbg;   // BNF_TC_DBG ablation mask (only read when compiled with -DBNF_TC_EXPERIMENT)
 };
 // Epilogue ablation hooks for scripts/epi_experiment.py: compiled out unless -DBNF_TC_EXPERIMENT.
@@ -593,6 +594,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0) {
             tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (MODE == TC_DGRAD_F32 && a.out_cm) {
+          // dfeat goes out COLUMN-major [net][col][row]: the 32 lanes (= 32 consecutive rows)
+          // write one full 128-byte line per column, and encode_bwd reads it back coalesced
+          if (row_ok) {
+            float* oc = a.outf + (size_t)net * a.out_batch + (size_t)col0 * a.m_valid + row;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) oc[(size_t)j * a.m_valid] = __uint_as_float(v[j]) * a.isf;
           }
         } else if (MODE == TC_DGRAD_F32 || MODE == TC_PLAIN_F32) {
           if (row_ok) {
@@ -981,6 +990,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   a.m_valid = B; a.n_valid = Kp;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.out0 = out_bf; a.outf = out_f32; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
+  a.out_cm = out_f32 != nullptr;   // layer-0 dgrad: dfeat is column-major (see launch_encode_bwd)
   OutMaps om;
   memset(&om, 0, sizeof(om));
   if (out_bf && (rc = make_out_map(&om.o0, out_bf, Kp, B, n_net))) return rc;
