@@ -162,15 +162,17 @@ extern "C" int bnf_plan_create(const bnf_config_t* c, bnf_plan_t** out) {
   return BNF_OK;
 }
 
+struct MapGraphKey;
+static void free_map_graph_keys(bnf_plan* p);
+
 extern "C" void bnf_plan_destroy(bnf_plan_t* p) {
   if (!p) return;
   if (p->graph_stream) {
-    cudaStreamSynchronize((cudaStream_t)p->graph_stream);
+    cudaDeviceSynchronize();
     if (p->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
-    cudaEventDestroy((cudaEvent_t)p->ev_in);
-    cudaEventDestroy((cudaEvent_t)p->ev_out);
     cudaStreamDestroy((cudaStream_t)p->graph_stream);
   }
+  free_map_graph_keys(p);
   delete p;
 }
 
@@ -283,23 +285,30 @@ int check_common(const bnf_plan* p, int prec, int n_net, int B) {
   return BNF_OK;
 }
 
+bool fused_encode_enabled() {
+  // bf16 tensor-core mode, BNF_FUSED_ENCODE=1: the feature encode is fused into the Dense_0 GEMM
+  const char* fe = getenv("BNF_FUSED_ENCODE");
+  return fe && fe[0] == '1';
+}
+// the transposed bf16 kernel copy is only read by the fused-encode kernel and the BNF_FWD_WT=1 path
+bool need_wt() { return fused_encode_enabled() || tc_fwd_uses_wt(); }
+
 // forward (+ optional backward) for n_net networks on B rows.
 template <typename T>
 int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
             const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
-            float* out_loc, float* ll, float* grad, cudaStream_t st, int32_t* tick_step = nullptr,
-            int32_t* tick_slot = nullptr) {
+            float* out_loc, float* ll, float* grad, cudaStream_t st, bool prepped = false) {
+  // prepped: the derived scalars and the bf16 weight copies are already current (the fused MAP
+  // update of the previous step wrote them)
   const DevModel& m = p->m;
   const bool tc = prec == BNF_PREC_BF16;
-  launch_prep(m, params, w.derived, n_net, tick_step, tick_slot, st);
-  // bf16 tensor-core mode, BNF_FUSED_ENCODE=1: the feature encode is fused into the Dense_0
-  // GEMM (encoder warps generate the A tile in shared memory; `feat` is written as a
+  if (!prepped) launch_prep(m, params, w.derived, n_net, nullptr, nullptr, nullptr, st);
+  // BNF_FUSED_ENCODE=1: encoder warps generate the A tile in shared memory (`feat` is written as a
   // by-product only when the backward pass needs it).  Correct and tested, but with 4 encoder
   // warps per SM it is latency-bound (profiles/README.md), so the two-kernel path is the default.
-  const char* fe = getenv("BNF_FUSED_ENCODE");
-  const bool fuse0 = tc && fe && fe[0] == '1';
+  const bool fuse0 = tc && fused_encode_enabled();
   if (!fuse0) launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
-  if (tc) tc_cast_weights(m, params, w.wt, w.wn, n_net, st);
+  if (tc && !prepped) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
   for (int l = 0; l < m.L; ++l) {
     const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
     if (tc && l == 0 && fuse0) {
@@ -307,7 +316,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
                                    (bf16*)w.z[0], (bf16*)w.h[0], n_net, B, st);
       if (rc) return fail(rc, "tc_fwd_layer0_fused failed: %s", tc_last_error());
     } else if (tc) {
-      int rc = tc_fwd_layer(p, l, params, w.derived, (const bf16*)a_in, w.wt, (bf16*)w.z[l], (bf16*)w.h[l], n_net, B, st);
+      int rc = tc_fwd_layer(p, l, params, w.derived, (const bf16*)a_in, w.wt, w.wn, (bf16*)w.z[l], (bf16*)w.h[l], n_net, B, st);
       if (rc) return fail(rc, "tc_fwd_layer failed: %s", tc_last_error());
     } else {
       launch_fwd_layer_simt_t<T>(m, l, params, w.derived, a_in, l == 0 ? m.F : m.W, l == 0 ? m.Fp : m.W,
@@ -373,11 +382,10 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
 
 int run_net_any(const bnf_plan* p, int prec, const float* params, int n_net, const float* x,
                 const float* y, const int32_t* idx, int64_t idx_stride, int B, const Ws& w,
-                float* out_loc, float* ll, float* grad, cudaStream_t st, int32_t* tick_step = nullptr,
-                int32_t* tick_slot = nullptr) {
+                float* out_loc, float* ll, float* grad, cudaStream_t st, bool prepped = false) {
   if (prec == BNF_PREC_FP32)
-    return run_net<float>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, tick_step, tick_slot);
-  return run_net<bf16>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, tick_step, tick_slot);
+    return run_net<float>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, prepped);
+  return run_net<bf16>(p, prec, params, n_net, x, y, idx, idx_stride, B, w, out_loc, ll, grad, st, prepped);
 }
 }  // namespace
 
@@ -395,6 +403,7 @@ extern "C" int bnf_forward(const bnf_plan_t* p, int32_t prec, const float* param
   if (!params || !x || !out_loc || !ws) return fail(BNF_ERR_INVALID, "null pointer");
   Ws w = carve(p, prec, n_net, B, BNF_WS_FORWARD, ws);
   if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  PdlScope pdl(true);
   return run_net_any(p, prec, params, n_net, x, nullptr, idx, idx_stride, B, w, out_loc, nullptr,
                      nullptr, (cudaStream_t)stream);
 }
@@ -413,7 +422,26 @@ extern "C" int bnf_loglik_grad(const bnf_plan_t* p, int32_t prec, const float* p
   float* grad = out_grad;
   if (grad) CU(cudaMemsetAsync(grad, 0, (size_t)n_net * p->m.P * 4, st));
   // value-only still needs r/opre scratch for the head kernel
+  PdlScope pdl(true);
   return run_net_any(p, prec, params, n_net, x, y, idx, idx_stride, B, w, nullptr, out_ll, grad, st);
+}
+
+// Signature of a captured MAP step: every pointer / scalar baked into the graph's kernel nodes.
+struct MapGraphKey {
+  const void* params; const void* am; const void* av; const void* step_count; const void* x;
+  const void* y; const void* out_loss; const void* ws;
+  int prec, n_net, B, n_total; float lr, pw; int flags, pad;
+  bool operator==(const MapGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+
+static void free_map_graph_keys(bnf_plan* p) {
+  delete (MapGraphKey*)p->graph_key;
+  delete (MapGraphKey*)p->last_key;
+  p->graph_key = p->last_key = nullptr;
+}
+static bool pdl_scope_would_enable() {
+  const char* e = getenv("BNF_PDL");
+  return !(e && e[0] == '0');
 }
 
 extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
@@ -431,66 +459,104 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
   const DevModel& m = p->m;
   const float c_ll = (float)((double)n_total / (double)B);  // target.shape[0] / batch_size
-  int32_t* slot = (int32_t*)(w.mm + 8);
-  CU(cudaMemsetAsync(slot, 0, 4, st));
-  auto one_step = [&](cudaStream_t s, const int32_t* idx_s) -> int {
-    CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, s));
-    CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, s));
-    CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, s));
-    int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, step_count, slot);
-    if (r) return r;
-    launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, s);
-    launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss, slot, s);
-    return BNF_OK;
-  };
-  // Full-batch epochs (idx == NULL) are n_steps identical launches sequences: run the
-  // first directly, capture the second into a CUDA graph and replay it.
-  const bool use_graph = idx == nullptr && n_steps >= 8 && !prof_enabled() && !getenv("BNF_NO_GRAPH");
-  int s0 = 0;
-  if (use_graph) {
-    rc = one_step(st, nullptr);
-    if (rc) return rc;
+  int32_t* slot = (int32_t*)(w.mm + 8);                      // loss-row cursor
+  unsigned int* counter = (unsigned int*)(w.mm + 9);         // map_update's block ticket
+  const bool tc = prec == BNF_PREC_BF16;
+  // The fused-encode experiment keeps the round-1 step (prep + cast every step): its Dense_0
+  // kernel reads the transposed weight copy, which the fused update does not maintain.
+  const bool legacy = (tc && fused_encode_enabled()) || getenv("BNF_LEGACY_STEP");
+
+  if (legacy) {
+    CU(cudaMemsetAsync(slot, 0, 4, st));
+    for (int s = 0; s < n_steps; ++s) {
+      const int32_t* idx_s = idx ? idx + (size_t)s * B : nullptr;
+      CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
+      CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
+      CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, st));
+      launch_tick(step_count, slot, st);
+      rc = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, st);
+      if (rc) return rc;
+      launch_map_adam(m.P, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, n_net, st);
+      launch_map_loss(n_net, w.ll, w.prior, c_ll, prior_weight, out_loss, slot, st);
+    }
     CUK();
-    s0 = 1;
-    if (!p->graph_stream) {
-      cudaStream_t gs; cudaEvent_t e1, e2;
-      CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-      p->graph_stream = gs; p->ev_in = e1; p->ev_out = e2;
-    }
-    cudaStream_t gs = (cudaStream_t)p->graph_stream;
-    if (p->graph_exec) {                       // previous call's graph: finished long ago
-      CU(cudaStreamSynchronize(gs));
-      cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
-      p->graph_exec = nullptr;
-    }
-    CU(cudaEventRecord((cudaEvent_t)p->ev_in, st));
-    CU(cudaStreamWaitEvent(gs, (cudaEvent_t)p->ev_in, 0));
-    cudaGraph_t graph = nullptr;
-    CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
-    const unsigned long long before = bnf_debug_launch_count();
-    rc = one_step(gs, nullptr);
-    const unsigned long long per_step = bnf_debug_launch_count() - before;
-    cudaError_t ce = cudaStreamEndCapture(gs, &graph);
-    if (rc || ce != cudaSuccess || !graph) {
-      if (graph) cudaGraphDestroy(graph);
-      cudaGetLastError();
-      return fail(BNF_ERR_CUDA, "CUDA graph capture of the MAP step failed (%s)", cudaGetErrorString(ce));
-    }
-    cudaGraphExec_t exec = nullptr;
-    ce = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-    p->graph_exec = exec;
-    for (int s = 1; s < n_steps; ++s) CU(cudaGraphLaunch(exec, gs));
-    // the capture counted one step's kernels without launching them; replays launch them
-    prof_add_launches((long long)per_step * (n_steps - 1) - (long long)per_step);
-    CU(cudaEventRecord((cudaEvent_t)p->ev_out, gs));
-    CU(cudaStreamWaitEvent(st, (cudaEvent_t)p->ev_out, 0));
     return BNF_OK;
   }
-  for (int s = s0; s < n_steps; ++s) {
+
+  // ---- prologue (once per call): zeroed accumulators, derived scalars, bf16 weight copies ----
+  CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
+  launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st);
+  if (tc) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
+  CUK();
+
+  // One training step: encode -> fwd GEMMs -> head -> bwd GEMMs -> encode_bwd -> fused update.
+  // Launch arguments do not depend on the step (device-side cursors), so the sequence replays
+  // as one CUDA graph; consecutive kernels are chained by programmatic dependent launch.
+  auto one_step = [&](cudaStream_t s, const int32_t* idx_s) -> int {
+    PdlScope pdl(true);
+    int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, /*prepped=*/true);
+    if (r) return r;
+    launch_map_update(m, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, w.ll, out_loss,
+                      slot, counter, w.derived, tc ? w.wn : nullptr, tc ? tc_weight_elems(m) : 0, n_net, s);
+    return BNF_OK;
+  };
+
+  // Full-batch steps (idx == NULL) replay a cached graph; it is re-captured when any baked
+  // argument changes.  A single short call with new arguments runs direct launches instead.
+  bool use_graph = idx == nullptr && !prof_enabled() && !getenv("BNF_NO_GRAPH");
+  MapGraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.params = params; key.am = am; key.av = av; key.step_count = step_count; key.x = x; key.y = y;
+  key.out_loss = out_loss; key.ws = ws; key.prec = prec; key.n_net = n_net; key.B = B; key.n_total = n_total;
+  key.lr = lr; key.pw = prior_weight; key.flags = (pdl_scope_would_enable() ? 1 : 0) | (need_wt() ? 2 : 0);
+  if (use_graph) {
+    MapGraphKey* cached = (MapGraphKey*)p->graph_key;
+    MapGraphKey* last = (MapGraphKey*)p->last_key;
+    const bool hit = p->graph_exec && cached && *cached == key;
+    const bool seen = last && *last == key;
+    if (!last) { last = new MapGraphKey(); p->last_key = last; }
+    *last = key;
+    if (!hit && n_steps < 4 && !seen) use_graph = false;     // not worth a capture yet
+    if (use_graph && !hit) {
+      if (!p->graph_stream) {
+        cudaStream_t gs;
+        CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        p->graph_stream = gs;
+      }
+      cudaStream_t gs = (cudaStream_t)p->graph_stream;
+      if (p->graph_exec) {
+        // the old graph may still be running on the caller's stream
+        CU(cudaStreamSynchronize(st));
+        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
+        p->graph_exec = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+      const unsigned long long before = bnf_debug_launch_count();
+      rc = one_step(gs, nullptr);
+      p->graph_launches = (long long)(bnf_debug_launch_count() - before);
+      cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+      prof_add_launches(-p->graph_launches);                 // captured, not launched
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return fail(BNF_ERR_CUDA, "CUDA graph capture of the MAP step failed (%s)", cudaGetErrorString(ce));
+      }
+      cudaGraphExec_t exec = nullptr;
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      p->graph_exec = exec;
+      if (!cached) { cached = new MapGraphKey(); p->graph_key = cached; }
+      *cached = key;
+    }
+  }
+  if (use_graph) {
+    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec, st));
+    prof_add_launches(p->graph_launches * n_steps);
+    return BNF_OK;
+  }
+  for (int s = 0; s < n_steps; ++s) {
     // idx == NULL: every step is a full pass over rows [0, B) (full-batch epochs)
     rc = one_step(st, idx ? idx + (size_t)s * B : nullptr);
     if (rc) return rc;
@@ -522,7 +588,10 @@ extern "C" int bnf_vi_step(const bnf_plan_t* p, int32_t prec, float* mu, float* 
   CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
   CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
   CU(cudaMemsetAsync(w.vloss, 0, (size_t)n_net * 4, st));
-  rc = run_net_any(p, prec, w.vz, n_net, x, y, idx, 0, B, w, nullptr, w.ll, w.grad, st);
+  {
+    PdlScope pdl(true);
+    rc = run_net_any(p, prec, w.vz, n_net, x, y, idx, 0, B, w, nullptr, w.ll, w.grad, st);
+  }
   if (rc) return rc;
   launch_vi_adam(m.P, E, S, mu, rho, am, av, w.vz, w.veps, w.grad, step_count, c, lr, w.vloss, st);
   launch_vi_loss(E, S, w.vloss, w.ll, c, out_loss, st);

@@ -22,6 +22,15 @@ constexpr int kDvSSeas = 41;
 constexpr int kDvSInter = 42;
 constexpr int kDvSFourier = 43; // + input dim i
 
+// ---- programmatic dependent launch (PDL) --------------------------------------
+// Every kernel of a training step starts with pdl_trigger(); <prologue>; pdl_wait():
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization the next kernel's CTAs may
+// become resident (barrier init, TMEM alloc, tensor-map prefetch) while this one drains, and
+// griddepcontrol.wait blocks them until every prerequisite grid has completed and flushed.
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float softplus_f(float x) {
   // jax.nn.softplus == logaddexp(x, 0)
   return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));

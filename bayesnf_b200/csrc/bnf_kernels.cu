@@ -17,33 +17,42 @@ namespace bnf {
 // =============================================================================
 // prep: per-network derived scalars
 // =============================================================================
-__global__ void prep_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
-                            float* __restrict__ derived, int n_net, int32_t* tick_step,
-                            int32_t* tick_slot) {
+// One network's derived scalars, computed by the first 32 threads t = 0..31 of the caller.
+// Loads bypass L1 (__ldcg): map_update_kernel calls this right after other blocks of the same
+// grid wrote the parameters.
+__device__ __forceinline__ void prep_one(const DevModel& m, const float* p, float* dv, int t) {
+  if (t == 0) {
+    dv[kDvActW] = sigmoid_f(__ldcg(p + m.off_actw));
+    dv[kDvSOut] = softplus_f(__ldcg(p + m.off_out_scale));
+    dv[kDvSigma] = 0.01f + expf(__ldcg(p));
+    dv[kDvShape] = softplus_f(__ldcg(p + 1));
+    dv[kDvPi] = 1.f / (1.f + expf(-__ldcg(p + 2)));  // literal models.py:184
+    dv[kDvSX] = softplus_f(__ldcg(p + m.off_scale_x));
+    dv[kDvSSeas] = m.off_scale_seasonal >= 0 ? softplus_f(__ldcg(p + m.off_scale_seasonal)) : 0.f;
+    dv[kDvSInter] = m.off_scale_inter >= 0 ? softplus_f(__ldcg(p + m.off_scale_inter)) : 0.f;
+  }
+  if (t < m.L) dv[kDvSLayer + t] = softplus_f(__ldcg(p + m.off_layer_scale[t]));
+  if (t < m.D) {
+    dv[kDvDenom + t] = m.input_scales[t] * expf(__ldcg(p + m.off_lsa + t));
+    dv[kDvSFourier + t] = m.fourier_scale_off[t] >= 0 ? softplus_f(__ldcg(p + m.fourier_scale_off[t])) : 0.f;
+  }
+}
+
+// zero_acc (optional): [ll | prior] accumulators of n_net floats each at zero_acc / zero_acc2,
+// zero_cursors (optional): two int32 cursors -- the prologue of bnf_map_steps in one launch.
+__global__ void prep_kernel(const __grid_constant__ DevModel m, const float* params,
+                            float* __restrict__ derived, int n_net, float* zero_acc, float* zero_acc2,
+                            int32_t* zero_cursors) {
+  pdl_trigger();
+  pdl_wait();
   int net = blockIdx.x;
   if (net >= n_net) return;
-  if (net == 0 && threadIdx.x == 0) {          // optional step tick (Adam count, loss row cursor)
-    if (tick_step) *tick_step += 1;
-    if (tick_slot) *tick_slot += 1;
+  if (threadIdx.x == 0) {
+    if (zero_acc) zero_acc[net] = 0.f;
+    if (zero_acc2) zero_acc2[net] = 0.f;
+    if (net == 0 && zero_cursors) { zero_cursors[0] = 0; zero_cursors[1] = 0; }
   }
-  const float* p = params + (size_t)net * m.P;
-  float* dv = derived + (size_t)net * kDerivedStride;
-  int t = threadIdx.x;
-  if (t == 0) {
-    dv[kDvActW] = sigmoid_f(p[m.off_actw]);
-    dv[kDvSOut] = softplus_f(p[m.off_out_scale]);
-    dv[kDvSigma] = 0.01f + expf(p[0]);
-    dv[kDvShape] = softplus_f(p[1]);
-    dv[kDvPi] = 1.f / (1.f + expf(-p[2]));  // literal models.py:184
-    dv[kDvSX] = softplus_f(p[m.off_scale_x]);
-    dv[kDvSSeas] = m.off_scale_seasonal >= 0 ? softplus_f(p[m.off_scale_seasonal]) : 0.f;
-    dv[kDvSInter] = m.off_scale_inter >= 0 ? softplus_f(p[m.off_scale_inter]) : 0.f;
-  }
-  if (t < m.L) dv[kDvSLayer + t] = softplus_f(p[m.off_layer_scale[t]]);
-  if (t < m.D) {
-    dv[kDvDenom + t] = m.input_scales[t] * expf(p[m.off_lsa + t]);
-    dv[kDvSFourier + t] = m.fourier_scale_off[t] >= 0 ? softplus_f(p[m.fourier_scale_off[t]]) : 0.f;
-  }
+  prep_one(m, params + (size_t)net * m.P, derived + (size_t)net * kDerivedStride, threadIdx.x);
 }
 
 // =============================================================================
@@ -58,12 +67,14 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
                               const float* __restrict__ x, const int32_t* __restrict__ idx,
                               int64_t idx_stride, int B, T* __restrict__ feat) {
   extern __shared__ float tile[];  // [kEncRows][Fp+1]
+  pdl_trigger();
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * kEncRows;
   const float* dv = derived + (size_t)net * kDerivedStride;
   const int ld = m.Fp + 1;
   for (int e = threadIdx.x; e < kEncRows * ld; e += blockDim.x) tile[e] = 0.f;
   __syncthreads();
+  pdl_wait();
   const int U = num_units(m);
   const float two_pi = 6.283185307179586f;
   for (int w = threadIdx.x; w < kEncRows * U; w += blockDim.x) {
@@ -123,6 +134,8 @@ encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
                   const float* __restrict__ dfeat, int64_t g_row, int64_t g_col /* element strides */,
                   float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
+  pdl_trigger();
+  pdl_wait();
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * R, row1 = min(B, row0 + R);
   const float* dv = derived + (size_t)net * kDerivedStride;
@@ -211,6 +224,8 @@ gemm_simt_kernel(const TA* __restrict__ A, size_t a_batch, int lda, const TB* __
                  size_t b_batch, int ldb, int M, int N, int K, Epi epi) {
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, net = blockIdx.z;
   A += (size_t)net * a_batch;
@@ -298,8 +313,8 @@ void launch_fwd_layer_simt(const DevModel& m, int layer, const float* params, co
                 layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W, z, h, (size_t)B * m.W, m.W};
   dim3 grid((m.W + 63) / 64, (B + 63) / 64, n_net);
   BNF_PROF("gemm_simt_fwd", st);
-  gemm_simt_kernel<T, float, true, false, EpiFwd<T>><<<grid, 256, 0, st>>>(
-      a_in, (size_t)B * lda, lda, params + m.off_kernel[layer], (size_t)m.P, m.W, B, m.W, K, epi);
+  launch_k(gemm_simt_kernel<T, float, true, false, EpiFwd<T>>, grid, dim3(256), 0, st,
+           a_in, (size_t)B * lda, lda, params + m.off_kernel[layer], (size_t)m.P, m.W, B, m.W, K, epi);
 }
 template <typename T, typename TO>
 void launch_dgrad_simt(const DevModel& m, int layer, const float* params, const T* dU, TO* out,
@@ -308,8 +323,8 @@ void launch_dgrad_simt(const DevModel& m, int layer, const float* params, const 
   EpiStoreScaled<TO> epi{out, (size_t)B * ld_out, ld_out, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
   dim3 grid((Kout + 63) / 64, (B + 63) / 64, n_net);
   BNF_PROF("gemm_simt_dgrad", st);
-  gemm_simt_kernel<T, float, true, true, EpiStoreScaled<TO>><<<grid, 256, 0, st>>>(
-      dU, (size_t)B * m.W, m.W, params + m.off_kernel[layer], (size_t)m.P, m.W, B, Kout, m.W, epi);
+  launch_k(gemm_simt_kernel<T, float, true, true, EpiStoreScaled<TO>>, grid, dim3(256), 0, st,
+           dU, (size_t)B * m.W, m.W, params + m.off_kernel[layer], (size_t)m.P, m.W, B, Kout, m.W, epi);
 }
 template <typename T>
 void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int lda, const T* dU,
@@ -317,8 +332,8 @@ void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int
   EpiWgrad epi{grad, m.P, m.off_kernel[layer], m.W, layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W};
   dim3 grid((m.W + 63) / 64, (Kin + 63) / 64, n_net);
   BNF_PROF("gemm_simt_wgrad", st);
-  gemm_simt_kernel<T, T, false, false, EpiWgrad><<<grid, 256, 0, st>>>(
-      a_in, (size_t)B * lda, lda, dU, (size_t)B * m.W, m.W, Kin, m.W, B, epi);
+  launch_k(gemm_simt_kernel<T, T, false, false, EpiWgrad>, grid, dim3(256), 0, st,
+           a_in, (size_t)B * lda, lda, dU, (size_t)B * m.W, m.W, Kin, m.W, B, epi);
 }
 
 // =============================================================================
@@ -333,6 +348,8 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
             const int32_t* __restrict__ idx, int64_t idx_stride, int B, float* __restrict__ out_loc,
             float* __restrict__ opre_out, float* __restrict__ r_out, float* __restrict__ ll,
             float* __restrict__ grad) {
+  pdl_trigger();
+  pdl_wait();
   const int net = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* p = params + (size_t)net * m.P;
@@ -472,6 +489,8 @@ act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __res
                const float* __restrict__ r, T* __restrict__ dU /* in: dh (unless head), out: dU */,
                int B, float* __restrict__ grad) {
   __shared__ float red[2][4];
+  pdl_trigger();
+  pdl_wait();
   const int net = blockIdx.z;
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int b0 = blockIdx.y * kActRows, b1 = min(B, b0 + kActRows);
@@ -534,9 +553,11 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
   constexpr bool FAST = FastMath<T>::value;
   __shared__ float red[2][8];
   extern __shared__ float colsum[];            // [W] bias grads (+ [W] Dense_L kernel grads at the head)
+  pdl_trigger();
   const int net = blockIdx.y;
   for (int i = threadIdx.x; i < (IS_HEAD ? 2 : 1) * m.W; i += blockDim.x) colsum[i] = 0.f;
   __syncthreads();
+  pdl_wait();
   const int G = m.W / VEC;                     // column groups per row
   const int cg = threadIdx.x % G;
   const int rstep = 256 / G;                   // rows covered per pass
@@ -631,6 +652,8 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
   float* colsum = fsm + kHeadFusedMaxRows;      // [2W] bias / Dense_L kernel column sums
   float* kos = colsum + 2 * m.W;                // [W] Dense_L kernel
   __shared__ float hred[8][8];
+  pdl_trigger();
+  pdl_wait();
   const int net = blockIdx.y;
   const int b0 = blockIdx.x * R, b1 = min(B, b0 + R);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -847,6 +870,99 @@ __global__ void map_loss_kernel(int n_net, const float* ll, const float* prior, 
   if (j < n_net) {
     out[j] = prior_weight == 0.f ? -(ll[j] * c_ll) : -(ll[j] * c_ll + prior[j] * prior_weight);
   }
+}
+
+// -----------------------------------------------------------------------------
+// Fused MAP update = the whole tail of a training step in one launch:
+//   prior gradient + optax.adam (as map_adam_kernel), gradient buffer zeroed for the next
+//   step, bf16 restaging of the hidden kernels (natural (in,out) layout = the same element
+//   order as the f32 master, so the store is coalesced), and -- by the LAST block to finish
+//   (ticket counter) -- the step's loss row, the reset of the loglik / prior accumulators, the
+//   Adam step count / loss-row cursor ticks and the derived scalars of the NEXT step.
+// A training step is then encode -> GEMMs -> head -> GEMMs -> encode_bwd -> this kernel, with
+// no memset / prep / cast / loss nodes in between (inference.py:599-608 per step).
+// step_count holds the number of COMPLETED steps on entry; slot the loss row to write.
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __restrict__ am,
+                  float* __restrict__ av, float* __restrict__ grad, int32_t* step_count, float c_ll,
+                  float prior_weight, float lr, float* prior, float* ll, float* __restrict__ out_loss,
+                  int32_t* slot, unsigned int* counter, float* __restrict__ derived,
+                  __nv_bfloat16* __restrict__ wn, size_t w_per_net, int n_net) {
+  __shared__ float pred[8];
+  __shared__ int s_last;
+  pdl_trigger();
+  pdl_wait();
+  const int net = blockIdx.y, P = m.P;
+  const int t = __ldcg(step_count) + 1;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  float lp = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)net * P + i;
+    const float th = params[o];
+    const float gl = grad[o];
+    grad[o] = 0.f;
+    float g = -(c_ll * gl);
+    if (prior_weight != 0.f) {
+      const float zz = th - (i == 1 ? -1.5f : 0.f);
+      lp += -zz - 2.f * softplus_f(-zz);
+      g = -(c_ll * gl + prior_weight * (-tanhf(0.5f * zz)));
+    }
+    const float mm = (1.f - b1) * g + b1 * am[o];
+    const float vv = (1.f - b2) * (g * g) + b2 * av[o];
+    am[o] = mm;
+    av[o] = vv;
+    const float th_new = th + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + eps));
+    params[o] = th_new;
+    if (wn) {
+      // hidden-layer kernel leaf?  wn = [layer][Kp][W] per network, rows >= fan_in stay zero
+      for (int l = 0; l < m.L; ++l) {
+        const int rel = i - m.off_kernel[l];
+        const int cnt = (l == 0 ? m.F : m.W) * m.W;
+        if (rel >= 0 && rel < cnt) {
+          const size_t lo = l == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(l - 1) * m.W * m.W;
+          wn[(size_t)net * w_per_net + lo + rel] = __float2bfloat16_rn(th_new);
+          break;
+        }
+      }
+    }
+  }
+  if (prior_weight != 0.f) {
+    lp = warp_sum(lp);
+    if ((threadIdx.x & 31) == 0) pred[threadIdx.x >> 5] = lp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < 8; ++i) tot += pred[i];
+      atomicAdd(&prior[net], tot);
+    }
+  }
+  // ---- last block of the grid: loss row, accumulator reset, ticks, next step's derived ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last = ticket == gridDim.x * gridDim.y - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int row = __ldcg(slot);
+  for (int j = threadIdx.x; j < n_net; j += blockDim.x) {
+    const float l = __ldcg(ll + j), pr = __ldcg(prior + j);
+    out_loss[(size_t)row * n_net + j] = prior_weight == 0.f ? -(l * c_ll) : -(l * c_ll + pr * prior_weight);
+    ll[j] = 0.f;
+    prior[j] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    *slot = row + 1;
+    *step_count = t;
+    *counter = 0u;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < n_net; j += 8)
+    prep_one(m, params + (size_t)j * P, derived + (size_t)j * kDerivedStride, lane);
 }
 
 // =============================================================================
@@ -1160,10 +1276,10 @@ nb_quantile_kernel(const float* __restrict__ loc, const float* __restrict__ shap
 // =============================================================================
 // host-side launch wrappers
 // =============================================================================
-void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, int32_t* tick_step,
-                 int32_t* tick_slot, cudaStream_t st) {
+void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, float* zero_acc,
+                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st) {
   BNF_PROF("prep", st);
-  prep_kernel<<<n_net, 32, 0, st>>>(m, params, derived, n_net, tick_step, tick_slot);
+  launch_k(prep_kernel, dim3(n_net), dim3(32), 0, st, m, params, derived, n_net, zero_acc, zero_acc2, zero_cursors);
 }
 
 // rows per block such that n_net * ceil(B / R) blocks fill a whole number of waves of
@@ -1192,7 +1308,7 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
   size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
   BNF_PROF("encode", st);
-  encode_kernel<T><<<grid, 256, smem, st>>>(m, derived, x, idx, idx_stride, B, feat);
+  launch_k(encode_kernel<T>, grid, dim3(256), smem, st, m, derived, x, idx, idx_stride, B, feat);
 }
 template void launch_encode<float>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, float*, int, cudaStream_t);
 template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, __nv_bfloat16*, int, cudaStream_t);
@@ -1214,9 +1330,9 @@ void launch_encode_bwd(const DevModel& m, const float* params, const float* deri
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("encode_bwd", st);
   if (fast_trig)
-    encode_bwd_kernel<true><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
+    launch_k(encode_bwd_kernel<true>, grid, dim3(256), 0, st, m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
   else
-    encode_bwd_kernel<false><<<grid, 256, 0, st>>>(m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
+    launch_k(encode_bwd_kernel<false>, grid, dim3(256), 0, st, m, params, derived, x, idx, idx_stride, B, R, dfeat, g_row, g_col, grad);
 }
 
 template <typename T>
@@ -1225,7 +1341,7 @@ void launch_head(const DevModel& m, const float* params, const float* derived, c
                  float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st) {
   dim3 grid((B + kHeadRows - 1) / kHeadRows, n_net);
   BNF_PROF("head", st);
-  head_kernel<T><<<grid, 256, 0, st>>>(m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
+  launch_k(head_kernel<T>, grid, dim3(256), 0, st, m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
 }
 template void launch_head<float>(const DevModel&, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 template void launch_head<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
@@ -1253,7 +1369,7 @@ bool launch_head_fused(const DevModel& m, const float* params, const float* deri
   const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("head_fused", st);
-  head_fused_kernel<T><<<grid, 256, smem, st>>>(m, params, derived, h, z, y, idx, idx_stride, B, R, dU, ll, grad);
+  launch_k(head_fused_kernel<T>, grid, dim3(256), smem, st, m, params, derived, h, z, y, idx, idx_stride, B, R, dU, ll, grad);
   return true;
 }
 template bool launch_head_fused<float>(const DevModel&, const float*, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, int, cudaStream_t);
@@ -1269,20 +1385,20 @@ void launch_act_bwd(const DevModel& m, int layer, bool is_head, const float* par
     dim3 grid((B + kActVecRows - 1) / kActVecRows, n_net);
     if (is_head) {
       BNF_PROF("act_bwd", st);
-      act_bwd_vec_kernel<T, true><<<grid, 256, 2 * m.W * sizeof(float), st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+      launch_k(act_bwd_vec_kernel<T, true>, grid, dim3(256), 2 * m.W * sizeof(float), st, m, layer, params, derived, z, h, r, dU, B, grad);
     } else {
       BNF_PROF("act_bwd", st);
-      act_bwd_vec_kernel<T, false><<<grid, 256, m.W * sizeof(float), st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+      launch_k(act_bwd_vec_kernel<T, false>, grid, dim3(256), m.W * sizeof(float), st, m, layer, params, derived, z, h, r, dU, B, grad);
     }
     return;
   }
   dim3 grid((m.W + 127) / 128, (B + kActRows - 1) / kActRows, n_net);
   if (is_head) {
     BNF_PROF("act_bwd", st);
-    act_bwd_kernel<T, true><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+    launch_k(act_bwd_kernel<T, true>, grid, dim3(128), 0, st, m, layer, params, derived, z, h, r, dU, B, grad);
   } else {
     BNF_PROF("act_bwd", st);
-    act_bwd_kernel<T, false><<<grid, 128, 0, st>>>(m, layer, params, derived, z, h, r, dU, B, grad);
+    launch_k(act_bwd_kernel<T, false>, grid, dim3(128), 0, st, m, layer, params, derived, z, h, r, dU, B, grad);
   }
 }
 template void launch_act_bwd<float>(const DevModel&, int, bool, const float*, const float*, const float*, const float*, const float*, float*, int, float*, int, cudaStream_t);
@@ -1330,6 +1446,16 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
   BNF_PROF("map_adam", st);
   map_adam_kernel<<<dim3(bx, n_net), 256, 0, st>>>(P, params, am, av, g_ll, step_count, c_ll,
                                                    prior_weight, lr, prior_out);
+}
+void launch_map_update(const DevModel& m, float* params, float* am, float* av, float* grad,
+                       int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
+                       float* ll, float* out_loss, int32_t* slot, unsigned int* counter, float* derived,
+                       __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st) {
+  int bx = (m.P + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  BNF_PROF("map_update", st);
+  launch_k(map_update_kernel, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
+           prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st) {

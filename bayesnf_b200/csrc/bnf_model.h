@@ -53,8 +53,9 @@ struct bnf_plan {
   int sm_count;
   // CUDA-graph replay of one full-batch MAP step (see bnf_map_steps); mutable
   // cache, so graph mode is single-threaded per plan.
-  mutable void* graph_stream = nullptr;
+  mutable void* graph_stream = nullptr;   // capture stream (nothing executes on it)
   mutable void* graph_exec = nullptr;
-  mutable void* ev_in = nullptr;
-  mutable void* ev_out = nullptr;
+  mutable void* graph_key = nullptr;      // MapGraphKey of graph_exec
+  mutable void* last_key = nullptr;       // MapGraphKey of the previous full-batch call
+  mutable long long graph_launches = 0;   // kernel nodes per replay
 };

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -35,6 +36,16 @@ void prof_end(cudaStream_t st, int slot) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (slot >= 0 && slot < (int)g_recs.size()) cudaEventRecord(g_recs[slot].b, st);
 }
+
+// PDL scope (see bnf_prof.h)
+static thread_local bool g_pdl = false;
+static bool pdl_env() {
+  const char* e = getenv("BNF_PDL");      // read per scope: tests flip it
+  return !(e && e[0] == '0');
+}
+bool pdl_active() { return g_pdl && !prof_enabled(); }
+PdlScope::PdlScope(bool on) : prev(g_pdl) { g_pdl = on && pdl_env(); }
+PdlScope::~PdlScope() { g_pdl = prev; }
 
 }  // namespace bnf
 

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256)
 cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                     bf16* __restrict__ wt, bf16* __restrict__ wn, size_t per_net) {
   __shared__ float tile[32][33];
+  pdl_trigger();
+  pdl_wait();
   const int net = blockIdx.z / m.L, layer = blockIdx.z % m.L;
   const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -66,6 +68,7 @@ cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict_
     tile[r][tx] = v;
     if (k < Kp && n < m.W) wn[base + (size_t)k * m.W + n] = __float2bfloat16_rn(v);
   }
+  if (wt == nullptr) return;     // forward reads wn MN-major: no transposed copy
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     int n = n0 + r, k = k0 + tx;
@@ -73,11 +76,12 @@ cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict_
   }
 }
 
+// wt may be NULL (only the natural-layout copy is needed)
 void tc_cast_weights(const DevModel& m, const float* params, bf16* wt, bf16* wn, int n_net, cudaStream_t st) {
   int kmax = m.Fp > m.W ? m.Fp : m.W;
   dim3 grid((m.W + 31) / 32, (kmax + 31) / 32, n_net * m.L);
   BNF_PROF("cast_weights", st);
-  cast_weights_kernel<<<grid, 256, 0, st>>>(m, params, wt, wn, tc_weight_elems(m));
+  launch_k(cast_weights_kernel, grid, dim3(256), 0, st, m, params, wt, wn, tc_weight_elems(m));
 }
 
 // -----------------------------------------------------------------------------
@@ -238,7 +242,9 @@ constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-enc
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kXTileBytes = 128 * kMaxD * 4;
 // A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
-// encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major.
+// encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major;
+// 3 = A K-major, B MN-major (forward straight from the natural (in,out) bf16 kernel copy, so the
+// transposed staging copy and its cast kernel are not needed).
 // CTA2: a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
 // from L2 drops by a third and the ring gets deeper (32 KB stages).
@@ -260,7 +266,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
   using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2>;
-  constexpr bool MN_MAJOR = A_MODE == 1;
+  constexpr bool A_MN = A_MODE == 1;                  // A operand MN-major
+  constexpr bool B_MN = A_MODE == 1 || A_MODE == 3;   // B operand MN-major
   constexpr bool ENCODE = A_MODE == 2;
   static_assert(!(CTA2 && ENCODE), "the fused encode kernel is single-CTA");
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
@@ -278,6 +285,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();                       // the next kernel's CTAs may start their own prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], ENCODE ? 1 + 32 * kEncWarps : (CTA2 ? 2 : 1));
@@ -312,6 +320,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (CTA2) cluster_sync_all();        // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                          // everything above overlapped the previous kernel's tail
 
   // work items: (net, m unit, split, n tile); a unit is one 128-row tile, or a PAIR of them for
   // a CTA pair (this CTA takes rows of tile 2*unit + cta_rank)
@@ -356,26 +365,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
               else mbar_arrive_remote(&full[stage], 0);
               const int nb = n_t * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);   // this CTA's half of B
-              if (!MN_MAJOR) {
+              if (!A_MN) {
                 tma_load_3d_2sm(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
-                tma_load_3d_2sm(sb, &map_b, &full[stage], kb * 64, nb, net);
               } else {
                 for (int j = 0; j < 2; ++j)
                   tma_load_3d_2sm(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+              }
+              if (!B_MN) {
+                tma_load_3d_2sm(sb, &map_b, &full[stage], kb * 64, nb, net);
+              } else {
                 for (int j = 0; j < BLOCK_N / 128; ++j)
                   tma_load_3d_2sm(sb + j * 8192, &map_b, &full[stage], nb + j * 64, kb * 64, net);
               }
-            } else if (!MN_MAJOR) {
-              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-              tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
-              tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
             } else {
               mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-              // MN-major: boxes of [64 reduction rows][64 MN elements]
-              for (int j = 0; j < 2; ++j)
-                tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
+              if (!A_MN) {
+                tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+              } else {   // MN-major: boxes of [64 reduction rows][64 MN elements]
+                for (int j = 0; j < 2; ++j)
+                  tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+              }
+              if (!B_MN) {
+                tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
+              } else {
+                for (int j = 0; j < BLOCK_N / 64; ++j)
+                  tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
+              }
             }
           }
           __syncwarp();
@@ -387,14 +402,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
     if (!CTA2 || cta_rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accum, bf16 x bf16
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
-                             ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                             ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                              ((uint32_t)((CTA2 ? 256 : 128) >> 4) << 24);
       // smem descriptors differ only in the 14-bit start address: build them once and add offsets
-      const uint64_t adesc0 = MN_MAJOR ? make_smem_desc(smem_u32(smem), 8192, 1024)
-                                       : make_smem_desc(smem_u32(smem), 16, 1024);
-      const uint64_t bdesc0 = adesc0 + (uint64_t)(Cfg::kABytes >> 4);
-      constexpr uint32_t kStep = (MN_MAJOR ? 2048 : 32) >> 4;      // one UMMA_K=16 slice
+      const uint64_t adesc0 = A_MN ? make_smem_desc(smem_u32(smem), 8192, 1024)
+                                   : make_smem_desc(smem_u32(smem), 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(smem_u32(smem) + Cfg::kABytes, 8192, 1024)
+                                   : make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 1024);
+      constexpr uint32_t kStepA = (A_MN ? 2048 : 32) >> 4;      // one UMMA_K=16 slice
+      constexpr uint32_t kStepB = (B_MN ? 2048 : 32) >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = tile0; t < total_tiles; t += tile_step) {
@@ -413,8 +430,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t so = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (CTA2) umma_bf16_2sm(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(d_tmem, adesc0 + so + k * kStep, bdesc0 + so + k * kStep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CTA2) umma_bf16_2sm(d_tmem, adesc0 + so + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc0 + so + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             if (CTA2) umma_commit_2sm(&empty[stage]);   // frees the slot in BOTH CTAs
             else umma_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
@@ -829,13 +846,18 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
   cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_active()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   const DevModel& dmr = dm ? *dm : dm_zero;
 #ifdef BNF_TC_EXPERIMENT
   TcArgs ax = a;
@@ -878,6 +900,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
   } else if constexpr (MN == 1) {
     if (a.mode == TC_WGRAD) return launch_tc_m<BLOCK_N, 1, TC_WGRAD>(ma, mb, om, a, sm, st, dm);
     return launch_tc_m<BLOCK_N, 1, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
+  } else if constexpr (MN == 3) {
+    if (a.mode == TC_FWD) return launch_tc_m<BLOCK_N, 3, TC_FWD>(ma, mb, om, a, sm, st, dm);
+    return launch_tc_m<BLOCK_N, 3, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else {
     switch (a.mode) {
       case TC_FWD: return launch_tc_m<BLOCK_N, 0, TC_FWD>(ma, mb, om, a, sm, st, dm);
@@ -909,10 +934,18 @@ static int sm_count_of(const bnf_plan* p) {
   return n;
 }
 
+// The forward B operand: the natural (in,out) bf16 copy `wn` read MN-major (default), or the
+// transposed copy `wt` read K-major (BNF_FWD_WT=1, the round-1 layout; kept for A/B timing).
+bool tc_fwd_uses_wt() {
+  const char* e = getenv("BNF_FWD_WT");   // read per call: tests flip it
+  return e && e[0] == '1';
+}
+
 int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived, const bf16* a_in,
-                 const bf16* wt, bf16* z, bf16* h, int n_net, int B, cudaStream_t st) {
+                 const bf16* wt, const bf16* wn, bf16* z, bf16* h, int n_net, int B, cudaStream_t st) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
+  const bool use_wt = tc_fwd_uses_wt() || wn == nullptr;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
   if (rc) return rc;
@@ -920,8 +953,13 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   memset(&a, 0, sizeof(a));
   a.mode = TC_FWD; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1; a.k_blocks = Kp / 64;
-  // a CTA pair loads the B tile in two halves (one per CTA)
-  rc = make_map(&mb, wt + layer_off(m, layer), Kp, m.W, n_net, Kp, tc_weight_elems(m), want_cta2(a, bn) ? bn / 2 : bn);
+  if (use_wt) {
+    // a CTA pair loads the B tile in two halves (one per CTA)
+    rc = make_map(&mb, wt + layer_off(m, layer), Kp, m.W, n_net, Kp, tc_weight_elems(m), want_cta2(a, bn) ? bn / 2 : bn);
+  } else {
+    // wn [Kp][W]: boxes of [64 reduction rows][64 output columns]
+    rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m), 64);
+  }
   if (rc) return rc;
   a.m_valid = B; a.n_valid = m.W;
   a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
@@ -931,7 +969,8 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   memset(&om, 0, sizeof(om));
   if ((rc = make_out_map(&om.o1, h, m.W, B, n_net))) return rc;
   if (z && (rc = make_out_map(&om.o0, z, m.W, B, n_net))) return rc;
-  return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
+  if (use_wt) return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
+  return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
 
 // Fused feature encode + Dense_0 (models.py:216-268 for the first layer): the A operand is
@@ -1034,7 +1073,7 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
 int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_net, int M, int N, int K,
                   int sm_count, cudaStream_t st) {
   const int bn = pick_block_n(N);
-  if (N % 64 != 0 || (K % 64 != 0 && !mn_major)) return tc_fail(BNF_ERR_INVALID, "N, K must be multiples of 64");
+  if (N % 64 != 0 || (K % 64 != 0 && mn_major != 1)) return tc_fail(BNF_ERR_INVALID, "N, K must be multiples of 64");
   CUtensorMap ma, mb;
   int rc;
   TcArgs a;
@@ -1044,6 +1083,11 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
   a.m_valid = M; a.n_valid = N; a.outf = C; a.out_batch = (long long)M * N; a.ld_out = N;
   OutMaps om;
   memset(&om, 0, sizeof(om));
+  if (mn_major == 2) {   // A [net][M][K] (K-major), B [net][K][N] (MN-major)
+    if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
+    if ((rc = make_map(&mb, Bm, N, K, n_net, N, (uint64_t)N * K, 64))) return rc;
+    return launch_tc_n<3>(bn, ma, mb, om, a, sm_count, st);
+  }
   if (!mn_major) {   // A [net][M][K], B [net][N][K]
     if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
     if ((rc = make_map(&mb, Bm, K, N, n_net, K, (uint64_t)N * K, want_cta2(a, bn) ? bn / 2 : bn))) return rc;

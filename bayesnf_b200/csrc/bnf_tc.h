@@ -16,9 +16,11 @@ size_t tc_weight_elems(const DevModel& m);
 // forward GEMM), wn = [layer][Kp][W] (natural (in,out); K-major for dgrad).
 void tc_cast_weights(const DevModel& m, const float* params, __nv_bfloat16* wt, __nv_bfloat16* wn,
                      int n_net, cudaStream_t st);
+// B operand: `wn` read MN-major (default) or `wt` read K-major (BNF_FWD_WT=1 / wn == NULL)
 int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived,
-                 const __nv_bfloat16* a_in, const __nv_bfloat16* wt, __nv_bfloat16* z,
-                 __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
+                 const __nv_bfloat16* a_in, const __nv_bfloat16* wt, const __nv_bfloat16* wn,
+                 __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
+bool tc_fwd_uses_wt();
 int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
                         const int32_t* idx, int64_t idx_stride, const __nv_bfloat16* wt,
                         __nv_bfloat16* feat, __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B,

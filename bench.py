@@ -119,7 +119,8 @@ class ClockSampler(threading.Thread):
 
 
 NCU_SUMMARY = {'chickenpox_map_e8': 'ncu_chickenpox_r1L_summary.csv', 'wind_map_e16': 'ncu_wind_tc_gemm_r1L_summary.csv'}
-NCU_PATTERN = {'tc_gemm_fwd': ', 0, 0, ', 'tc_gemm_dgrad': ', 0, 5, ', 'tc_gemm_wgrad': ', 1, 3, '}
+# kernel class -> template-argument substrings <BLOCK_N, A_MODE, MODE, CTA2> of its instantiations
+NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, ', ', 0, 0, '), 'tc_gemm_dgrad': (', 0, 5, ',), 'tc_gemm_wgrad': (', 1, 3, ',)}
 
 
 def ncu_traffic_gb(workload, kernel):
@@ -134,7 +135,7 @@ def ncu_traffic_gb(workload, kernel):
   ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
   scale = {'Gbyte': 1.0, 'Mbyte': 1e-3, 'Kbyte': 1e-6, 'byte': 1e-9}[units[ir]]
   vals = [(float(r[ir]) + float(r[iw])) * scale for r in rows[2:]
-          if NCU_PATTERN[kernel] in r[ik] and r[ik].startswith('void tc_gemm_kernel<256')]
+          if any(pat in r[ik] for pat in NCU_PATTERN[kernel]) and r[ik].startswith('void tc_gemm_kernel<256')]
   return max(vals) if vals else None      # the widest launch of that class (hidden layers)
 
 

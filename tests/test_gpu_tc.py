@@ -245,3 +245,69 @@ def test_estimators_bf16_end_to_end(cuda):
   assert est.losses_.shape == (1, 2, 2 * (len(df) // 480)) and np.isfinite(est.losses_).all()
   means, q = est.predict(df.iloc[:50])
   assert means.shape == (1, 3, 2, 50) and np.isfinite(q[0]).all()
+
+
+@pytest.mark.parametrize('cta2', ['0', '1'])
+@pytest.mark.parametrize('nets,m,n,k', [(1, 128, 64, 64), (1, 256, 256, 64), (2, 300, 256, 256),
+                                        (3, 200, 128, 192), (2, 1000, 512, 1024), (8, 10440, 256, 256)])
+def test_gemm_mixed_major(cuda, monkeypatch, cta2, nets, m, n, k):
+  """C = A[M,K] . B[K,N]: A K-major, B MN-major -- the forward GEMM reading the natural
+  (in,out) bf16 kernel copy, single-CTA and CTA-pair tiles."""
+  monkeypatch.setenv('BNF_CTA2', cta2)
+  g = torch.Generator(device='cuda').manual_seed(m + 3 * n + k)
+  a = torch.randn(nets, m, k, generator=g, device=cuda).to(torch.bfloat16)
+  b = torch.randn(nets, k, n, generator=g, device=cuda).to(torch.bfloat16)
+  c = _gemm(2, a, b, nets, m, n, k)
+  want = torch.bmm(a.float(), b.float())
+  err = float((c - want).abs().max())
+  assert err <= 2e-3 * float(want.abs().max()), err
+
+
+@pytest.mark.parametrize('flag,val', [('BNF_LEGACY_STEP', '1'), ('BNF_PDL', '0'), ('BNF_FWD_WT', '1'),
+                                      ('BNF_NO_GRAPH', '1')])
+def test_fused_step_variants_agree(cuda, monkeypatch, flag, val):
+  """The fused MAP step (map_update kernel, programmatic dependent launch, forward reading the
+  natural-layout bf16 kernels, CUDA-graph replay) against the same training run with each piece
+  switched off: same losses and parameters up to atomic-order noise."""
+  from bayesnf_b200 import inference
+  n = 1500
+  cfg = _cfg(256, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3)
+  x, y = xd.cpu().numpy().astype(np.float64), yd.cpu().numpy().astype(np.float64)
+  monkeypatch.delenv(flag, raising=False)
+  p0, l0 = inference.fit_map(x, y, 0, 'NORMAL', cfg, 3, 0.005, 12, precision='bf16', init_params=P.numpy())
+  monkeypatch.setenv(flag, val)
+  p1, l1 = inference.fit_map(x, y, 0, 'NORMAL', cfg, 3, 0.005, 12, precision='bf16', init_params=P.numpy())
+  assert np.isfinite(l0).all() and l0.shape == (1, 3, 12)
+  np.testing.assert_allclose(l0, l1, rtol=2e-3)
+  f0, f1 = spec.flatten(p0)[0], spec.flatten(p1)[0]
+  # Adam normalises the step, so an entry whose gradient is pure summation noise may walk the
+  # other way; everything else must agree closely
+  assert float(np.quantile(np.abs(f0 - f1), 0.999)) <= 2e-3
+
+
+def test_single_step_calls_replay_cached_graph(cuda):
+  """bnf_map_steps called one step at a time (what bench.py's e2e loop does) == one call with
+  all the steps: the cached graph is keyed on its baked arguments and the device-side cursors
+  (Adam count, loss row) are re-armed by every call's prologue."""
+  from bayesnf_b200 import inference, _lib
+  n = 900
+  cfg = _cfg(128, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 2)
+  for prec in ('fp32', 'bf16'):
+    eng = inference.Engine(spec, prec)
+    outs = []
+    for mode in ('single', 'batched'):
+      p = P.cuda().clone()
+      m, v = torch.zeros_like(p), torch.zeros_like(p)
+      sc = torch.zeros(1, dtype=torch.int32, device=cuda)
+      if mode == 'single':
+        ls = torch.cat([eng.map_steps(p, m, v, sc, xd, yd, None, n, n, 1, 0.01, 1.0) for _ in range(7)])
+      else:
+        ls = eng.map_steps(p, m, v, sc, xd, yd, None, n, n, 7, 0.01, 1.0)
+      torch.cuda.synchronize()
+      assert int(sc[0]) == 7
+      outs.append((p.cpu(), ls.cpu()))
+    tol = 1e-5 if prec == 'fp32' else 2e-3
+    np.testing.assert_allclose(outs[0][1].numpy(), outs[1][1].numpy(), rtol=tol)
+    assert float((outs[0][0] - outs[1][0]).abs().max()) <= (1e-5 if prec == 'fp32' else 2e-2)
