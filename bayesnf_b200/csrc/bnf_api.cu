@@ -367,6 +367,12 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
       }
       cur ^= 1;
     } else {
+      if (tc && tc_dgrad0_enc_supported(m)) {
+        // dgrad_0 + feature-encode backward in one kernel: dfeat never goes to HBM
+        int rc = tc_dgrad0_enc(p, w.wn, (const bf16*)w.dU[cur], x, idx, idx_stride, params, w.derived, grad, n_net, B, st);
+        if (rc) return fail(rc, "tc_dgrad0_enc failed: %s", tc_last_error());
+        continue;
+      }
       if (tc) {
         int rc = tc_dgrad(p, 0, w.wn, (const bf16*)w.dU[cur], nullptr, w.dfeat, n_net, B, st);
         if (rc) return fail(rc, "tc_dgrad failed: %s", tc_last_error());
@@ -462,9 +468,9 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   int32_t* slot = (int32_t*)(w.mm + 8);                      // loss-row cursor
   unsigned int* counter = (unsigned int*)(w.mm + 9);         // map_update's block ticket
   const bool tc = prec == BNF_PREC_BF16;
-  // The fused-encode experiment keeps the round-1 step (prep + cast every step): its Dense_0
-  // kernel reads the transposed weight copy, which the fused update does not maintain.
-  const bool legacy = (tc && fused_encode_enabled()) || getenv("BNF_LEGACY_STEP");
+  // Paths that read the transposed weight copy (fused-encode experiment, BNF_FWD_WT=1) keep the
+  // round-1 step (prep + cast every step): the fused update only maintains the natural copy.
+  const bool legacy = (tc && need_wt()) || getenv("BNF_LEGACY_STEP");
 
   if (legacy) {
     CU(cudaMemsetAsync(slot, 0, 4, st));

@@ -30,6 +30,23 @@ constexpr int kDvSFourier = 43; // + input dim i
 // Without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// `const __restrict__` loads are treated as kernel-lifetime invariants and may be hoisted ABOVE
+// an asm memory barrier (seen in SASS: LDG.E.CONSTANT before ACQBULK) -- with PDL that reads
+// data the previous kernel has not written yet.  pdl_enter() therefore runs first in a kernel
+// and passes every pointer through an opaque asm after the wait: loads through the laundered
+// pointers carry a true dependency on it.
+// (an opaque ZERO OFFSET is added rather than the pointer itself being laundered, so the
+// compiler still knows the pointer derives from a kernel parameter = global address space)
+template <typename T> __device__ __forceinline__ void pdl_launder(T& p) {   // T = any pointer type
+  long long z = 0;
+  asm volatile("" : "+l"(z) :: "memory");
+  p = (T)((const char*)p + z);
+}
+template <typename... P> __device__ __forceinline__ void pdl_enter(P&... ptrs) {
+  pdl_trigger();
+  pdl_wait();
+  (pdl_launder(ptrs), ...);
+}
 
 __device__ __forceinline__ float softplus_f(float x) {
   // jax.nn.softplus == logaddexp(x, 0)

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 #include "bnf_device.cuh"
 #include "bnf_kernels.h"
@@ -43,8 +44,7 @@ __device__ __forceinline__ void prep_one(const DevModel& m, const float* p, floa
 __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* params,
                             float* __restrict__ derived, int n_net, float* zero_acc, float* zero_acc2,
                             int32_t* zero_cursors) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, derived, zero_acc, zero_acc2, zero_cursors);
   int net = blockIdx.x;
   if (net >= n_net) return;
   if (threadIdx.x == 0) {
@@ -67,14 +67,13 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
                               const float* __restrict__ x, const int32_t* __restrict__ idx,
                               int64_t idx_stride, int B, T* __restrict__ feat) {
   extern __shared__ float tile[];  // [kEncRows][Fp+1]
-  pdl_trigger();
+  pdl_enter(derived, x, idx, feat);
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * kEncRows;
   const float* dv = derived + (size_t)net * kDerivedStride;
   const int ld = m.Fp + 1;
   for (int e = threadIdx.x; e < kEncRows * ld; e += blockDim.x) tile[e] = 0.f;
   __syncthreads();
-  pdl_wait();
   const int U = num_units(m);
   const float two_pi = 6.283185307179586f;
   for (int w = threadIdx.x; w < kEncRows * U; w += blockDim.x) {
@@ -119,6 +118,84 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
   }
 }
 
+// bf16 path: the same features with the per-item bookkeeping hoisted out of the inner loop.
+// ncu on the generic kernel above (chickenpox shape): 236 instructions per (row, unit) item,
+// 84 % issue-slot utilisation -- it is instruction-bound on unit decoding, IEEE divisions and
+// the element-wise copy-out.  Here a block first builds a per-unit constant table (column
+// indices, argument multiplier, output scales with the 1/(d+1), 1/h divisions folded in) and
+// the scaled inputs of its 64 rows in shared memory; an item is then table lookup -> one
+// sincos -> two bf16 stores into a padded tile that leaves as 16-byte vectors.
+struct EncUnit { float mult, k0, k1; int kind, dim, dim2, c0, c1; };
+constexpr int kEncFastRows = 64;
+
+__global__ void __launch_bounds__(256)
+encode_fast_kernel(const __grid_constant__ DevModel m, const float* __restrict__ derived,
+                   const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t idx_stride,
+                   int B, __nv_bfloat16* __restrict__ feat, int U) {
+  extern __shared__ __align__(16) uint8_t esm[];
+  constexpr int R = kEncFastRows;
+  pdl_enter(derived, x, idx, feat);
+  const int ldt = m.Fp * 2 + 16;                         // bytes per tile row (16-byte aligned, 4-way banks)
+  uint8_t* tile = esm;                                   // [R][ldt] bf16 features
+  float* sxs = reinterpret_cast<float*>(esm + R * ldt);  // [R][kMaxD+1] x/denom, slot D = raw time
+  EncUnit* tab = reinterpret_cast<EncUnit*>(sxs + R * (kMaxD + 1));
+  const int net = blockIdx.y, row0 = blockIdx.x * R, tid = threadIdx.x;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  for (int e = tid; e < R * ldt / 16; e += 256) reinterpret_cast<uint4*>(tile)[e] = make_uint4(0, 0, 0, 0);
+  for (int u = tid; u < U; u += 256) {
+    const UnitInfo ui = decode_unit(m, u);
+    EncUnit t;
+    t.kind = ui.kind; t.dim = 0; t.dim2 = 0; t.c0 = 0; t.c1 = 0; t.mult = 0.f; t.k0 = 0.f; t.k1 = 0.f;
+    if (ui.kind == 0) {
+      t.dim = ui.a; t.c0 = m.col_x + ui.a; t.k0 = dv[kDvSX];
+    } else if (ui.kind == 1) {
+      const int i = ui.a, d = ui.b;
+      t.dim = i; t.mult = 6.283185307179586f * (float)(1 << d);
+      t.c0 = m.fourier_col[i] + d; t.c1 = t.c0 + m.fourier_deg[i];
+      t.k0 = t.k1 = dv[kDvSFourier + i] / (float)(d + 1);
+    } else if (ui.kind == 2) {
+      const int k = ui.a;
+      t.dim = m.D; t.mult = m.seasonal_w[k];
+      t.c0 = m.col_seasonal + k; t.c1 = t.c0 + m.n_seasonal;
+      t.k0 = t.k1 = dv[kDvSSeas] / m.seasonal_h[k];
+    } else {
+      t.dim = m.inter_a[ui.a]; t.dim2 = m.inter_b[ui.a]; t.c0 = m.col_inter + ui.a; t.k0 = dv[kDvSInter];
+    }
+    tab[u] = t;
+  }
+  for (int e = tid; e < R * m.D; e += 256) {
+    const int r = e / m.D, i = e - r * m.D;
+    const int b = min(row0 + r, B - 1);
+    const float xv = row_ptr(x, idx, idx_stride, net, b, m.D)[i];
+    sxs[r * (kMaxD + 1) + i] = xv / dv[kDvDenom + i];
+    if (i == 0) sxs[r * (kMaxD + 1) + m.D] = xv;
+  }
+  __syncthreads();
+  for (int w = tid; w < R * U; w += 256) {
+    const int u = w / R, r = w % R;                      // a warp shares one unit: uniform table reads
+    const EncUnit t = tab[u];
+    const float* sr = sxs + r * (kMaxD + 1);
+    __nv_bfloat16* trow = reinterpret_cast<__nv_bfloat16*>(tile + r * ldt);
+    if (t.kind == 0) {
+      trow[t.c0] = __float2bfloat16_rn(sr[t.dim] * t.k0);
+    } else if (t.kind == 3) {
+      trow[t.c0] = __float2bfloat16_rn((sr[t.dim] * sr[t.dim2]) * t.k0);
+    } else {
+      float sn, cs;
+      sincos_reduced(t.mult * sr[t.dim], &sn, &cs);
+      trow[t.c0] = __float2bfloat16_rn(cs * t.k0);
+      trow[t.c1] = __float2bfloat16_rn(sn * t.k1);
+    }
+  }
+  __syncthreads();
+  const int rows = min(R, B - row0), chunks = m.Fp / 8;
+  uint4* out = reinterpret_cast<uint4*>(feat + ((size_t)net * B + row0) * m.Fp);
+  for (int e = tid; e < rows * chunks; e += 256) {
+    const int r = e / chunks, j = e - r * chunks;
+    out[e] = *reinterpret_cast<const uint4*>(tile + r * ldt + j * 16);
+  }
+}
+
 // encode backward: dfeat [n_net,B,Fp] f32 -> grads of
 // feature_inv_sp_scale{g} and log_scale_adjustment, accumulated into grad[n_net,P].
 // A warp owns whole units (one x column / one sin-cos pair / one interaction column): its
@@ -134,8 +211,7 @@ encode_bwd_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
                   const float* __restrict__ dfeat, int64_t g_row, int64_t g_col /* element strides */,
                   float* __restrict__ grad) {
   __shared__ float acc[kMaxD + kMaxD + 3];  // [0,D): lsa ; D + {0:x,1:seasonal,2:inter, 3+i: fourier_i}
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, derived, x, idx, dfeat, grad);
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * R, row1 = min(B, row0 + R);
   const float* dv = derived + (size_t)net * kDerivedStride;
@@ -224,8 +300,7 @@ gemm_simt_kernel(const TA* __restrict__ A, size_t a_batch, int lda, const TB* __
                  size_t b_batch, int ldb, int M, int N, int K, Epi epi) {
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(A, Bm);   // the epilogue functor's pointers are not __restrict__: ordinary loads
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64, net = blockIdx.z;
   A += (size_t)net * a_batch;
@@ -348,8 +423,7 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
             const int32_t* __restrict__ idx, int64_t idx_stride, int B, float* __restrict__ out_loc,
             float* __restrict__ opre_out, float* __restrict__ r_out, float* __restrict__ ll,
             float* __restrict__ grad) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, derived, h, y_all, idx, out_loc, opre_out, r_out, ll, grad);
   const int net = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* p = params + (size_t)net * m.P;
@@ -489,8 +563,7 @@ act_bwd_kernel(const __grid_constant__ DevModel m, int layer, const float* __res
                const float* __restrict__ r, T* __restrict__ dU /* in: dh (unless head), out: dU */,
                int B, float* __restrict__ grad) {
   __shared__ float red[2][4];
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, derived, z, h, r, dU, grad);
   const int net = blockIdx.z;
   const int n = blockIdx.x * 128 + threadIdx.x;
   const int b0 = blockIdx.y * kActRows, b1 = min(B, b0 + kActRows);
@@ -553,11 +626,10 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
   constexpr bool FAST = FastMath<T>::value;
   __shared__ float red[2][8];
   extern __shared__ float colsum[];            // [W] bias grads (+ [W] Dense_L kernel grads at the head)
-  pdl_trigger();
+  pdl_enter(params, derived, z, h, r, dU, grad);
   const int net = blockIdx.y;
   for (int i = threadIdx.x; i < (IS_HEAD ? 2 : 1) * m.W; i += blockDim.x) colsum[i] = 0.f;
   __syncthreads();
-  pdl_wait();
   const int G = m.W / VEC;                     // column groups per row
   const int cg = threadIdx.x % G;
   const int rstep = 256 / G;                   // rows covered per pass
@@ -652,8 +724,7 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
   float* colsum = fsm + kHeadFusedMaxRows;      // [2W] bias / Dense_L kernel column sums
   float* kos = colsum + 2 * m.W;                // [W] Dense_L kernel
   __shared__ float hred[8][8];
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, derived, h, z, y_all, idx, dU, ll, grad);
   const int net = blockIdx.y;
   const int b0 = blockIdx.x * R, b1 = min(B, b0 + R);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -883,6 +954,10 @@ __global__ void map_loss_kernel(int n_net, const float* ll, const float* prior, 
 // no memset / prep / cast / loss nodes in between (inference.py:599-608 per step).
 // step_count holds the number of COMPLETED steps on entry; slot the loss row to write.
 // -----------------------------------------------------------------------------
+// FAST (tensor-core mode): MUFU exp/log/rcp/sqrt approximations (~1e-6 relative on the update of
+// f32 master weights whose bf16 copies feed the GEMMs); the fp32 parity mode keeps optax's exact
+// division / sqrt sequence.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __restrict__ am,
                   float* __restrict__ av, float* __restrict__ grad, int32_t* step_count, float c_ll,
@@ -891,39 +966,76 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
                   __nv_bfloat16* __restrict__ wn, size_t w_per_net, int n_net) {
   __shared__ float pred[8];
   __shared__ int s_last;
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, am, av, grad, step_count, prior, ll, out_loss, slot, counter, derived, wn);
   const int net = blockIdx.y, P = m.P;
   const int t = __ldcg(step_count) + 1;
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
-  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  // the two powf() bias corrections cost more than a whole element update: once per block
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) { s_bc[0] = 1.f - powf(b1, (float)t); s_bc[1] = 1.f - powf(b2, (float)t); }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2 = s_bc[1];
+  const float rbc1 = 1.f / bc1, rbc2 = 1.f / bc2;
   float lp = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-    const size_t o = (size_t)net * P + i;
-    const float th = params[o];
-    const float gl = grad[o];
-    grad[o] = 0.f;
-    float g = -(c_ll * gl);
-    if (prior_weight != 0.f) {
-      const float zz = th - (i == 1 ? -1.5f : 0.f);
-      lp += -zz - 2.f * softplus_f(-zz);
-      g = -(c_ll * gl + prior_weight * (-tanhf(0.5f * zz)));
+  // four independent elements per thread and iteration: 16 loads in flight before the first use
+  constexpr int U = 4;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < P; i0 += U * stride) {
+    float th[U], gl[U], m0[U], v0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i < P) {
+        const size_t o = (size_t)net * P + i;
+        th[u] = params[o]; gl[u] = grad[o]; m0[u] = am[o]; v0[u] = av[o];
+      }
     }
-    const float mm = (1.f - b1) * g + b1 * am[o];
-    const float vv = (1.f - b2) * (g * g) + b2 * av[o];
-    am[o] = mm;
-    av[o] = vv;
-    const float th_new = th + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + eps));
-    params[o] = th_new;
-    if (wn) {
-      // hidden-layer kernel leaf?  wn = [layer][Kp][W] per network, rows >= fan_in stay zero
-      for (int l = 0; l < m.L; ++l) {
-        const int rel = i - m.off_kernel[l];
-        const int cnt = (l == 0 ? m.F : m.W) * m.W;
-        if (rel >= 0 && rel < cnt) {
-          const size_t lo = l == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(l - 1) * m.W * m.W;
-          wn[(size_t)net * w_per_net + lo + rel] = __float2bfloat16_rn(th_new);
-          break;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i >= P) break;
+      const size_t o = (size_t)net * P + i;
+      float g = -(c_ll * gl[u]);
+      if (prior_weight != 0.f) {
+        const float zz = th[u] - (i == 1 ? -1.5f : 0.f);
+        if (FAST) {
+          // one exponential serves both: softplus(-z) = max(-z,0) + log(1+e), tanh(z/2) = sgn(z)(1-e)/(1+e), e = exp(-|z|)
+          const float e = ex2_fast(-fabsf(zz) * 1.4426950408889634f);
+          const float r1 = __fdividef(1.f, 1.f + e);
+          lp += -zz - 2.f * (fmaxf(-zz, 0.f) + __logf(1.f + e));
+          g = -(c_ll * gl[u] - prior_weight * copysignf((1.f - e) * r1, zz));
+        } else {
+          lp += -zz - 2.f * softplus_f(-zz);
+          g = -(c_ll * gl[u] + prior_weight * (-tanhf(0.5f * zz)));
+        }
+      }
+      const float mm = (1.f - b1) * g + b1 * m0[u];
+      const float vv = (1.f - b2) * (g * g) + b2 * v0[u];
+      am[o] = mm;
+      av[o] = vv;
+      float th_new;
+      if (FAST) {
+        float sq;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(vv * rbc2));
+        th_new = th[u] - lr * __fdividef(mm * rbc1, sq + eps);
+      } else {
+        th_new = th[u] + (-lr) * ((mm / bc1) / (sqrtf(vv / bc2) + eps));
+      }
+      params[o] = th_new;
+      // The zero for the next step's accumulation is stored AFTER the values that depend on the
+      // loaded gradient: a store issued right behind the load of the same address stalls the
+      // SM's in-order LSU until the line arrives (measured: 4x slower kernel).
+      grad[o] = 0.f;
+      if (wn) {
+        // hidden-layer kernel leaf?  wn = [layer][Kp][W] per network, rows >= fan_in stay zero
+        for (int l = 0; l < m.L; ++l) {
+          const int rel = i - m.off_kernel[l];
+          const int cnt = (l == 0 ? m.F : m.W) * m.W;
+          if (rel >= 0 && rel < cnt) {
+            const size_t lo = l == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(l - 1) * m.W * m.W;
+            wn[(size_t)net * w_per_net + lo + rel] = __float2bfloat16_rn(th_new);
+            break;
+          }
         }
       }
     }
@@ -939,9 +1051,11 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
     }
   }
   // ---- last block of the grid: loss row, accumulator reset, ticks, next step's derived ----
-  __threadfence();
+  // (bar.sync, then ONE gpu-scope fence by the signalling thread: fences are cumulative over
+  // the block barrier, the same pattern as a cooperative-groups grid sync)
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned int ticket = atomicAdd(counter, 1u);
     s_last = ticket == gridDim.x * gridDim.y - 1u;
   }
@@ -1305,6 +1419,21 @@ static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int 
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st) {
+  if constexpr (FastMath<T>::value) {
+    const char* e = getenv("BNF_ENCODE_GENERIC");
+    if (!(e && e[0] == '1')) {
+      int U = m.D + m.n_seasonal + m.n_inter;
+      for (int i = 0; i < m.D; ++i) U += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+      const size_t smem_f = (size_t)kEncFastRows * (m.Fp * 2 + 16) + (size_t)kEncFastRows * (kMaxD + 1) * 4 +
+                            (size_t)U * sizeof(EncUnit);
+      if (smem_f <= 48 * 1024) {
+        dim3 grid_f((B + kEncFastRows - 1) / kEncFastRows, n_net);
+        BNF_PROF("encode", st);
+        launch_k(encode_fast_kernel, grid_f, dim3(256), smem_f, st, m, derived, x, idx, idx_stride, B, feat, U);
+        return;
+      }
+    }
+  }
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
   size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
   BNF_PROF("encode", st);
@@ -1451,11 +1580,25 @@ void launch_map_update(const DevModel& m, float* params, float* am, float* av, f
                        int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
                        float* ll, float* out_loss, int32_t* slot, unsigned int* counter, float* derived,
                        __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st) {
-  int bx = (m.P + 255) / 256;
-  if (bx > 1024) bx = 1024;
+  // about one wave of resident blocks in total: every block pays one fence + one ticket atomic
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int bx = (sms * 8 + n_net - 1) / n_net;
+  const int bmax = (m.P + 255) / 256;
+  if (bx > bmax) bx = bmax;
+  if (bx < 1) bx = 1;
   BNF_PROF("map_update", st);
-  launch_k(map_update_kernel, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
-           prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
+  if (wn)
+    launch_k(map_update_kernel<true>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
+             prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
+  else
+    launch_k(map_update_kernel<false>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
+             prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st) {

@@ -53,8 +53,7 @@ __global__ void __launch_bounds__(256)
 cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
                     bf16* __restrict__ wt, bf16* __restrict__ wn, size_t per_net) {
   __shared__ float tile[32][33];
-  pdl_trigger();
-  pdl_wait();
+  pdl_enter(params, wt, wn);
   const int net = blockIdx.z / m.L, layer = blockIdx.z % m.L;
   const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -207,7 +206,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // -----------------------------------------------------------------------------
 // the GEMM kernel
 // -----------------------------------------------------------------------------
-enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4, TC_DGRAD_ACT = 5 };
+enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4, TC_DGRAD_ACT = 5,
+       TC_DGRAD_ENC = 6 /* layer-0 dgrad fused with the feature-encode backward */ };
 
 struct TcArgs {
   int mode, n_net;
@@ -248,24 +248,30 @@ constexpr int kXTileBytes = 128 * kMaxD * 4;
 // CTA2: a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
 // from L2 drops by a third and the ring gets deeper (32 KB stages).
-template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false> struct TcCfg {
-  static constexpr int kStages = A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8)));
+template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct TcCfg {
+  // TC_DGRAD_ENC: the dfeat tile stays on chip -- a 128 x (BLOCK_N+1) f32 tile in shared memory.
+  // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
+  // SM at Fp = 64: two ring stages, no TMA-store staging tiles (~100 KB, 128 TMEM columns each).
+  static constexpr int kGBytes = MODE == TC_DGRAD_ENC ? 128 * (BLOCK_N + 1) * 4 + 2 * 128 * (kMaxD + 1) * 4 : 0;
+  static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
+      (A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kThreads = kTcThreads + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes;
+  static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
+  static constexpr int kMinBlocks = (MODE == TC_DGRAD_ENC && BLOCK_N == 64) ? 2 : 1;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
 template <int BLOCK_N, int A_MODE, int MODE, bool CTA2>
-__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE, CTA2>::kThreads), 1)
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE, CTA2, MODE>::kThreads), (TcCfg<BLOCK_N, A_MODE, CTA2, MODE>::kMinBlocks))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
-  using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2>;
+  using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2, MODE>;
   constexpr bool A_MN = A_MODE == 1;                  // A operand MN-major
   constexpr bool B_MN = A_MODE == 1 || A_MODE == 3;   // B operand MN-major
   constexpr bool ENCODE = A_MODE == 2;
@@ -283,6 +289,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* xfull = tempty + 3;                      // A_MODE 2: raw input tile landed
   float* sbias = (float*)(staging + Cfg::kStagingBytes + 256);  // [2][256]: s_l * bias of the tile's columns
   float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
+  float* gtile = sbias + 2 * 256;                    // TC_DGRAD_ENC: [128][BLOCK_N+1] f32 dfeat tile
+  float* eacc = sbias;                               // TC_DGRAD_ENC: [2*kMaxD+3] partial sums
+  float* sxt = gtile + 128 * (BLOCK_N + 1);          // TC_DGRAD_ENC: [2][128][kMaxD+1] scaled inputs + raw time
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();                       // the next kernel's CTAs may start their own prologue
@@ -328,14 +337,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tiles_per_net = m_units * a.n_tiles * a.k_splits;
   const int total_tiles = a.n_net * tiles_per_net;
   const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
-  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // tile -> CTA mapping: round-robin, except TC_DGRAD_ENC where a CTA takes a CONTIGUOUS range of
+  // tiles (mostly one network: its partial sums stay in shared memory until the network changes)
+  const int cta_id = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_ctas = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool contiguous = MODE == TC_DGRAD_ENC;
+  const int tile0 = contiguous ? (int)((long long)total_tiles * cta_id / n_ctas) : cta_id;
+  const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
+  const int tile_step = contiguous ? 1 : n_ctas;
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0;
-      for (int t = tile0; t < total_tiles; t += tile_step) {
+      for (int t = tile0; t < tile_end; t += tile_step) {
         const int net = t / tiles_per_net;
         int r = t % tiles_per_net;
         const int n_t = r % a.n_tiles; r /= a.n_tiles;
@@ -414,7 +429,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t kStepB = (B_MN ? 2048 : 32) >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = tile0; t < total_tiles; t += tile_step) {
+      for (int t = tile0; t < tile_end; t += tile_step) {
         int r = t % tiles_per_net;
         r /= a.n_tiles;
         const int split = r % a.k_splits;
@@ -455,7 +470,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = warp >> 2;
     const int epi_tid = threadIdx.x;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = tile0; t < total_tiles; t += tile_step) {
+    if (MODE == TC_DGRAD_ENC && epi_tid < 2 * kMaxD + 3) eacc[epi_tid] = 0.f;
+    for (int t = tile0; t < tile_end; t += tile_step) {
       const int net = t / tiles_per_net;
       int r = t % tiles_per_net;
       const int n_t = r % a.n_tiles; r /= a.n_tiles;
@@ -490,6 +506,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (BLOCK_N > 64) zq1[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32 + 64) + k);
         }
       }
+      // TC_DGRAD_ENC: a tile's input rows -> shared memory (scaled by 1/(input_scale*exp(lsa));
+      // slot D keeps the raw time for the seasonal units), double-buffered: tile i+1's rows are
+      // fetched while tile i's encode backward runs
+      auto stage_x = [&](int tt, float* dst) {
+        const int net_x = tt / tiles_per_net;
+        const int m_x = (tt % tiles_per_net) / (a.n_tiles * a.k_splits);
+        const float* dvx = a.derived + (size_t)net_x * kDerivedStride;
+        for (int e = epi_tid; e < 128 * dm.D; e += 32 * kEpiWarps) {
+          const int r = e / dm.D, i = e - r * dm.D;
+          const int b = min(m_x * 128 + r, a.m_valid - 1);
+          const float xv = a.x[(a.idx ? (size_t)a.idx[(size_t)net_x * a.idx_stride + b] : (size_t)b) * dm.D + i];
+          dst[r * (kMaxD + 1) + i] = xv / dvx[kDvDenom + i];
+          if (i == 0) dst[r * (kMaxD + 1) + dm.D] = xv;
+        }
+      };
+      float* sx_cur = sxt + ((t - tile0) & 1) * 128 * (kMaxD + 1);
+      float* sx_nxt = sxt + (((t - tile0) & 1) ^ 1) * 128 * (kMaxD + 1);
+      if (MODE == TC_DGRAD_ENC && t == tile0) stage_x(t, sx_cur);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -612,6 +646,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+        } else if (MODE == TC_DGRAD_ENC) {
+          // dfeat chunk -> shared-memory tile (row stride BLOCK_N+1: conflict-free for the
+          // row-per-lane reads of the encode backward below); nothing goes to HBM
+          float* gr = gtile + (q * 32 + lane) * (BLOCK_N + 1) + c;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gr[j] = __uint_as_float(v[j]) * a.isf;
         } else if (MODE == TC_DGRAD_F32 && a.out_cm) {
           // dfeat goes out COLUMN-major [net][col][row]: the 32 lanes (= 32 consecutive rows)
           // write one full 128-byte line per column, and encode_bwd reads it back coalesced
@@ -663,6 +703,101 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (CTA2) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns both TMEMs' reuse
       else mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (MODE == TC_DGRAD_ENC) {
+        // ---- feature-encode backward of this tile's 128 rows (same math
+        // as encode_bwd_kernel<true>): a warp owns whole units, its lanes stride over the rows.
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // tile complete
+        if (t + 1 < tile_end) stage_x(t + 1, sx_nxt);
+        const float* dvp = a.derived + (size_t)net * kDerivedStride;
+        const int U = num_units(dm);
+        const float two_pi = 6.283185307179586f;
+        for (int u = warp; u < U; u += kEpiWarps) {
+          const UnitInfo ui = decode_unit(dm, u);
+          int slot = 0, dim_a = 0, dim_b = -1;
+          if (ui.kind == 0) { slot = 0; dim_a = ui.a; }
+          else if (ui.kind == 1) { slot = 3 + ui.a; dim_a = ui.a; }
+          else if (ui.kind == 2) { slot = 1; dim_a = -1; }
+          else { slot = 2; dim_a = dm.inter_a[ui.a]; dim_b = dm.inter_b[ui.a]; }
+          float gs = 0.f, gl_a = 0.f, gl_b = 0.f;
+          // four independent rows per lane (rows >= B carry a zero dfeat row: their dU rows were
+          // zero-filled by TMA, so they add nothing)
+          if (ui.kind == 0) {
+            const float s_x = dvp[kDvSX];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = lane + 32 * j;
+              const float sx = sx_cur[r * (kMaxD + 1) + ui.a];
+              const float G = gtile[r * (BLOCK_N + 1) + dm.col_x + ui.a];
+              gs = fmaf(G, sx, gs);
+              gl_a = fmaf(s_x * G, -sx, gl_a);
+            }
+          } else if (ui.kind == 1) {
+            const int i = ui.a, d = ui.b, deg = dm.fourier_deg[i];
+            const float cc = two_pi * (float)(1 << d);
+            const float rden = 1.f / (float)(d + 1);
+            const float kf = dvp[kDvSFourier + i] * (cc * rden);
+            const int cc0 = dm.fourier_col[i] + d, cs0 = cc0 + deg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = lane + 32 * j;
+              const float sx = sx_cur[r * (kMaxD + 1) + i];
+              float sn, cs;
+              sincos_reduced(cc * sx, &sn, &cs);
+              const float Gc = gtile[r * (BLOCK_N + 1) + cc0], Gs = gtile[r * (BLOCK_N + 1) + cs0];
+              gs += (Gc * cs + Gs * sn) * rden;
+              gl_a = fmaf(kf * (cs * Gs - sn * Gc), -sx, gl_a);
+            }
+          } else if (ui.kind == 2) {
+            const int k = ui.a;
+            const float wk = dm.seasonal_w[k], rh = 1.f / dm.seasonal_h[k];
+            const int c0 = dm.col_seasonal + k, c1i = c0 + dm.n_seasonal;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = lane + 32 * j;
+              float sn, cs;
+              sincos_reduced(wk * sx_cur[r * (kMaxD + 1) + dm.D], &sn, &cs);
+              gs += (gtile[r * (BLOCK_N + 1) + c0] * cs + gtile[r * (BLOCK_N + 1) + c1i] * sn) * rh;
+            }
+          } else {
+            const float s_i = dvp[kDvSInter];
+            const int cj = dm.col_inter + ui.a;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = lane + 32 * j;
+              const float pr = sx_cur[r * (kMaxD + 1) + dim_a] * sx_cur[r * (kMaxD + 1) + dim_b];
+              const float G = gtile[r * (BLOCK_N + 1) + cj];
+              gs = fmaf(G, pr, gs);
+              gl_a = fmaf(s_i * G, -pr, gl_a);
+            }
+          }
+          if (ui.kind == 3) gl_b = gl_a;
+          gs = warp_sum(gs);
+          gl_a = warp_sum(gl_a);
+          gl_b = warp_sum(gl_b);
+          if (lane == 0) {
+            atomicAdd(&eacc[dm.D + slot], gs);
+            if (dim_a >= 0) atomicAdd(&eacc[dim_a], gl_a);
+            if (dim_b >= 0) atomicAdd(&eacc[dim_b], gl_b);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sums complete, tile free
+        const int nacc = dm.D + 3 + dm.D;
+        const bool flush = t + 1 >= tile_end || (t + 1) / tiles_per_net != net;
+        if (flush && epi_tid < nacc) {
+          const float val = eacc[epi_tid];
+          eacc[epi_tid] = 0.f;               // ordered before the next tile's atomics by its bar.sync
+          const float* pp = a.params + (size_t)net * a.P;
+          float* gp = a.gradp + (size_t)net * a.P;
+          if (epi_tid < dm.D) {
+            atomicAdd(&gp[dm.off_lsa + epi_tid], val);
+          } else {
+            const int slot = epi_tid - dm.D;
+            const int off = slot == 0 ? dm.off_scale_x : (slot == 1 ? dm.off_scale_seasonal
+                          : (slot == 2 ? dm.off_scale_inter : dm.fourier_scale_off[slot - 3]));
+            if (off >= 0) atomicAdd(&gp[off], val * sigmoid_f(pp[off]));   // d softplus = sigmoid
+          }
+        }
+      }
       if (MODE == TC_DGRAD_ACT) {
         g_w = warp_sum(g_w);
         g_s = warp_sum(g_s);
@@ -684,7 +819,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int U = num_units(dm);
     const float two_pi = 6.283185307179586f;
     int stage = 0; uint32_t phase = 0;
-    for (int t = tile0; t < total_tiles; t += tile_step) {
+    for (int t = tile0; t < tile_end; t += tile_step) {
       const int net = t / tiles_per_net;
       int r0 = t % tiles_per_net;
       const int n_t = r0 % a.n_tiles; r0 /= a.n_tiles;
@@ -825,7 +960,7 @@ struct OutMaps { CUtensorMap o0, o1; };
 template <int BLOCK_N, int MN, int MODE, bool CTA2>
 static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
                        const DevModel* dm) {
-  using Cfg = TcCfg<BLOCK_N, MN, CTA2>;
+  using Cfg = TcCfg<BLOCK_N, MN, CTA2, MODE>;
   static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
   static bool attr_set = false;
   if (!attr_set) {
@@ -835,11 +970,11 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
   }
   const int m_units = CTA2 ? (a.m_tiles + 1) / 2 : a.m_tiles;
   long long total = (long long)a.n_net * m_units * a.n_tiles * a.k_splits;
-  const int slots = CTA2 ? sm_count / 2 : sm_count;
+  const int slots = (CTA2 ? sm_count / 2 : sm_count) * Cfg::kMinBlocks;
   int grid = (int)(total < slots ? total : slots);
   if (grid < 1) grid = 1;
   if (CTA2) grid *= 2;
-  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -909,6 +1044,9 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
       case TC_DGRAD_ACT: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ACT>(ma, mb, om, a, sm, st, dm);
       case TC_DGRAD_BF16: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_BF16>(ma, mb, om, a, sm, st, dm);
       case TC_DGRAD_F32: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_F32>(ma, mb, om, a, sm, st, dm);
+      case TC_DGRAD_ENC:
+        if constexpr (BLOCK_N <= 128) return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ENC>(ma, mb, om, a, sm, st, dm);
+        else return tc_fail(BNF_ERR_INVALID, "TC_DGRAD_ENC needs one n-tile of <= 128 columns");
       default: return launch_tc_m<BLOCK_N, 0, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
     }
   }
@@ -1034,6 +1172,39 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   memset(&om, 0, sizeof(om));
   if (out_bf && (rc = make_out_map(&om.o0, out_bf, Kp, B, n_net))) return rc;
   return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
+}
+
+// Layer-0 dgrad fused with the feature-encode backward: dfeat = isf * dU_0 @ K_0^T never leaves
+// the SM (TMEM -> shared-memory tile); the epilogue warps reduce it against the regenerated
+// features into the feature-scale / log_scale_adjustment gradients.  One n-tile must cover all
+// padded features (Fp <= 128).
+bool tc_dgrad0_enc_supported(const DevModel& m) {
+  const char* e = getenv("BNF_NO_FUSED_ENC_BWD");
+  if (e && e[0] == '1') return false;
+  return m.Fp <= 128 && pick_block_n(m.Fp) == m.Fp;
+}
+
+int tc_dgrad0_enc(const bnf_plan* p, const bf16* wn, const bf16* dU, const float* x, const int32_t* idx,
+                  int64_t idx_stride, const float* params, const float* derived, float* grad, int n_net,
+                  int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = m.Fp, bn = pick_block_n(Kp);
+  if (!tc_dgrad0_enc_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad0 + encode backward needs Fp <= 128");
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 128);
+  if (rc) return rc;
+  if ((rc = make_map(&mb, wn, m.W, Kp, n_net, m.W, tc_weight_elems(m), bn))) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_DGRAD_ENC; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = m.W / 64;
+  a.m_valid = B; a.n_valid = Kp;
+  a.isf = m.inv_sqrt_F;
+  a.x = x; a.idx = idx; a.idx_stride = idx_stride;
+  a.params = params; a.derived = derived; a.gradp = grad; a.P = m.P;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
 int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,

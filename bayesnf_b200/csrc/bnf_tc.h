@@ -32,6 +32,11 @@ int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_b
              __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st,
              const __nv_bfloat16* z_prev = nullptr, const float* params = nullptr,
              const float* derived = nullptr, float* grad = nullptr);
+// layer-0 dgrad with the feature-encode backward fused into its epilogue (dfeat stays on chip)
+bool tc_dgrad0_enc_supported(const DevModel& m);
+int tc_dgrad0_enc(const bnf_plan* p, const __nv_bfloat16* wn, const __nv_bfloat16* dU, const float* x,
+                  const int32_t* idx, int64_t idx_stride, const float* params, const float* derived,
+                  float* grad, int n_net, int B, cudaStream_t st);
 int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
              float* grad, int n_net, int B, cudaStream_t st);
 

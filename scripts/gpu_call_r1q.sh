@@ -4,14 +4,14 @@ set -x
 mkdir -p gpurun_out
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
-tail -5 gpurun_out/pytest.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
+tail -8 gpurun_out/pytest.log
+python scripts/tmp/diag1.py 2>&1 | tail -12
 timeout 300 python bench.py --steps 300 --warmup 20 > gpurun_out/bench_cp_default.json 2> gpurun_out/bench_cp_default.err
 BNF_PDL=0 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/bench_cp_nopdl.json 2> gpurun_out/bench_cp_nopdl.err
 BNF_LEGACY_STEP=1 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/bench_cp_legacy.json 2> gpurun_out/bench_cp_legacy.err
-BNF_FWD_WT=1 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/bench_cp_fwdwt.json 2> gpurun_out/bench_cp_fwdwt.err
 timeout 300 python bench.py --workload wind_map_e16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_wind.json 2> gpurun_out/bench_wind.err
-BNF_PDL=0 timeout 300 python bench.py --workload wind_map_e16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_wind_nopdl.json 2> gpurun_out/bench_wind_nopdl.err
+BNF_LEGACY_STEP=1 timeout 300 python bench.py --workload wind_map_e16 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_wind_legacy.json 2> gpurun_out/bench_wind_legacy.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 60 --csv --log-file gpurun_out/launches_chickenpox.csv python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/ncu_bench.log 2>&1
 for f in gpurun_out/bench_*.json; do echo $f; python - "$f" <<'P'
 import json,sys

@@ -138,10 +138,12 @@ def test_bf16_training_tracks_fp32(cuda):
   assert (res['bf16'][:, -1] < res['bf16'][:, 0]).all()
 
 
-@pytest.mark.parametrize('flag', ['BNF_FUSED_ENCODE', 'BNF_NO_FUSED_ACT_BWD'])
+@pytest.mark.parametrize('flag', ['BNF_FUSED_ENCODE', 'BNF_NO_FUSED_ACT_BWD', 'BNF_NO_FUSED_ENC_BWD',
+                                  'BNF_ENCODE_GENERIC'])
 def test_alternative_kernel_paths_agree(cuda, flag, monkeypatch):
-  """The opt-in fused encode+Dense_0 kernel and the unfused dgrad/act_bwd pair compute the
-  same thing as the default path (same bf16 storage; only reduction order differs)."""
+  """The opt-in fused encode+Dense_0 kernel, the unfused dgrad/act_bwd pair and the unfused
+  dgrad_0 / encode-backward pair compute the same thing as the default path (same bf16 storage;
+  only reduction order differs)."""
   from bayesnf_b200 import inference
   n = 700
   cfg = _cfg(256, 3, n)
