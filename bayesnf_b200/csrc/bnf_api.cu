@@ -309,8 +309,17 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
   const bool fuse0 = tc && fused_encode_enabled();
   if (!fuse0) launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
   if (tc && !prepped) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
+  const bool g = grad != nullptr;
+  // training in tensor-core mode with W <= 256: the last hidden layer's GEMM also runs the head,
+  // the log-likelihood and its own activation backward (z, h of that layer never reach HBM)
+  const bool head_epi = tc && g && ll && tc_fwd_head_supported(m) && !(fuse0 && m.L == 1);
   for (int l = 0; l < m.L; ++l) {
     const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
+    if (head_epi && l == m.L - 1) {
+      int rc = tc_fwd_head(p, params, w.derived, (const bf16*)a_in, w.wn, y, idx, idx_stride, (bf16*)w.dU[0], ll, grad, n_net, B, st);
+      if (rc) return fail(rc, "tc_fwd_head failed: %s", tc_last_error());
+      continue;
+    }
     if (tc && l == 0 && fuse0) {
       int rc = tc_fwd_layer0_fused(p, params, w.derived, x, idx, idx_stride, w.wt, grad ? (bf16*)w.feat : nullptr,
                                    (bf16*)w.z[0], (bf16*)w.h[0], n_net, B, st);
@@ -323,12 +332,11 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
                                  (T*)w.z[l], (T*)w.h[l], n_net, B, st);
     }
   }
-  const bool g = grad != nullptr;
   int cur = 0;
   // training: head + activation backward of the last layer in one kernel when the shape allows
   const char* nh = getenv("BNF_NO_FUSED_HEAD");
-  bool head_done = false;
-  if (g && ll && !(nh && nh[0] == '1'))
+  bool head_done = head_epi;
+  if (!head_done && g && ll && !(nh && nh[0] == '1'))
     head_done = launch_head_fused<T>(m, params, w.derived, (const T*)w.h[m.L - 1], (const T*)w.z[m.L - 1], y, idx,
                                      idx_stride, B, (T*)w.dU[cur], ll, grad, n_net, st);
   if (!head_done) {

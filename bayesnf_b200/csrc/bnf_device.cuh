@@ -129,6 +129,50 @@ __device__ __forceinline__ float digamma_f(float x) {
          - inv2 * (1.f / 12.f - inv2 * (1.f / 120.f - inv2 * (1.f / 252.f)));
 }
 
+// ---- per-row log-likelihood of the head (models.py:157-191) ------------
+// o = network output of the row, yv = observation, dv = the network's derived scalars.
+// Returns log p(y | o); *rr = d logp / d o; g[0..2] receive this row's addends of the raw
+// gradient sums w.r.t. sigma (NORMAL: multiplied by exp(log_noise_scale) later), shape
+// (NB/ZINB: by sigmoid(shape_raw)) and pi (ZINB: by pi(1-pi)).  Same expressions as head_kernel.
+__device__ __forceinline__ float head_row_loglik(int likelihood, const float* __restrict__ dv, float o, float yv,
+                                                 float* rr, float* g) {
+  float logp;
+  if (likelihood == BNF_NORMAL) {
+    const float sg = dv[kDvSigma];
+    const float d = yv / sg - o / sg;
+    logp = -0.5f * d * d - (0.9189385332046727f + logf(sg));
+    *rr = d / sg;
+    g[0] += (d * d - 1.f) / sg;
+  } else {
+    const float mean = softplus_f(o);
+    const float shp = dv[kDvShape];
+    const float rc = 1.f / shp;
+    const float lg = -logf(shp) - logf(mean);
+    const float sig_l = sigmoid_f(lg);
+    const float nb = rc * log_sigmoid_f(-lg) + yv * log_sigmoid_f(lg)
+                     - (lgammaf(1.f + yv) + lgammaf(rc) - lgammaf(1.f + yv + rc)) - logf(rc + yv);
+    const float dnb_dl = yv * (1.f - sig_l) - rc * sig_l;
+    const float dnb_dr = log_sigmoid_f(-lg) - digamma_f(rc) + digamma_f(1.f + yv + rc) - 1.f / (rc + yv);
+    float wnb = 1.f;
+    logp = nb;
+    if (likelihood == BNF_ZINB) {
+      const float pi = dv[kDvPi];
+      if (yv == 0.f) {
+        const float A = (1.f - pi) * expf(nb), tot = A + pi;
+        logp = logf(tot);
+        wnb = A / tot;
+        g[2] += (1.f - expf(nb)) / tot;
+      } else {
+        logp = log1pf(-pi) + nb;
+        g[2] += -1.f / (1.f - pi);
+      }
+    }
+    *rr = wnb * dnb_dl * (-sigmoid_f(o) / mean);
+    g[1] += wnb * (dnb_dl * (-1.f / shp) + dnb_dr * (-1.f / (shp * shp)));
+  }
+  return logp;
+}
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) {

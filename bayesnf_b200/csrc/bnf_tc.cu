@@ -207,7 +207,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 // the GEMM kernel
 // -----------------------------------------------------------------------------
 enum { TC_FWD = 0, TC_DGRAD_BF16 = 1, TC_DGRAD_F32 = 2, TC_WGRAD = 3, TC_PLAIN_F32 = 4, TC_DGRAD_ACT = 5,
-       TC_DGRAD_ENC = 6 /* layer-0 dgrad fused with the feature-encode backward */ };
+       TC_DGRAD_ENC = 6 /* layer-0 dgrad fused with the feature-encode backward */,
+       TC_FWD_HEAD = 7 /* last hidden layer fwd + head + log-likelihood + its own activation backward */ };
 
 struct TcArgs {
   int mode, n_net;
@@ -222,6 +223,7 @@ struct TcArgs {
   // TC_DGRAD_ACT (dgrad fused with the activation backward of the previous layer)
   const bf16* zin; float* gradp; int off_bias_prev, off_ls_prev, off_actw, layer_prev;
   int out_cm; // TC_DGRAD_F32: write outf column-major [net][col][row]
+  const float* y; float* ll;   // TC_FWD_HEAD: observations, per-network log-likelihood accumulators
   int dbg;   // BNF_TC_DBG ablation mask (only read when compiled with -DBNF_TC_EXPERIMENT)
 };
 // Epilogue ablation hooks for scripts/epi_experiment.py: compiled out unless -DBNF_TC_EXPERIMENT.
@@ -253,7 +255,10 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
   // SM at Fp = 64: two ring stages, no TMA-store staging tiles (~100 KB, 128 TMEM columns each).
   static constexpr int kGBytes = MODE == TC_DGRAD_ENC ? 128 * (BLOCK_N + 1) * 4 + 2 * 128 * (kMaxD + 1) * 4 : 0;
+  // TC_FWD_HEAD: Dense_L kernel [2][256] + per-row partial dots [2][128] in shared memory
+  static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 2 * 128) * 4 : 0;
   static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
+      MODE == TC_FWD_HEAD ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : 4)) :
       (A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kThreads = kTcThreads + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
@@ -262,7 +267,9 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
   static constexpr int kMinBlocks = (MODE == TC_DGRAD_ENC && BLOCK_N == 64) ? 2 : 1;
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes;
+  static_assert(kStages * kStageBytes + kStagingBytes + 256 + 2 * 256 * 4 + kXBytes + kGBytes + kHeadBytes <= 232448,
+                "dynamic shared memory exceeds the 227 KB per-CTA limit");
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes + kHeadBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
@@ -291,6 +298,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
   float* gtile = sbias + 2 * 256;                    // TC_DGRAD_ENC: [128][BLOCK_N+1] f32 dfeat tile
   float* eacc = sbias;                               // TC_DGRAD_ENC: [2*kMaxD+3] partial sums
+  float* kos_s = sbias + 2 * 256;                    // TC_FWD_HEAD: [2][256] Dense_L kernel of the tile's network
+  float* rowdot = kos_s + 2 * 256;                   // TC_FWD_HEAD: [2][128] partial h.Ko of the two column halves
   float* sxt = gtile + 128 * (BLOCK_N + 1);          // TC_DGRAD_ENC: [2][128][kMaxD+1] scaled inputs + raw time
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -479,6 +488,148 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
       float c1 = a.isf, w_act = 0.f;
       float* sb = sbias + acc * 256;
+      if constexpr (MODE == TC_FWD_HEAD) {
+        // ================= last hidden layer + head + log-likelihood + activation backward =================
+        // One tile holds whole rows (n_tiles == 1), so everything downstream of the GEMM happens on
+        // the accumulator while it sits in TMEM (models.py:263-273 forward, :157-191 likelihood,
+        // and the backward of both): pass 1 forms h = act(z) and the row's h.Ko partial dot;
+        // the two warps of a lane quarter exchange partials through shared memory; every lane
+        // evaluates log p(y|o) and r = dlogp/do of its row; pass 2 re-reads the accumulator and
+        // emits dU = s_l*r*(s_out/sqrt(W))*Ko*act'(z) (the only HBM output) plus the bias /
+        // Dense_L-kernel column sums and the scalar gradients.  z and h never leave the SM.
+        const float* pnet = a.params + (size_t)net * a.P;
+        const float s_l = dv[kDvSLayer + a.layer];
+        const float w = dv[kDvActW], s_out = dv[kDvSOut];
+        const float cz = s_l * a.isf;
+        const float hc = s_out * dm.inv_sqrt_W;
+        const float bo = pnet[dm.off_bias[dm.L]];
+        float* kos = kos_s + acc * 256;
+        if (epi_tid < BLOCK_N) {
+          sb[epi_tid] = s_l * pnet[a.off_bias + epi_tid];
+          kos[epi_tid] = pnet[dm.off_kernel[dm.L] + epi_tid];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        const int row = m_t * 128 + q * 32 + lane;
+        const bool row_ok = row < a.m_valid;
+        float yv = 0.f;
+        if (row_ok) yv = a.y[a.idx ? (size_t)a.idx[(size_t)net * a.idx_stride + row] : (size_t)row];
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+        // ---- pass 1: partial dot of this warp's column chunks
+        float dot = 0.f;
+#pragma unroll 1
+        for (int c = half * 32; c < BLOCK_N; c += 64) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)c, v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+            const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
+            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j]), cz, b4.x), w), k4.x, dot);
+            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 1]), cz, b4.y), w), k4.y, dot);
+            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 2]), cz, b4.z), w), k4.z, dot);
+            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 3]), cz, b4.w), w), k4.w, dot);
+          }
+        }
+        rowdot[half * 128 + q * 32 + lane] = dot;
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");        // the two warps of this lane quarter
+        const float opre = (rowdot[q * 32 + lane] + rowdot[128 + q * 32 + lane]) * dm.inv_sqrt_W + bo;
+        // ---- likelihood of the row (both warps evaluate it; warp half 0 owns the sums)
+        float gl3[3] = {0.f, 0.f, 0.f};
+        float rr = 0.f, logp = 0.f;
+        if (row_ok) logp = head_row_loglik(dm.likelihood, dv, s_out * opre, yv, &rr, gl3);
+        if (!row_ok) rr = 0.f;
+        const float rk = rr * hc;                       // dh[col] = rk * Ko[col]
+        // ---- pass 2: dU, column sums, scalar sums
+        float g_w = 0.f, g_s = 0.f;
+#pragma unroll 1
+        for (int c = half * 32; c < BLOCK_N; c += 64) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)c, v);
+          float du[32], gk[32];
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 b2 = *reinterpret_cast<const float2*>(sb + c + j);
+            const float2 k2 = *reinterpret_cast<const float2*>(kos + c + j);
+            const float z0 = fmaf(__uint_as_float(v[j]), cz, b2.x);
+            const float z1 = fmaf(__uint_as_float(v[j + 1]), cz, b2.y);
+            const float t0 = tanh_fast(z0), t1 = tanh_fast(z1);
+            const float e0 = ex2_fast(z0 * 1.4426950408889634f), e1 = ex2_fast(z1 * 1.4426950408889634f);
+            const float df0 = (z0 > 0.f ? z0 : e0 - 1.f) - t0, df1 = (z1 > 0.f ? z1 : e1 - 1.f) - t1;   // elu - tanh
+            const float dt0 = fmaf(-t0, t0, 1.f), dt1 = fmaf(-t1, t1, 1.f);
+            const float da0 = fmaf(w, (z0 > 0.f ? 1.f : e0) - dt0, dt0);
+            const float da1 = fmaf(w, (z1 > 0.f ? 1.f : e1) - dt1, dt1);
+            gk[j] = rr * fmaf(w, df0, t0);              // r * h  (Dense_L kernel gradient addend)
+            gk[j + 1] = rr * fmaf(w, df1, t1);
+            const float dh0 = rk * k2.x, dh1 = rk * k2.y;
+            const float dz0 = dh0 * da0, dz1 = dh1 * da1;
+            g_w = fmaf(dh0, df0, fmaf(dh1, df1, g_w));
+            g_s = fmaf(dz0, z0, fmaf(dz1, z1, g_s));
+            du[j] = dz0 * s_l;
+            du[j + 1] = dz1 * s_l;
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(du[j], du[j + 1]);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          uint8_t* stg = staging + warp * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o0, stg, c, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L)
+#pragma unroll
+          for (int hh = 16; hh >= 1; hh >>= 1) {
+            const bool up = (lane & hh) != 0;
+#pragma unroll
+            for (int i = 0; i < hh; ++i) {
+              const float s0 = up ? du[i] : du[i + hh], k0 = up ? du[i + hh] : du[i];
+              du[i] = k0 + __shfl_xor_sync(0xffffffffu, s0, hh);
+              const float s1 = up ? gk[i] : gk[i + hh], k1 = up ? gk[i + hh] : gk[i];
+              gk[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, hh);
+            }
+          }
+          float* gp = a.gradp + (size_t)net * a.P;
+          atomicAdd(gp + a.off_bias + c + lane, du[0]);
+          atomicAdd(gp + dm.off_kernel[dm.L] + c + lane, gk[0] * hc);
+        }
+        tc_fence_before();
+        if (CTA2) mbar_arrive_remote(&tempty[acc], 0);
+        else mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // ---- scalar sums of the tile (one atomic per warp and quantity)
+        g_w = warp_sum(g_w);
+        g_s = warp_sum(g_s);
+        float* gp = a.gradp + (size_t)net * a.P;
+        if (lane == 0) {
+          atomicAdd(gp + dm.off_actw, g_w * w * (1.f - w));
+          atomicAdd(gp + dm.off_layer_scale[a.layer], (g_s / s_l) * sigmoid_f(pnet[dm.off_layer_scale[a.layer]]));
+        }
+        if (half == 0) {
+          const float a_ll = warp_sum(logp), a_gs = warp_sum(rr * opre), a_gb = warp_sum(rr * s_out);
+          const float a_g0 = warp_sum(gl3[0]), a_g1 = warp_sum(gl3[1]), a_g2 = warp_sum(gl3[2]);
+          if (lane == 0) {
+            atomicAdd(a.ll + net, a_ll);
+            if (dm.likelihood == BNF_NORMAL) {
+              atomicAdd(gp + 0, a_g0 * expf(pnet[0]));
+            } else {
+              atomicAdd(gp + 1, a_g1 * sigmoid_f(pnet[1]));
+              if (dm.likelihood == BNF_ZINB) { const float pi = dv[kDvPi]; atomicAdd(gp + 2, a_g2 * pi * (1.f - pi)); }
+            }
+            atomicAdd(gp + dm.off_out_scale, a_gs * sigmoid_f(pnet[dm.off_out_scale]));
+            atomicAdd(gp + dm.off_bias[dm.L], a_gb);
+          }
+        }
+        continue;
+      }
       if (MODE == TC_FWD) {
         const float s_l = dv[kDvSLayer + a.layer];
         c1 = s_l * a.isf;
@@ -974,7 +1125,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
   int grid = (int)(total < slots ? total : slots);
   if (grid < 1) grid = 1;
   if (CTA2) grid *= 2;
-  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD_HEAD ? "tc_fwd_head" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1019,7 +1170,7 @@ static bool want_cta2(const TcArgs& a, int block_n) {
 template <int BLOCK_N, int MN, int MODE>
 static int launch_tc_m(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
                        const DevModel* dm = nullptr) {
-  if constexpr (BLOCK_N == 256 && MN != 2 && (MODE == TC_FWD || MODE == TC_DGRAD_ACT || MODE == TC_WGRAD || MODE == TC_PLAIN_F32)) {
+  if constexpr (BLOCK_N == 256 && MN != 2 && (MODE == TC_FWD || MODE == TC_FWD_HEAD || MODE == TC_DGRAD_ACT || MODE == TC_WGRAD || MODE == TC_PLAIN_F32)) {
     if (want_cta2(a, BLOCK_N)) return launch_tc_k<BLOCK_N, MN, MODE, true>(ma, mb, om, a, sm_count, st, dm);
   }
   return launch_tc_k<BLOCK_N, MN, MODE, false>(ma, mb, om, a, sm_count, st, dm);
@@ -1036,6 +1187,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
     if (a.mode == TC_WGRAD) return launch_tc_m<BLOCK_N, 1, TC_WGRAD>(ma, mb, om, a, sm, st, dm);
     return launch_tc_m<BLOCK_N, 1, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else if constexpr (MN == 3) {
+    if (a.mode == TC_FWD_HEAD) return launch_tc_m<BLOCK_N, 3, TC_FWD_HEAD>(ma, mb, om, a, sm, st, dm);
     if (a.mode == TC_FWD) return launch_tc_m<BLOCK_N, 3, TC_FWD>(ma, mb, om, a, sm, st, dm);
     return launch_tc_m<BLOCK_N, 3, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else {
@@ -1109,6 +1261,41 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
   if (z && (rc = make_out_map(&om.o0, z, m.W, B, n_net))) return rc;
   if (use_wt) return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
   return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st);
+}
+
+// Last hidden layer of a TRAINING step: forward GEMM + head + log-likelihood + the layer's own
+// activation backward in one kernel (TC_FWD_HEAD).  Needs whole rows in one tile (W <= 256) and
+// the natural-layout weight copy.  Outputs: dU [n_net,B,W] bf16, ll[n_net] += loglik, grad +=
+// Dense_L / bias / scale / likelihood-parameter gradients.
+bool tc_fwd_head_supported(const DevModel& m) {
+  const char* e = getenv("BNF_NO_FUSED_HEAD_EPI");
+  if (e && e[0] == '1') return false;
+  return pick_block_n(m.W) == m.W && !tc_fwd_uses_wt();
+}
+
+int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const bf16* a_in, const bf16* wn,
+                const float* y, const int32_t* idx, int64_t idx_stride, bf16* dU, float* ll, float* grad,
+                int n_net, int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int layer = m.L - 1;
+  const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
+  if (!tc_fwd_head_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused head epilogue needs W in {64,128,256}");
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
+  if (rc) return rc;
+  if ((rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m), 64))) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_FWD_HEAD; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = Kp / 64;
+  a.m_valid = B; a.n_valid = m.W;
+  a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
+  a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
+  a.y = y; a.ll = ll; a.idx = idx; a.idx_stride = idx_stride; a.gradp = grad;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if ((rc = make_out_map(&om.o0, dU, m.W, B, n_net))) return rc;
+  return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
 // Fused feature encode + Dense_0 (models.py:216-268 for the first layer): the A operand is

@@ -21,6 +21,11 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
                  const __nv_bfloat16* a_in, const __nv_bfloat16* wt, const __nv_bfloat16* wn,
                  __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
 bool tc_fwd_uses_wt();
+// training step, last hidden layer: fwd GEMM + head + log-likelihood + activation backward
+bool tc_fwd_head_supported(const DevModel& m);
+int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const __nv_bfloat16* a_in,
+                const __nv_bfloat16* wn, const float* y, const int32_t* idx, int64_t idx_stride,
+                __nv_bfloat16* dU, float* ll, float* grad, int n_net, int B, cudaStream_t st);
 int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
                         const int32_t* idx, int64_t idx_stride, const __nv_bfloat16* wt,
                         __nv_bfloat16* feat, __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B,

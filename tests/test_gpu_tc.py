@@ -139,7 +139,7 @@ def test_bf16_training_tracks_fp32(cuda):
 
 
 @pytest.mark.parametrize('flag', ['BNF_FUSED_ENCODE', 'BNF_NO_FUSED_ACT_BWD', 'BNF_NO_FUSED_ENC_BWD',
-                                  'BNF_ENCODE_GENERIC'])
+                                  'BNF_ENCODE_GENERIC', 'BNF_NO_FUSED_HEAD_EPI'])
 def test_alternative_kernel_paths_agree(cuda, flag, monkeypatch):
   """The opt-in fused encode+Dense_0 kernel, the unfused dgrad/act_bwd pair and the unfused
   dgrad_0 / encode-backward pair compute the same thing as the default path (same bf16 storage;
