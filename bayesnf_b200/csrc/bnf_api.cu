@@ -358,7 +358,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
     }
     if (l > 0) {
       const char* nf = getenv("BNF_NO_FUSED_ACT_BWD");
-      if (tc && !(nf && nf[0] == '1')) {
+      if (tc && !(nf && nf[0] == '1') && tc_dgrad_act_supported(m)) {
         // dgrad + activation backward of layer l-1 in one kernel (epilogue fusion)
         int rc = tc_dgrad(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], nullptr, n_net, B, st,
                           (const bf16*)w.z[l - 1], params, w.derived, grad);

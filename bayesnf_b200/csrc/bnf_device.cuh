@@ -101,6 +101,100 @@ __device__ __forceinline__ float act_grad_fast(float z, float w, float* diff) {
   const float dt = fmaf(-t, t, 1.f);
   return fmaf(w, delu - dt, dt);
 }
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 on a 64-bit register pair) ---------------------
+// The tcgen05 epilogues are bound by the fma pipe (a 3-register FFMA has a reciprocal throughput
+// of 2 cycles per SMSP) and by issue slots; FFMA2 does two lanes' worth of work per issue, so the
+// element-wise math of those epilogues runs on pairs of adjacent accumulator columns.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_dup(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ float f2_lo(f32x2 v) {
+  float lo;
+  [[maybe_unused]] float hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float f2_hi(f32x2 v) {
+  [[maybe_unused]] float lo;
+  float hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {   // lo -> bits 0..15, hi -> bits 16..31
+  __nv_bfloat162 t = __floats2bfloat162_rn(f2_lo(v), f2_hi(v));
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// Per-kernel constants of the packed activation math (models.py:255-258).
+struct ActConst2 {
+  f32x2 w, omw, n_omw, log2e, n_one;
+  __device__ __forceinline__ explicit ActConst2(float wa)
+      : w(f2_dup(wa)), omw(f2_dup(1.f - wa)), n_omw(f2_dup(wa - 1.f)), log2e(f2_dup(1.4426950408889634f)),
+        n_one(f2_dup(-1.f)) {}
+};
+// Two activations at once; same element math as act_fast / act_grad_fast, written without
+// selects (a select of two packed halves costs two moves each): with m = min(z,0), r = max(z,0)
+//   e = 2^(m*log2e) (exactly 1 for z > 0), elu = r + (e-1), elu' = e, t = tanh(z),
+//   diff = elu - t, h = w*diff + t, act'(z) = w*e + (1-w)*(1-t^2)
+__device__ __forceinline__ f32x2 act_fast2(f32x2 z, const ActConst2& k) {
+  const float z0 = f2_lo(z), z1 = f2_hi(z);
+  const f32x2 t = f2_pack(tanh_fast(z0), tanh_fast(z1));
+  const f32x2 zl = f2_mul(f2_pack(fminf(z0, 0.f), fminf(z1, 0.f)), k.log2e);
+  const f32x2 em1 = f2_add(f2_pack(ex2_fast(f2_lo(zl)), ex2_fast(f2_hi(zl))), k.n_one);
+  const f32x2 elu = f2_add(f2_pack(fmaxf(z0, 0.f), fmaxf(z1, 0.f)), em1);
+  return f2_fma(k.w, f2_fma(t, k.n_one, elu), t);
+}
+__device__ __forceinline__ f32x2 act_grad_fast2(f32x2 z, const ActConst2& k, f32x2* diff, f32x2* h = nullptr) {
+  const float z0 = f2_lo(z), z1 = f2_hi(z);
+  const f32x2 t = f2_pack(tanh_fast(z0), tanh_fast(z1));
+  const f32x2 zl = f2_mul(f2_pack(fminf(z0, 0.f), fminf(z1, 0.f)), k.log2e);
+  const f32x2 e = f2_pack(ex2_fast(f2_lo(zl)), ex2_fast(f2_hi(zl)));
+  const f32x2 elu = f2_add(f2_pack(fmaxf(z0, 0.f), fmaxf(z1, 0.f)), f2_add(e, k.n_one));
+  const f32x2 d = f2_fma(t, k.n_one, elu);
+  *diff = d;
+  if (h) *h = f2_fma(k.w, d, t);
+  const f32x2 dtw = f2_fma(f2_mul(t, t), k.n_omw, k.omw);      // (1-w)*(1-t^2)
+  return f2_fma(k.w, e, dtw);
+}
+
+// Column sums over a warp's 32 rows: lane r holds row r's 32 values v[0..31]; a 5-step
+// transpose-reduce (31 shuffles) leaves sum_r v_r[L] in v[0] of lane L.
+__device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int hh = 16; hh >= 1; hh >>= 1) {
+    const bool up = (lane & hh) != 0;
+#pragma unroll
+    for (int i = 0; i < hh; ++i) {
+      const float send = up ? v[i] : v[i + hh];
+      const float keep = up ? v[i + hh] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, hh);
+    }
+  }
+}
+
 // sin/cos for the bf16 path with arguments up to ~1e5 rad (seasonal features): one exact
 // f32 range reduction to [-pi, pi] (two-constant Cody-Waite) and the MUFU approximations.
 // Absolute error ~1e-6 + |x|*6e-8 (the latter is the rounding of the f32 argument itself,

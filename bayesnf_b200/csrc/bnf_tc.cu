@@ -235,14 +235,18 @@ struct TcArgs {
 #define DBG(bit) 0
 #endif
 
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter
-// Warp roles.  The SM's issue arbiter favours the highest warp id, so the single-thread MMA
-// issuer and the TMA producer are the LAST two warps of the CTA: the eight epilogue warps
-// (ids 0..7) can never starve the tensor-core feed.  (A_MODE 2 adds encoder warps after them.)
-constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+// Epilogue warps per mode (ids 0..kEpi-1; kEpi/4 warps share one TMEM lane quarter and interleave
+// its 32-column chunks).  Measured (profiles/experiments/README.md, r1s): 16 warps for the forward
+// epilogue change nothing at W=256 (31.2 vs 31.3 us) -- that kernel is bound by writing z and h
+// (84 MB per layer at ~2.7 TB/s), not by epilogue latency -- and cost a ring stage at W=1024, so
+// every mode runs two warps per quarter.
+__host__ __device__ constexpr int epi_warps_of(int /*mode*/, int /*a_mode*/) { return 8; }
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+
 constexpr int kXTileBytes = 128 * kMaxD * 4;
+constexpr int kBarBytes = 512;                     // mbarriers + TMEM base slot
+constexpr int kZRing = 2;                          // TC_DGRAD_ACT: per-warp ring of 32x32 z tiles
+constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer whose bias sums stay in smem
 // A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
 // encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major;
 // 3 = A K-major, B MN-major (forward straight from the natural (in,out) bf16 kernel copy, so the
@@ -257,19 +261,26 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   static constexpr int kGBytes = MODE == TC_DGRAD_ENC ? 128 * (BLOCK_N + 1) * 4 + 2 * 128 * (kMaxD + 1) * 4 : 0;
   // TC_FWD_HEAD: Dense_L kernel [2][256] + per-row partial dots [2][128] in shared memory
   static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 2 * 128) * 4 : 0;
+  // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
+  // plus a ring of kZRing z tiles landed by TMA
+  static constexpr int kStgWarp = MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096;
   static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
       MODE == TC_FWD_HEAD ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : 4)) :
+      MODE == TC_DGRAD_ACT ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7))) :
       (A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
-  static constexpr int kThreads = kTcThreads + (A_MODE == 2 ? 32 * kEncWarps : 0);
+  static constexpr int kEpi = epi_warps_of(MODE, A_MODE);
+  static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpiWarps * 4096;   // per epilogue warp: two 32x32 bf16 tiles
+  static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpi * kStgWarp;
+  // CTA-wide partial sums of the epilogue's column / scalar gradients (flushed to HBM when the
+  // network changes): TC_DGRAD_ACT [kAccCols] bias columns + scalars, TC_FWD_HEAD 2 x 256 columns
+  static constexpr int kAccFloats = MODE == TC_DGRAD_ACT ? kAccCols + 32 : (MODE == TC_FWD_HEAD ? 512 + 32 : 0);
   static constexpr int kMinBlocks = (MODE == TC_DGRAD_ENC && BLOCK_N == 64) ? 2 : 1;
-  static_assert(kStages * kStageBytes + kStagingBytes + 256 + 2 * 256 * 4 + kXBytes + kGBytes + kHeadBytes <= 232448,
-                "dynamic shared memory exceeds the 227 KB per-CTA limit");
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes + kHeadBytes;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarBytes + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes + kHeadBytes + kAccFloats * 4;
+  static_assert(kSmem <= 232448, "dynamic shared memory exceeds the 227 KB per-CTA limit");
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
@@ -283,6 +294,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr bool B_MN = A_MODE == 1 || A_MODE == 3;   // B operand MN-major
   constexpr bool ENCODE = A_MODE == 2;
   static_assert(!(CTA2 && ENCODE), "the fused encode kernel is single-CTA");
+  constexpr int kEpi = Cfg::kEpi;                    // epilogue warps (ids 0..kEpi-1)
+  constexpr int kParts = kEpi / 4;                   // warps per TMEM lane quarter = column interleave
+  constexpr int kProd = kEpi, kMma = kEpi + 1;       // producer / MMA issuer: the highest warp ids
+  constexpr int kBaseThreads = 64 + 32 * kEpi;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
@@ -294,7 +309,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
   uint64_t* xfull = tempty + 3;                      // A_MODE 2: raw input tile landed
-  float* sbias = (float*)(staging + Cfg::kStagingBytes + 256);  // [2][256]: s_l * bias of the tile's columns
+  uint64_t* zbar = bars + 40;                        // TC_DGRAD_ACT: [kEpi][kZRing] z tile landed
+  float* sbias = (float*)(staging + Cfg::kStagingBytes + kBarBytes);  // [2][256]: s_l * bias of the tile's columns
+  float* colacc = (float*)(smem + Cfg::kSmem - Cfg::kAccFloats * 4);  // TC_DGRAD_ACT / TC_FWD_HEAD partial sums
   float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
   float* gtile = sbias + 2 * 256;                    // TC_DGRAD_ENC: [128][BLOCK_N+1] f32 dfeat tile
   float* eacc = sbias;                               // TC_DGRAD_ENC: [2*kMaxD+3] partial sums
@@ -310,10 +327,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&empty[s], 1);
       if (ENCODE) mbar_init(&xfull[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (CTA2 ? 2 : 1) * 32 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (CTA2 ? 2 : 1) * 32 * kEpi); }
+    if (MODE == TC_DGRAD_ACT) for (int s = 0; s < kEpi * kZRing; ++s) mbar_init(&zbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp) {
+  for (int i = threadIdx.x; i < Cfg::kAccFloats; i += Cfg::kThreads) colacc[i] = 0.f;
+  if (warp == kMma) {
     if (CTA2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                    ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::kTmemCols) : "memory");
@@ -324,9 +343,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  if (ENCODE && warp > kMmaWarp) {
+  if (ENCODE && warp > kMma) {
     // zero the A slots once: pad columns [F, Fp) are never written again
-    const int et = threadIdx.x - kTcThreads;
+    const int et = threadIdx.x - kBaseThreads;
     for (int s = 0; s < Cfg::kStages; ++s) {
       uint4* pz = reinterpret_cast<uint4*>(smem + s * Cfg::kStageBytes);
       for (int i = et; i < Cfg::kABytes / 16; i += 32 * kEncWarps) pz[i] = make_uint4(0, 0, 0, 0);
@@ -355,7 +374,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
   const int tile_step = contiguous ? 1 : n_ctas;
 
-  if (warp == kProducerWarp) {
+  if (warp == kProd) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0;
@@ -422,7 +441,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
     }
-  } else if (warp == kMmaWarp) {
+  } else if (warp == kMma) {
     // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
     if (!CTA2 || cta_rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): f32 accum, bf16 x bf16
@@ -470,15 +489,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < kEpiWarps) {
+  } else if (warp < kEpi) {
     // ===================== epilogue (warps 0..7) =====================
     // warp%4 selects the TMEM lane quarter it may read; the two warps of a quarter
     // take alternate 32-column chunks, so every SM sub-partition has two epilogue
     // warps to hide tcgen05.ld / MUFU / store latency behind each other.
     const int q = warp & 3;
-    const int half = warp >> 2;
+    const int half = warp >> 2;        // which of the quarter's kParts warps: column chunks half, half+kParts, ...
     const int epi_tid = threadIdx.x;
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t zc = 0;                 // TC_DGRAD_ACT: this warp's running chunk count (z ring slot / phase)
+    int acc_net = -1;                // TC_DGRAD_ACT / TC_FWD_HEAD: network whose partial sums sit in colacc
     if (MODE == TC_DGRAD_ENC && epi_tid < 2 * kMaxD + 3) eacc[epi_tid] = 0.f;
     for (int t = tile0; t < tile_end; t += tile_step) {
       const int net = t / tiles_per_net;
@@ -504,11 +525,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const float hc = s_out * dm.inv_sqrt_W;
         const float bo = pnet[dm.off_bias[dm.L]];
         float* kos = kos_s + acc * 256;
+        if (net != acc_net) {
+          // the network changed: flush the CTA's column sums of the previous one (kept in shared
+          // memory so that no global atomic is in flight at the chunk loop's proxy fences)
+          if (acc_net >= 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
+            float* g = a.gradp + (size_t)acc_net * a.P;
+            if (epi_tid < BLOCK_N) {
+              atomicAdd(g + a.off_bias + epi_tid, colacc[epi_tid]);
+              atomicAdd(g + dm.off_kernel[dm.L] + epi_tid, colacc[256 + epi_tid]);
+              colacc[epi_tid] = 0.f;
+              colacc[256 + epi_tid] = 0.f;
+            }
+          }
+          acc_net = net;     // (the bar.sync below orders the zeroing before the tile's adds)
+        }
         if (epi_tid < BLOCK_N) {
           sb[epi_tid] = s_l * pnet[a.off_bias + epi_tid];
           kos[epi_tid] = pnet[dm.off_kernel[dm.L] + epi_tid];
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
         const int row = m_t * 128 + q * 32 + lane;
         const bool row_ok = row < a.m_valid;
         float yv = 0.f;
@@ -516,8 +552,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-        // ---- pass 1: partial dot of this warp's column chunks
-        float dot = 0.f;
+        // ---- pass 1: partial dot of this warp's column chunks (packed f32x2 math: FFMA2)
+        const ActConst2 ak(w);
+        const f32x2 cz2 = f2_dup(cz);
+        f32x2 dot2 = 0ull;
 #pragma unroll 1
         for (int c = half * 32; c < BLOCK_N; c += 64) {
           uint32_t v[32];
@@ -526,12 +564,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
             const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
-            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j]), cz, b4.x), w), k4.x, dot);
-            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 1]), cz, b4.y), w), k4.y, dot);
-            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 2]), cz, b4.z), w), k4.z, dot);
-            dot = fmaf(act_fast(fmaf(__uint_as_float(v[j + 3]), cz, b4.w), w), k4.w, dot);
+            dot2 = f2_fma(act_fast2(f2_fma(f2_pack(v[j], v[j + 1]), cz2, f2_pack(b4.x, b4.y)), ak),
+                          f2_pack(k4.x, k4.y), dot2);
+            dot2 = f2_fma(act_fast2(f2_fma(f2_pack(v[j + 2], v[j + 3]), cz2, f2_pack(b4.z, b4.w)), ak),
+                          f2_pack(k4.z, k4.w), dot2);
           }
         }
+        const float dot = f2_lo(dot2) + f2_hi(dot2);
         rowdot[half * 128 + q * 32 + lane] = dot;
         asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");        // the two warps of this lane quarter
         const float opre = (rowdot[q * 32 + lane] + rowdot[128 + q * 32 + lane]) * dm.inv_sqrt_W + bo;
@@ -541,38 +580,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (row_ok) logp = head_row_loglik(dm.likelihood, dv, s_out * opre, yv, &rr, gl3);
         if (!row_ok) rr = 0.f;
         const float rk = rr * hc;                       // dh[col] = rk * Ko[col]
-        // ---- pass 2: dU, column sums, scalar sums
-        float g_w = 0.f, g_s = 0.f;
+        // ---- pass 2: dU, column sums, scalar sums.  Per column pair (FFMA2): kd = Ko*act'(z),
+        // dU = kd*(rk*s_l); sum Ko*diff and sum kd*z are scaled by the row's rk after the loop.
+        const f32x2 rr2 = f2_dup(rr);
+        const f32x2 rks2 = f2_dup(rk * s_l);
+        f32x2 gw2 = 0ull, gs2 = 0ull;
 #pragma unroll 1
         for (int c = half * 32; c < BLOCK_N; c += 64) {
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c, v);
-          float du[32], gk[32];
           uint32_t pk[16];
+          float du[32], gk[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 b2 = *reinterpret_cast<const float2*>(sb + c + j);
-            const float2 k2 = *reinterpret_cast<const float2*>(kos + c + j);
-            const float z0 = fmaf(__uint_as_float(v[j]), cz, b2.x);
-            const float z1 = fmaf(__uint_as_float(v[j + 1]), cz, b2.y);
-            const float t0 = tanh_fast(z0), t1 = tanh_fast(z1);
-            const float e0 = ex2_fast(z0 * 1.4426950408889634f), e1 = ex2_fast(z1 * 1.4426950408889634f);
-            const float df0 = (z0 > 0.f ? z0 : e0 - 1.f) - t0, df1 = (z1 > 0.f ? z1 : e1 - 1.f) - t1;   // elu - tanh
-            const float dt0 = fmaf(-t0, t0, 1.f), dt1 = fmaf(-t1, t1, 1.f);
-            const float da0 = fmaf(w, (z0 > 0.f ? 1.f : e0) - dt0, dt0);
-            const float da1 = fmaf(w, (z1 > 0.f ? 1.f : e1) - dt1, dt1);
-            gk[j] = rr * fmaf(w, df0, t0);              // r * h  (Dense_L kernel gradient addend)
-            gk[j + 1] = rr * fmaf(w, df1, t1);
-            const float dh0 = rk * k2.x, dh1 = rk * k2.y;
-            const float dz0 = dh0 * da0, dz1 = dh1 * da1;
-            g_w = fmaf(dh0, df0, fmaf(dh1, df1, g_w));
-            g_s = fmaf(dz0, z0, fmaf(dz1, z1, g_s));
-            du[j] = dz0 * s_l;
-            du[j + 1] = dz1 * s_l;
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(du[j], du[j + 1]);
-            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+            const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
+#pragma unroll
+            for (int jj = 0; jj < 4; jj += 2) {
+              const f32x2 b2 = jj ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+              const f32x2 k2 = jj ? f2_pack(k4.z, k4.w) : f2_pack(k4.x, k4.y);
+              const f32x2 z2 = f2_fma(f2_pack(v[j + jj], v[j + jj + 1]), cz2, b2);
+              f32x2 d2, h2;
+              const f32x2 da2 = act_grad_fast2(z2, ak, &d2, &h2);
+              const f32x2 kd2 = f2_mul(k2, da2);
+              gw2 = f2_fma(k2, d2, gw2);
+              gs2 = f2_fma(kd2, z2, gs2);
+              const f32x2 gk2 = f2_mul(h2, rr2);            // r * h  (Dense_L kernel gradient addend)
+              const f32x2 du2 = f2_mul(kd2, rks2);
+              gk[j + jj] = f2_lo(gk2); gk[j + jj + 1] = f2_hi(gk2);
+              du[j + jj] = f2_lo(du2); du[j + jj + 1] = f2_hi(du2);
+              pk[(j + jj) >> 1] = f2_to_bf16x2(du2);
+            }
           }
-          uint8_t* stg = staging + warp * 4096;
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -585,22 +625,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, c, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L)
-#pragma unroll
-          for (int hh = 16; hh >= 1; hh >>= 1) {
-            const bool up = (lane & hh) != 0;
-#pragma unroll
-            for (int i = 0; i < hh; ++i) {
-              const float s0 = up ? du[i] : du[i + hh], k0 = up ? du[i + hh] : du[i];
-              du[i] = k0 + __shfl_xor_sync(0xffffffffu, s0, hh);
-              const float s1 = up ? gk[i] : gk[i + hh], k1 = up ? gk[i + hh] : gk[i];
-              gk[i] = k1 + __shfl_xor_sync(0xffffffffu, s1, hh);
-            }
-          }
-          float* gp = a.gradp + (size_t)net * a.P;
-          atomicAdd(gp + a.off_bias + c + lane, du[0]);
-          atomicAdd(gp + dm.off_kernel[dm.L] + c + lane, gk[0] * hc);
+          // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L):
+          // bias gradient and Dense_L kernel gradient, added to the CTA's shared-memory partial sums
+          warp_transpose_sum(du, lane);
+          warp_transpose_sum(gk, lane);
+          atomicAdd(&colacc[c + lane], du[0]);
+          atomicAdd(&colacc[256 + c + lane], gk[0] * hc);
         }
+        float g_w = rk * (f2_lo(gw2) + f2_hi(gw2));      // sum dh*diff,  dh = rk*Ko
+        float g_s = rk * (f2_lo(gs2) + f2_hi(gs2));      // sum dz*z,     dz = dh*act'(z)
         tc_fence_before();
         if (CTA2) mbar_arrive_remote(&tempty[acc], 0);
         else mbar_arrive(&tempty[acc]);
@@ -636,25 +669,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         w_act = dv[kDvActW];
         if (epi_tid < BLOCK_N)
           sb[epi_tid] = s_l * a.params[(size_t)net * a.P + a.off_bias + n_t * BLOCK_N + epi_tid];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
       }
       const int row = m_t * 128 + q * 32 + lane;
       const bool row_ok = row < a.m_valid;
-      // TC_DGRAD_ACT: this row's z of the previous layer, register-prefetched one chunk ahead
-      // (two chunks ahead, so the DRAM latency of the strided z rows hides behind the math of
-      // the chunks in between; the chunk loop itself stays rolled to keep the code in I-cache)
-      float s_prev = 0.f, g_w = 0.f, g_s = 0.f;
-      uint4 zq0[4], zq1[4];
-      const bf16* zrow = nullptr;
+      // TC_DGRAD_ACT: the z tile (bf16, previous layer's forward epilogue) of every 32x32 chunk
+      // arrives by TMA in this warp's ring of kZRing 64B-swizzled 2 KB slots, kZRing chunks ahead;
+      // each lane then reads its own row with conflict-free 16-byte LDS.  The epilogue issues NO
+      // global loads or atomics inside the chunk loop: the fence.proxy.async in front of every
+      // TMA store is a MEMBAR.ALL.CTA, which waits for all of the thread's outstanding LSU
+      // traffic -- with per-lane z loads and per-chunk atomics in flight every chunk paid a full
+      // DRAM round trip (measured: 15.1 -> 10.1 ms on the wind shard with both removed).
+      float s_prev = 0.f;
+      f32x2 gw2 = 0ull, gs2 = 0ull, cdu2 = 0ull;   // packed partial sums (both halves 0.f)
+      constexpr int kChunks = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;   // chunks per warp and tile
+      uint8_t* zring = staging + warp * Cfg::kStgWarp + 2048;
+      uint64_t* zb = zbar + warp * kZRing;
       if (MODE == TC_DGRAD_ACT) {
+        if (net != acc_net) {
+          // the network changed: flush the CTA's partial sums of the previous one
+          if (acc_net >= 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
+            float* g = a.gradp + (size_t)acc_net * a.P;
+            for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) {
+              atomicAdd(g + a.off_bias_prev + i, colacc[i]);
+              colacc[i] = 0.f;
+            }
+            if (epi_tid < 2) {
+              atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
+              colacc[kAccCols + epi_tid] = 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // zeroed before new adds
+          }
+          acc_net = net;
+        }
         w_act = dv[kDvActW];
         s_prev = dv[kDvSLayer + a.layer_prev];
-        zrow = a.zin + (size_t)net * a.out_batch + (size_t)min(row, a.m_valid - 1) * a.ld_out + n_t * BLOCK_N;
+        cdu2 = f2_dup(a.isf * s_prev);
+        if (lane == 0 && !DBG(1)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (DBG(1)) { zq0[k] = make_uint4(0, 0, 0, 0); zq1[k] = zq0[k]; continue; }
-          zq0[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32) + k);
-          if (BLOCK_N > 64) zq1[k] = __ldg(reinterpret_cast<const uint4*>(zrow + half * 32 + 64) + k);
+          for (int i = 0; i < kZRing && i < kChunks; ++i) {
+            const uint32_t sl = (zc + i) % kZRing;
+            mbar_arrive_expect_tx(&zb[sl], 2048);
+            tma_load_3d(zring + sl * 2048, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 64 * i, m_t * 128 + q * 32, net);
+          }
         }
       }
       // TC_DGRAD_ENC: a tile's input rows -> shared memory (scaled by 1/(input_scale*exp(lsa));
@@ -664,7 +722,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int net_x = tt / tiles_per_net;
         const int m_x = (tt % tiles_per_net) / (a.n_tiles * a.k_splits);
         const float* dvx = a.derived + (size_t)net_x * kDerivedStride;
-        for (int e = epi_tid; e < 128 * dm.D; e += 32 * kEpiWarps) {
+        for (int e = epi_tid; e < 128 * dm.D; e += 32 * kEpi) {
           const int r = e / dm.D, i = e - r * dm.D;
           const int b = min(m_x * 128 + r, a.m_valid - 1);
           const float xv = a.x[(a.idx ? (size_t)a.idx[(size_t)net_x * a.idx_stride + b] : (size_t)b) * dm.D + i];
@@ -678,30 +736,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = half * 32; c < BLOCK_N; c += 64) {
+      for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
         if (MODE == TC_FWD) {
           uint32_t zp[16], hp[16];
+          const ActConst2 ak(w_act);
+          const f32x2 c12 = f2_dup(c1);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int jj = 0; jj < 4; jj += 2) {
-            float z0 = fmaf(__uint_as_float(v[j + jj]), c1, bb[jj]);
-            float z1 = fmaf(__uint_as_float(v[j + jj + 1]), c1, bb[jj + 1]);
-            __nv_bfloat162 zz = __floats2bfloat162_rn(z0, z1);
-            __nv_bfloat162 hh = DBG(8) ? __floats2bfloat162_rn(z1, z0) : __floats2bfloat162_rn(act_fast(z0, w_act), act_fast(z1, w_act));
-            zp[(j + jj) >> 1] = *reinterpret_cast<uint32_t*>(&zz);
-            hp[(j + jj) >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+              // packed f32x2 math (FFMA2): z = acc*c1 + s_l*b, h = act(z)
+              const f32x2 z2 = f2_fma(f2_pack(v[j + jj], v[j + jj + 1]), c12, jj ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
+              zp[(j + jj) >> 1] = f2_to_bf16x2(z2);
+              hp[(j + jj) >> 1] = f2_to_bf16x2(DBG(8) ? z2 : act_fast2(z2, ak));
             }
           }
           // registers -> 64B-swizzled smem tile (conflict-free 16B stores) -> TMA store:
           // full 64-byte rows leave the SM as bulk writes instead of 32 scattered
           // 16-byte stores per instruction; rows >= B are clipped by the tensor map.
-          uint8_t* stg = staging + warp * 4096;
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
           if (lane == 0 && !DBG(4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -723,36 +780,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // separate act_bwd kernel used to do (bias column sums, activation-mix and
           // layer-scale scalars).  models.py:255-268 backward.
           uint32_t zw[16];
+          const uint32_t zsl = zc % kZRing;
+          if (!DBG(1)) {
+            mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
+            const uint8_t* zt = zring + zsl * 2048 + lane * 64;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            zw[4 * k] = zq0[k].x; zw[4 * k + 1] = zq0[k].y; zw[4 * k + 2] = zq0[k].z; zw[4 * k + 3] = zq0[k].w;
-            zq0[k] = zq1[k];
-            if (c + 128 < BLOCK_N && !DBG(1)) zq1[k] = __ldg(reinterpret_cast<const uint4*>(zrow + c + 128) + k);
+            for (int k = 0; k < 4; ++k) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(zt + ((k ^ ((lane >> 1) & 3)) << 4));
+              zw[4 * k] = q4.x; zw[4 * k + 1] = q4.y; zw[4 * k + 2] = q4.z; zw[4 * k + 3] = q4.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zw[k] = 0u;
           }
-          float du[32];
+          // packed f32x2 math on adjacent column pairs (FFMA2): x = acc*act'(z), dU = x*(isf*s_prev);
+          // the scalar sums are kept unscaled (sum acc*diff, sum x*z) and scaled once per tile
           uint32_t pk[16];
+          float du[32];
+          const ActConst2 ak(w_act);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&zw[j >> 1]);
-            const float z0 = __low2float(z2), z1 = __high2float(z2);
-            float d0, d1;
-            // rows >= B carry a zero accumulator (their A rows were zero-filled by TMA)
-            const float dh0 = __uint_as_float(v[j]) * a.isf;
-            const float dh1 = __uint_as_float(v[j + 1]) * a.isf;
-            float da0, da1;
-            if (DBG(8)) { da0 = z0; da1 = z1; d0 = z1; d1 = z0; }
-            else { da0 = act_grad_fast(z0, w_act, &d0); da1 = act_grad_fast(z1, w_act, &d1); }
-            const float dz0 = dh0 * da0, dz1 = dh1 * da1;
-            g_w = fmaf(dh0, d0, fmaf(dh1, d1, g_w));
-            g_s = fmaf(dz0, z0, fmaf(dz1, z1, g_s));
-            du[j] = dz0 * s_prev;
-            du[j + 1] = dz1 * s_prev;
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(du[j], du[j + 1]);
-            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+            const uint32_t zb = zw[j >> 1];
+            const f32x2 z2 = f2_pack(zb << 16, zb & 0xffff0000u);
+            const f32x2 v2 = f2_pack(v[j], v[j + 1]);
+            f32x2 d2;
+            f32x2 da2 = act_grad_fast2(z2, ak, &d2);
+            if (DBG(8)) { da2 = z2; d2 = z2; }
+            const f32x2 x2 = f2_mul(v2, da2);
+            gw2 = f2_fma(v2, d2, gw2);
+            gs2 = f2_fma(x2, z2, gs2);
+            const f32x2 du2 = f2_mul(x2, cdu2);
+            du[j] = f2_lo(du2);
+            du[j + 1] = f2_hi(du2);
+            pk[j >> 1] = f2_to_bf16x2(du2);
           }
-          uint8_t* stg = staging + warp * 4096;
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
           if (lane == 0 && !DBG(4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
+          // every lane holds its z values in registers: refill the slot with the tile kZRing ahead
+          if (lane == 0 && c + 64 * kZRing < BLOCK_N && !DBG(1)) {
+            mbar_arrive_expect_tx(&zb[zsl], 2048);
+            tma_load_3d(zring + zsl * 2048, &map_o1, &zb[zsl], col0 + 64 * kZRing, m_t * 128 + q * 32, net);
+          }
+          ++zc;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
@@ -764,19 +834,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (DBG(2)) continue;
-          // bias gradient: column sums over this warp's 32 rows by a transpose-reduce
-          // (31 shuffles); lane L ends up with column L, one coalesced atomic per chunk.
-#pragma unroll
-          for (int hh = 16; hh >= 1; hh >>= 1) {
-            const bool up = (lane & hh) != 0;
-#pragma unroll
-            for (int i = 0; i < hh; ++i) {
-              const float send = up ? du[i] : du[i + hh];
-              const float keep = up ? du[i + hh] : du[i];
-              du[i] = keep + __shfl_xor_sync(0xffffffffu, send, hh);
-            }
-          }
-          atomicAdd(a.gradp + (size_t)net * a.P + a.off_bias_prev + col0 + lane, du[0]);
+          // bias gradient: column sums over this warp's 32 rows by a transpose-reduce (31
+          // shuffles; lane L ends up with column L), added to the CTA's shared-memory partial
+          // sums.  (mma.sync on the staged tile was tried for this and is far slower: the legacy
+          // HMMA queues behind the tcgen05 MMAs in flight -- profiles/experiments/README.md.)
+          warp_transpose_sum(du, lane);
+          atomicAdd(&colacc[col0 + lane], du[0]);
         } else if (MODE == TC_DGRAD_BF16) {
           uint32_t pk[16];
 #pragma unroll
@@ -784,7 +847,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[j]) * a.isf, __uint_as_float(v[j + 1]) * a.isf);
             pk[j >> 1] = *reinterpret_cast<uint32_t*>(&t2);
           }
-          uint8_t* stg = staging + warp * 4096;
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -825,7 +888,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // two 128-byte lines) instead of one float in each of 32 rows: 32x fewer L2 requests,
           // which is what bounds the split-K reduction at small shapes.  (Parameter leaves sit
           // at arbitrary 4-byte offsets of the flat vector, so no 16-byte vector atomics.)
-          float* st32 = reinterpret_cast<float*>(staging + warp * 4096);
+          float* st32 = reinterpret_cast<float*>(staging + warp * Cfg::kStgWarp);
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -857,12 +920,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (MODE == TC_DGRAD_ENC) {
         // ---- feature-encode backward of this tile's 128 rows (same math
         // as encode_bwd_kernel<true>): a warp owns whole units, its lanes stride over the rows.
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // tile complete
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // tile complete
         if (t + 1 < tile_end) stage_x(t + 1, sx_nxt);
         const float* dvp = a.derived + (size_t)net * kDerivedStride;
         const int U = num_units(dm);
         const float two_pi = 6.283185307179586f;
-        for (int u = warp; u < U; u += kEpiWarps) {
+        for (int u = warp; u < U; u += kEpi) {
           const UnitInfo ui = decode_unit(dm, u);
           int slot = 0, dim_a = 0, dim_b = -1;
           if (ui.kind == 0) { slot = 0; dim_a = ui.a; }
@@ -931,7 +994,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (dim_b >= 0) atomicAdd(&eacc[dim_b], gl_b);
           }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");     // sums complete, tile free
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // sums complete, tile free
         const int nacc = dm.D + 3 + dm.D;
         const bool flush = t + 1 >= tile_end || (t + 1) / tiles_per_net != net;
         if (flush && epi_tid < nacc) {
@@ -950,14 +1013,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       if (MODE == TC_DGRAD_ACT) {
-        g_w = warp_sum(g_w);
-        g_s = warp_sum(g_s);
+        const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2)) * a.isf;     // sum dh*diff,  dh = acc*isf
+        const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2)) * a.isf;     // sum dz*z,     dz = dh*act'(z)
         if (lane == 0) {
-          float* g = a.gradp + (size_t)net * a.P;
-          atomicAdd(g + a.off_actw, g_w * w_act * (1.f - w_act));
-          atomicAdd(g + a.off_ls_prev, (g_s / s_prev) * sigmoid_f(a.params[(size_t)net * a.P + a.off_ls_prev]));
+          atomicAdd(&colacc[kAccCols], g_w * w_act * (1.f - w_act));
+          atomicAdd(&colacc[kAccCols + 1], (g_s / s_prev) * sigmoid_f(a.params[(size_t)net * a.P + a.off_ls_prev]));
         }
       }
+    }
+    if (MODE == TC_FWD_HEAD && acc_net >= 0) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
+      float* g = a.gradp + (size_t)acc_net * a.P;
+      if (epi_tid < BLOCK_N) {
+        atomicAdd(g + a.off_bias + epi_tid, colacc[epi_tid]);
+        atomicAdd(g + dm.off_kernel[dm.L] + epi_tid, colacc[256 + epi_tid]);
+      }
+    }
+    if (MODE == TC_DGRAD_ACT && acc_net >= 0) {
+      // the CTA's last network: flush its partial sums
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
+      float* g = a.gradp + (size_t)acc_net * a.P;
+      for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) atomicAdd(g + a.off_bias_prev + i, colacc[i]);
+      if (epi_tid < 2) atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (ENCODE) {
@@ -966,7 +1043,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // Each item writes its one or two bf16 feature values straight into the 128B-swizzled
     // K-major A tile the MMA reads; the finished tile is also TMA-stored as `feat` (wgrad
     // of Dense_0 needs it) by one elected thread.
-    const int et = threadIdx.x - kTcThreads;
+    const int et = threadIdx.x - kBaseThreads;
     const int U = num_units(dm);
     const float two_pi = 6.283185307179586f;
     int stage = 0; uint32_t phase = 0;
@@ -1042,7 +1119,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (CTA2) cluster_sync_all();        // the peer's smem / TMEM stay alive until both CTAs are done
-  if (warp == kMmaWarp) {
+  if (warp == kMma) {
     __syncwarp();
     tc_fence_after();
     if (CTA2)
@@ -1346,6 +1423,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
                 (a.mode == TC_DGRAD_ACT && want_cta2(a, bn)) ? bn / 2 : bn);
   if (rc) return rc;
   if (z_prev) {
+    if (Kp > kAccCols) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad + activation backward needs W <= 1024");
     a.zin = z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
     a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
     a.off_ls_prev = m.off_layer_scale[layer - 1]; a.off_actw = m.off_actw;
@@ -1358,8 +1436,12 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   OutMaps om;
   memset(&om, 0, sizeof(om));
   if (out_bf && (rc = make_out_map(&om.o0, out_bf, Kp, B, n_net))) return rc;
+  // the z tiles of the fused activation backward are TMA-loaded through the second map
+  if (z_prev && (rc = make_out_map(&om.o1, z_prev, Kp, B, n_net))) return rc;
   return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
+
+bool tc_dgrad_act_supported(const DevModel& m) { return m.W <= kAccCols; }
 
 // Layer-0 dgrad fused with the feature-encode backward: dfeat = isf * dU_0 @ K_0^T never leaves
 // the SM (TMEM -> shared-memory tile); the epilogue warps reduce it against the regenerated

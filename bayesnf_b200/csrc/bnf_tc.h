@@ -37,6 +37,8 @@ int tc_dgrad(const bnf_plan* p, int layer, const __nv_bfloat16* wn, const __nv_b
              __nv_bfloat16* out_bf, float* out_f32, int n_net, int B, cudaStream_t st,
              const __nv_bfloat16* z_prev = nullptr, const float* params = nullptr,
              const float* derived = nullptr, float* grad = nullptr);
+// the fused dgrad + activation backward keeps a layer's bias column sums in shared memory
+bool tc_dgrad_act_supported(const DevModel& m);
 // layer-0 dgrad with the feature-encode backward fused into its epilogue (dfeat stays on chip)
 bool tc_dgrad0_enc_supported(const DevModel& m);
 int tc_dgrad0_enc(const bnf_plan* p, const __nv_bfloat16* wn, const __nv_bfloat16* dU, const float* x,

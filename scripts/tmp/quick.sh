@@ -1,7 +1,7 @@
 set -x
 timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q -x 2>&1 | tail -15
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -5
-for env in "X=1" "BNF_NO_FUSED_HEAD_EPI=1"; do
+for env in "X=1"; do
 env $env timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 for line in sys.stdin:
