@@ -192,6 +192,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// registers -> TMEM (32 lanes x 32 columns); the caller issues tmem_st_wait() before re-reading
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -225,14 +238,18 @@ struct TcArgs {
   int out_cm; // TC_DGRAD_F32: write outf column-major [net][col][row]
   const float* y; float* ll;   // TC_FWD_HEAD: observations, per-network log-likelihood accumulators
   int dbg;   // BNF_TC_DBG ablation mask (only read when compiled with -DBNF_TC_EXPERIMENT)
+  long long* tl;   // BNF_TC_TL timeline buffer [cta][16 tiles][16 events] of clock64 (experiment builds)
 };
 // Epilogue ablation hooks for scripts/epi_experiment.py: compiled out unless -DBNF_TC_EXPERIMENT.
 // bits: 1 skip z loads (dgrad), 2 skip bias column sums (dgrad), 4 skip TMA stores, 8 skip the
 // activation math.  Results are wrong with a non-zero mask - timing only.
 #ifdef BNF_TC_EXPERIMENT
 #define DBG(bit) (a.dbg & (bit))
+// timeline stamp: event `ev` of this CTA's `ti`-th tile (one lane of one warp per event id)
+#define TL(ti, ev) do { if (a.tl && (ti) < 16) a.tl[((size_t)blockIdx.x * 16 + (ti)) * 16 + (ev)] = clock64(); } while (0)
 #else
 #define DBG(bit) 0
+#define TL(ti, ev) do { } while (0)
 #endif
 
 // Epilogue warps per mode (ids 0..kEpi-1; kEpi/4 warps share one TMEM lane quarter and interleave
@@ -240,7 +257,12 @@ struct TcArgs {
 // epilogue change nothing at W=256 (31.2 vs 31.3 us) -- that kernel is bound by writing z and h
 // (84 MB per layer at ~2.7 TB/s), not by epilogue latency -- and cost a ring stage at W=1024, so
 // every mode runs two warps per quarter.
+#ifdef BNF_EPI12
+// three warps per quarter for the two latency-bound fused epilogues (mode 5 = TC_DGRAD_ACT, 7 = TC_FWD_HEAD)
+__host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return (mode == 5 || mode == 7) ? 12 : 8; }
+#else
 __host__ __device__ constexpr int epi_warps_of(int /*mode*/, int /*a_mode*/) { return 8; }
+#endif
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 
 constexpr int kXTileBytes = 128 * kMaxD * 4;
@@ -259,14 +281,18 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
   // SM at Fp = 64: two ring stages, no TMA-store staging tiles (~100 KB, 128 TMEM columns each).
   static constexpr int kGBytes = MODE == TC_DGRAD_ENC ? 128 * (BLOCK_N + 1) * 4 + 2 * 128 * (kMaxD + 1) * 4 : 0;
-  // TC_FWD_HEAD: Dense_L kernel [2][256] + per-row partial dots [2][128] in shared memory
-  static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 2 * 128) * 4 : 0;
+  // TC_FWD_HEAD: Dense_L kernel [2][256] + per-row partial dots [<= 4][128] in shared memory
+  // + the tile's h = act(z) as bf16 in per-warp 64B-swizzled 32x32 tiles (pass 1 -> pass 2)
+  static constexpr int kHeadScratch = MODE == TC_FWD_HEAD
+      ? epi_warps_of(MODE, A_MODE) * ((BLOCK_N / 32 + epi_warps_of(MODE, A_MODE) / 4 - 1) / (epi_warps_of(MODE, A_MODE) / 4)) * 2048 : 0;
+  static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadScratch : 0;
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
   static constexpr int kStgWarp = MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096;
   static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
-      MODE == TC_FWD_HEAD ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : 4)) :
-      MODE == TC_DGRAD_ACT ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7))) :
+      MODE == TC_FWD_HEAD ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : 4)) :
+      MODE == TC_DGRAD_ACT ? (epi_warps_of(MODE, A_MODE) > 8 ? (CTA2 ? 4 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6)))
+                                                            : (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))) :
       (A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kEpi = epi_warps_of(MODE, A_MODE);
   static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
@@ -276,8 +302,8 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpi * kStgWarp;
   // CTA-wide partial sums of the epilogue's column / scalar gradients (flushed to HBM when the
-  // network changes): TC_DGRAD_ACT [kAccCols] bias columns + scalars, TC_FWD_HEAD 2 x 256 columns
-  static constexpr int kAccFloats = MODE == TC_DGRAD_ACT ? kAccCols + 32 : (MODE == TC_FWD_HEAD ? 512 + 32 : 0);
+  // network changes): TC_DGRAD_ACT [kAccCols] bias columns + scalars
+  static constexpr int kAccFloats = MODE == TC_DGRAD_ACT ? kAccCols + 32 : 0;
   static constexpr int kMinBlocks = (MODE == TC_DGRAD_ENC && BLOCK_N == 64) ? 2 : 1;
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarBytes + 2 * 256 * 4 /*bias*/ + kXBytes + kGBytes + kHeadBytes + kAccFloats * 4;
   static_assert(kSmem <= 232448, "dynamic shared memory exceeds the 227 KB per-CTA limit");
@@ -298,6 +324,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr int kParts = kEpi / 4;                   // warps per TMEM lane quarter = column interleave
   constexpr int kProd = kEpi, kMma = kEpi + 1;       // producer / MMA issuer: the highest warp ids
   constexpr int kBaseThreads = 64 + 32 * kEpi;
+  // TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1
+  constexpr int kAccStages = 2;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
@@ -316,7 +344,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* gtile = sbias + 2 * 256;                    // TC_DGRAD_ENC: [128][BLOCK_N+1] f32 dfeat tile
   float* eacc = sbias;                               // TC_DGRAD_ENC: [2*kMaxD+3] partial sums
   float* kos_s = sbias + 2 * 256;                    // TC_FWD_HEAD: [2][256] Dense_L kernel of the tile's network
-  float* rowdot = kos_s + 2 * 256;                   // TC_FWD_HEAD: [2][128] partial h.Ko of the two column halves
+  uint8_t* hscr = (uint8_t*)(kos_s + 2 * 256 + 4 * 128);   // TC_FWD_HEAD: [kEpi][chunks][2 KB] bf16 h tiles
+  float* rowdot = kos_s + 2 * 256;                   // TC_FWD_HEAD: [kParts][128] partial h.Ko of the quarter's warps
   float* sxt = gtile + 128 * (BLOCK_N + 1);          // TC_DGRAD_ENC: [2][128][kMaxD+1] scaled inputs + raw time
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -358,6 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                          // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) TL(0, 15);
 
   // work items: (net, m unit, split, n tile); a unit is one 128-row tile, or a PAIR of them for
   // a CTA pair (this CTA takes rows of tile 2*unit + cta_rank)
@@ -365,11 +395,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tiles_per_net = m_units * a.n_tiles * a.k_splits;
   const int total_tiles = a.n_net * tiles_per_net;
   const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
-  // tile -> CTA mapping: round-robin, except TC_DGRAD_ENC where a CTA takes a CONTIGUOUS range of
-  // tiles (mostly one network: its partial sums stay in shared memory until the network changes)
+  // tile -> CTA mapping: round-robin, except the epilogues that keep per-network partial sums on
+  // chip (TC_DGRAD_ENC, TC_FWD_HEAD, single-n-tile TC_DGRAD_ACT): there a CTA takes a CONTIGUOUS
+  // range of tiles, i.e. mostly one network, and flushes its sums only when the network changes
   const int cta_id = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_ctas = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const bool contiguous = MODE == TC_DGRAD_ENC;
+  const bool contiguous = MODE == TC_DGRAD_ENC || MODE == TC_FWD_HEAD || (MODE == TC_DGRAD_ACT && a.n_tiles == 1);
   const int tile0 = contiguous ? (int)((long long)total_tiles * cta_id / n_ctas) : cta_id;
   const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
   const int tile_step = contiguous ? 1 : n_ctas;
@@ -388,6 +419,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (lane == 0 && kb == kb0) TL((t - tile0) / tile_step, 0);
+          if (lane == 0 && kb == kb1 - 1) TL((t - tile0) / tile_step, 1);
           if (elect_one()) {
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
@@ -465,10 +498,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (lane == 0) TL((t - tile0) / tile_step, 2);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (lane == 0 && kb == kb0) TL((t - tile0) / tile_step, 3);
+          if (lane == 0 && kb == kb1 - 1) TL((t - tile0) / tile_step, 4);
           if (elect_one()) {
             const uint64_t so = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
 #pragma unroll
@@ -486,7 +522,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (CTA2) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
         }
         __syncwarp();
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (lane == 0) TL((t - tile0) / tile_step, 5);
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < kEpi) {
@@ -500,6 +537,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t zc = 0;                 // TC_DGRAD_ACT: this warp's running chunk count (z ring slot / phase)
     int acc_net = -1;                // TC_DGRAD_ACT / TC_FWD_HEAD: network whose partial sums sit in colacc
+    int cbuf = 0;                    // TC_FWD_HEAD: which [2][256] constant buffer holds acc_net's bias / Dense_L kernel
+    float h_sl = 0.f, h_w = 0.f, h_sout = 0.f, h_bo = 0.f, h_fls = 0.f, h_flik = 0.f, h_fpi = 0.f, h_fos = 0.f;
+    float p_wact = 0.f, p_sprev = 0.f, p_fls = 0.f;   // TC_DGRAD_ACT: per-network constants
+    f32x2 gw2 = 0ull, gs2 = 0ull;    // TC_DGRAD_ACT: per-lane packed partial sums of the current network
+    // this warp's share of the two scalar gradients -> the CTA's shared-memory sums (before a flush)
+    auto dact_scalars = [&]() {
+      const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2)) * a.isf;     // sum dh*diff,  dh = acc*isf
+      const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2)) * a.isf;     // sum dz*z,     dz = dh*act'(z)
+      if (lane == 0) {
+        atomicAdd(&colacc[kAccCols], g_w * p_wact * (1.f - p_wact));
+        atomicAdd(&colacc[kAccCols + 1], g_s * p_fls);
+      }
+      gw2 = 0ull; gs2 = 0ull;
+    };
+    // TC_FWD_HEAD: per-lane partial sums of the current network, kept in registers across the CTA's
+    // tiles and reduced only when the network changes: column sums (lane L <-> column c+L of this
+    // warp's chunk i) of dU (bias gradient) and r*h (Dense_L kernel), and the scalar gradients
+    constexpr int kHeadChunks = MODE == TC_FWD_HEAD ? (BLOCK_N / 32 + kParts - 1) / kParts : 1;
+    float hcol_b[kHeadChunks], hcol_k[kHeadChunks], hsc[7];
+#pragma unroll
+    for (int i = 0; i < kHeadChunks; ++i) { hcol_b[i] = 0.f; hcol_k[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) hsc[i] = 0.f;
+    auto head_flush = [&](int fnet) {
+      float* g = a.gradp + (size_t)fnet * a.P;
+#pragma unroll
+      for (int i = 0; i < kHeadChunks; ++i) {
+        const int c = half * 32 + i * 32 * kParts;
+        if (c < BLOCK_N) {
+          atomicAdd(g + a.off_bias + c + lane, hcol_b[i]);
+          atomicAdd(g + dm.off_kernel[dm.L] + c + lane, hcol_k[i] * (h_sout * dm.inv_sqrt_W));
+        }
+        hcol_b[i] = 0.f; hcol_k[i] = 0.f;
+      }
+      const float s0 = warp_sum(hsc[0]), s1 = warp_sum(hsc[1]);
+      if (lane == 0) {
+        atomicAdd(g + dm.off_actw, s0 * h_w * (1.f - h_w));
+        atomicAdd(g + dm.off_layer_scale[a.layer], s1 * h_fls);
+      }
+      if (half == 0) {
+        const float s2 = warp_sum(hsc[2]), s3 = warp_sum(hsc[3]), s4 = warp_sum(hsc[4]);
+        const float s5 = warp_sum(hsc[5]), s6 = warp_sum(hsc[6]);
+        if (lane == 0) {
+          atomicAdd(a.ll + fnet, s2);
+          atomicAdd(g + (dm.likelihood == BNF_NORMAL ? 0 : 1), s3 * h_flik);
+          if (dm.likelihood == BNF_ZINB) atomicAdd(g + 2, s4 * h_fpi);
+          atomicAdd(g + dm.off_out_scale, s5 * h_fos);
+          atomicAdd(g + dm.off_bias[dm.L], s6 * h_sout);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 7; ++i) hsc[i] = 0.f;
+    };
     if (MODE == TC_DGRAD_ENC && epi_tid < 2 * kMaxD + 3) eacc[epi_tid] = 0.f;
     for (int t = tile0; t < tile_end; t += tile_step) {
       const int net = t / tiles_per_net;
@@ -513,87 +603,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ================= last hidden layer + head + log-likelihood + activation backward =================
         // One tile holds whole rows (n_tiles == 1), so everything downstream of the GEMM happens on
         // the accumulator while it sits in TMEM (models.py:263-273 forward, :157-191 likelihood,
-        // and the backward of both): pass 1 forms h = act(z) and the row's h.Ko partial dot;
-        // the two warps of a lane quarter exchange partials through shared memory; every lane
-        // evaluates log p(y|o) and r = dlogp/do of its row; pass 2 re-reads the accumulator and
-        // emits dU = s_l*r*(s_out/sqrt(W))*Ko*act'(z) (the only HBM output) plus the bias /
-        // Dense_L-kernel column sums and the scalar gradients.  z and h never leave the SM.
-        const float* pnet = a.params + (size_t)net * a.P;
-        const float s_l = dv[kDvSLayer + a.layer];
-        const float w = dv[kDvActW], s_out = dv[kDvSOut];
+        // and the backward of both).  Pass 1 does all the transcendental math once: h = act(z),
+        // the row's h.Ko partial dot, kd = Ko*act'(z) and the row-local parts of the scalar
+        // gradients; kd replaces the accumulator in TMEM (tcgen05.st) and h goes, as bf16, to this
+        // warp's swizzled shared-memory tiles.  The warps of a lane quarter exchange their partial dots through shared
+        // memory; every lane evaluates log p(y|o) and r = dlogp/do of its row.  Pass 2 re-reads
+        // kd and h and emits dU = (s_l*r*s_out/sqrt(W))*kd (the only HBM output) plus the bias /
+        // Dense_L-kernel column sums.  z and h never leave the SM.  Column and scalar sums
+        // collect in shared memory and are flushed when the CTA's network changes (tiles are
+        // assigned in contiguous ranges, so that is at most twice per CTA).
+        if (net != acc_net) {
+          if (acc_net >= 0) head_flush(acc_net);     // this warp's partial sums of the previous network
+          acc_net = net;
+          cbuf ^= 1;
+          const float* pnet = a.params + (size_t)net * a.P;
+          h_sl = dv[kDvSLayer + a.layer];
+          h_w = dv[kDvActW];
+          h_sout = dv[kDvSOut];
+          h_bo = pnet[dm.off_bias[dm.L]];
+          h_fls = sigmoid_f(pnet[dm.off_layer_scale[a.layer]]) / h_sl;
+          h_flik = dm.likelihood == BNF_NORMAL ? expf(pnet[0]) : sigmoid_f(pnet[1]);
+          h_fpi = dv[kDvPi] * (1.f - dv[kDvPi]);
+          h_fos = sigmoid_f(pnet[dm.off_out_scale]);
+          if (epi_tid < BLOCK_N) {
+            sbias[cbuf * 256 + epi_tid] = h_sl * pnet[a.off_bias + epi_tid];
+            kos_s[cbuf * 256 + epi_tid] = pnet[dm.off_kernel[dm.L] + epi_tid];
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");       // constants staged
+        }
+        const float* hsb = sbias + cbuf * 256;
+        const float* kos = kos_s + cbuf * 256;
+        const float s_l = h_sl, w = h_w, s_out = h_sout, bo = h_bo;
         const float cz = s_l * a.isf;
         const float hc = s_out * dm.inv_sqrt_W;
-        const float bo = pnet[dm.off_bias[dm.L]];
-        float* kos = kos_s + acc * 256;
-        if (net != acc_net) {
-          // the network changed: flush the CTA's column sums of the previous one (kept in shared
-          // memory so that no global atomic is in flight at the chunk loop's proxy fences)
-          if (acc_net >= 0) {
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
-            float* g = a.gradp + (size_t)acc_net * a.P;
-            if (epi_tid < BLOCK_N) {
-              atomicAdd(g + a.off_bias + epi_tid, colacc[epi_tid]);
-              atomicAdd(g + dm.off_kernel[dm.L] + epi_tid, colacc[256 + epi_tid]);
-              colacc[epi_tid] = 0.f;
-              colacc[256 + epi_tid] = 0.f;
-            }
-          }
-          acc_net = net;     // (the bar.sync below orders the zeroing before the tile's adds)
-        }
-        if (epi_tid < BLOCK_N) {
-          sb[epi_tid] = s_l * pnet[a.off_bias + epi_tid];
-          kos[epi_tid] = pnet[dm.off_kernel[dm.L] + epi_tid];
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
         const int row = m_t * 128 + q * 32 + lane;
         const bool row_ok = row < a.m_valid;
         float yv = 0.f;
         if (row_ok) yv = a.y[a.idx ? (size_t)a.idx[(size_t)net * a.idx_stride + row] : (size_t)row];
+        if (epi_tid == 0) TL((t - tile0) / tile_step, 6);
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-        // ---- pass 1: partial dot of this warp's column chunks (packed f32x2 math: FFMA2)
+        if (epi_tid == 0) TL((t - tile0) / tile_step, 7);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);   // kd replaces the accumulator
+        constexpr int kMaxChunks = (BLOCK_N / 32 + kParts - 1) / kParts;   // chunks per warp and tile
+        uint8_t* hw_scr = hscr + (size_t)warp * kMaxChunks * 2048;        // this warp's h tiles
+        // ---- pass 1 (packed f32x2 math: FFMA2)
         const ActConst2 ak(w);
         const f32x2 cz2 = f2_dup(cz);
-        f32x2 dot2 = 0ull;
+        f32x2 dot2 = 0ull, gw2 = 0ull, gs2 = 0ull;
 #pragma unroll 1
-        for (int c = half * 32; c < BLOCK_N; c += 64) {
-          uint32_t v[32];
+        for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
+          uint32_t v[32], hv[16];
           tmem_ld32(tacc + (uint32_t)c, v);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
-            const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
-            dot2 = f2_fma(act_fast2(f2_fma(f2_pack(v[j], v[j + 1]), cz2, f2_pack(b4.x, b4.y)), ak),
-                          f2_pack(k4.x, k4.y), dot2);
-            dot2 = f2_fma(act_fast2(f2_fma(f2_pack(v[j + 2], v[j + 3]), cz2, f2_pack(b4.z, b4.w)), ak),
-                          f2_pack(k4.z, k4.w), dot2);
-          }
-        }
-        const float dot = f2_lo(dot2) + f2_hi(dot2);
-        rowdot[half * 128 + q * 32 + lane] = dot;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");        // the two warps of this lane quarter
-        const float opre = (rowdot[q * 32 + lane] + rowdot[128 + q * 32 + lane]) * dm.inv_sqrt_W + bo;
-        // ---- likelihood of the row (both warps evaluate it; warp half 0 owns the sums)
-        float gl3[3] = {0.f, 0.f, 0.f};
-        float rr = 0.f, logp = 0.f;
-        if (row_ok) logp = head_row_loglik(dm.likelihood, dv, s_out * opre, yv, &rr, gl3);
-        if (!row_ok) rr = 0.f;
-        const float rk = rr * hc;                       // dh[col] = rk * Ko[col]
-        // ---- pass 2: dU, column sums, scalar sums.  Per column pair (FFMA2): kd = Ko*act'(z),
-        // dU = kd*(rk*s_l); sum Ko*diff and sum kd*z are scaled by the row's rk after the loop.
-        const f32x2 rr2 = f2_dup(rr);
-        const f32x2 rks2 = f2_dup(rk * s_l);
-        f32x2 gw2 = 0ull, gs2 = 0ull;
-#pragma unroll 1
-        for (int c = half * 32; c < BLOCK_N; c += 64) {
-          uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)c, v);
-          uint32_t pk[16];
-          float du[32], gk[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(hsb + c + j);
             const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
 #pragma unroll
             for (int jj = 0; jj < 4; jj += 2) {
@@ -603,14 +667,61 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               f32x2 d2, h2;
               const f32x2 da2 = act_grad_fast2(z2, ak, &d2, &h2);
               const f32x2 kd2 = f2_mul(k2, da2);
-              gw2 = f2_fma(k2, d2, gw2);
-              gs2 = f2_fma(kd2, z2, gs2);
-              const f32x2 gk2 = f2_mul(h2, rr2);            // r * h  (Dense_L kernel gradient addend)
-              const f32x2 du2 = f2_mul(kd2, rks2);
-              gk[j + jj] = f2_lo(gk2); gk[j + jj + 1] = f2_hi(gk2);
-              du[j + jj] = f2_lo(du2); du[j + jj + 1] = f2_hi(du2);
-              pk[(j + jj) >> 1] = f2_to_bf16x2(du2);
+              dot2 = f2_fma(h2, k2, dot2);
+              gw2 = f2_fma(k2, d2, gw2);              // sum Ko*diff   (x rk  = sum dh*diff)
+              gs2 = f2_fma(kd2, z2, gs2);             // sum kd*z      (x rk  = sum dz*z)
+              v[j + jj] = __float_as_uint(f2_lo(kd2)); v[j + jj + 1] = __float_as_uint(f2_hi(kd2));
+              hv[(j + jj) >> 1] = f2_to_bf16x2(h2);
             }
+          }
+          tmem_st32(tacc + (uint32_t)c, v);
+          uint8_t* ht = hw_scr + ((c - half * 32) / (32 * kParts)) * 2048 + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(ht + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(hv[4 * k], hv[4 * k + 1], hv[4 * k + 2], hv[4 * k + 3]);
+        }
+        tmem_st_wait();
+        const float dot = f2_lo(dot2) + f2_hi(dot2);
+        if (epi_tid == 0) TL((t - tile0) / tile_step, 8);
+        rowdot[half * 128 + q * 32 + lane] = dot;
+        asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");   // the warps of this lane quarter
+        float dsum = rowdot[q * 32 + lane];
+#pragma unroll
+        for (int pp = 1; pp < kParts; ++pp) dsum += rowdot[pp * 128 + q * 32 + lane];
+        const float opre = dsum * dm.inv_sqrt_W + bo;
+        // ---- likelihood of the row (every warp of the quarter evaluates it; part 0 owns the sums)
+        float gl3[3] = {0.f, 0.f, 0.f};
+        float rr = 0.f, logp = 0.f;
+        if (row_ok) logp = head_row_loglik(dm.likelihood, dv, s_out * opre, yv, &rr, gl3);
+        if (!row_ok) rr = 0.f;
+        const float rk = rr * hc;                       // dh[col] = rk * Ko[col]
+        if (epi_tid == 0) TL((t - tile0) / tile_step, 9);
+        // ---- pass 2: dU = kd*(rk*s_l), column sums of dU (bias gradient) and of r*h (Dense_L kernel)
+        const f32x2 rr2 = f2_dup(rr);
+        const f32x2 rks2 = f2_dup(rk * s_l);
+#pragma unroll
+        for (int ci = 0; ci < kHeadChunks; ++ci) {
+          const int c = half * 32 + ci * 32 * kParts;
+          if (c >= BLOCK_N) break;
+          uint32_t v[32], hv[16];
+          tmem_ld32(tacc + (uint32_t)c, v);
+          const uint8_t* ht = hw_scr + ci * 2048 + lane * 64;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 q4 = *reinterpret_cast<const uint4*>(ht + ((k ^ ((lane >> 1) & 3)) << 4));
+            hv[4 * k] = q4.x; hv[4 * k + 1] = q4.y; hv[4 * k + 2] = q4.z; hv[4 * k + 3] = q4.w;
+          }
+          uint32_t pk[16];
+          float du[32], gk[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const f32x2 du2 = f2_mul(f2_pack(v[j], v[j + 1]), rks2);
+            const uint32_t hb = hv[j >> 1];
+            const f32x2 gk2 = f2_mul(f2_pack(hb << 16, hb & 0xffff0000u), rr2);      // r * h
+            du[j] = f2_lo(du2); du[j + 1] = f2_hi(du2);
+            gk[j] = f2_lo(gk2); gk[j + 1] = f2_hi(gk2);
+            pk[j >> 1] = f2_to_bf16x2(du2);
           }
           uint8_t* stg = staging + warp * Cfg::kStgWarp;
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -625,41 +736,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, c, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L):
-          // bias gradient and Dense_L kernel gradient, added to the CTA's shared-memory partial sums
+          // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L)
           warp_transpose_sum(du, lane);
           warp_transpose_sum(gk, lane);
-          atomicAdd(&colacc[c + lane], du[0]);
-          atomicAdd(&colacc[256 + c + lane], gk[0] * hc);
+          hcol_b[ci] += du[0];
+          hcol_k[ci] += gk[0];
         }
-        float g_w = rk * (f2_lo(gw2) + f2_hi(gw2));      // sum dh*diff,  dh = rk*Ko
-        float g_s = rk * (f2_lo(gs2) + f2_hi(gs2));      // sum dz*z,     dz = dh*act'(z)
+        if (epi_tid == 0) TL((t - tile0) / tile_step, 10);
         tc_fence_before();
         if (CTA2) mbar_arrive_remote(&tempty[acc], 0);
         else mbar_arrive(&tempty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        // ---- scalar sums of the tile (one atomic per warp and quantity)
-        g_w = warp_sum(g_w);
-        g_s = warp_sum(g_s);
-        float* gp = a.gradp + (size_t)net * a.P;
-        if (lane == 0) {
-          atomicAdd(gp + dm.off_actw, g_w * w * (1.f - w));
-          atomicAdd(gp + dm.off_layer_scale[a.layer], (g_s / s_l) * sigmoid_f(pnet[dm.off_layer_scale[a.layer]]));
-        }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        // ---- this row's share of the scalar gradients (reduced over lanes at the flush)
+        hsc[0] += rk * (f2_lo(gw2) + f2_hi(gw2));       // sum dh*diff,  dh = rk*Ko
+        hsc[1] += rk * (f2_lo(gs2) + f2_hi(gs2));       // sum dz*z,     dz = dh*act'(z)
         if (half == 0) {
-          const float a_ll = warp_sum(logp), a_gs = warp_sum(rr * opre), a_gb = warp_sum(rr * s_out);
-          const float a_g0 = warp_sum(gl3[0]), a_g1 = warp_sum(gl3[1]), a_g2 = warp_sum(gl3[2]);
-          if (lane == 0) {
-            atomicAdd(a.ll + net, a_ll);
-            if (dm.likelihood == BNF_NORMAL) {
-              atomicAdd(gp + 0, a_g0 * expf(pnet[0]));
-            } else {
-              atomicAdd(gp + 1, a_g1 * sigmoid_f(pnet[1]));
-              if (dm.likelihood == BNF_ZINB) { const float pi = dv[kDvPi]; atomicAdd(gp + 2, a_g2 * pi * (1.f - pi)); }
-            }
-            atomicAdd(gp + dm.off_out_scale, a_gs * sigmoid_f(pnet[dm.off_out_scale]));
-            atomicAdd(gp + dm.off_bias[dm.L], a_gb);
-          }
+          hsc[2] += logp;
+          hsc[3] += dm.likelihood == BNF_NORMAL ? gl3[0] : gl3[1];
+          hsc[4] += gl3[2];
+          hsc[5] += rr * opre;
+          hsc[6] += rr;
         }
         continue;
       }
@@ -681,14 +777,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // traffic -- with per-lane z loads and per-chunk atomics in flight every chunk paid a full
       // DRAM round trip (measured: 15.1 -> 10.1 ms on the wind shard with both removed).
       float s_prev = 0.f;
-      f32x2 gw2 = 0ull, gs2 = 0ull, cdu2 = 0ull;   // packed partial sums (both halves 0.f)
-      constexpr int kChunks = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;   // chunks per warp and tile
+      f32x2 cdu2 = 0ull;
       uint8_t* zring = staging + warp * Cfg::kStgWarp + 2048;
       uint64_t* zb = zbar + warp * kZRing;
       if (MODE == TC_DGRAD_ACT) {
         if (net != acc_net) {
           // the network changed: flush the CTA's partial sums of the previous one
           if (acc_net >= 0) {
+            dact_scalars();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
             float* g = a.gradp + (size_t)acc_net * a.P;
             for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) {
@@ -702,16 +798,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // zeroed before new adds
           }
           acc_net = net;
+          p_wact = dv[kDvActW];
+          p_sprev = dv[kDvSLayer + a.layer_prev];
+          p_fls = sigmoid_f(a.params[(size_t)net * a.P + a.off_ls_prev]) / p_sprev;
         }
-        w_act = dv[kDvActW];
-        s_prev = dv[kDvSLayer + a.layer_prev];
+        w_act = p_wact;
+        s_prev = p_sprev;
         cdu2 = f2_dup(a.isf * s_prev);
         if (lane == 0 && !DBG(1)) {
 #pragma unroll
-          for (int i = 0; i < kZRing && i < kChunks; ++i) {
+          for (int i = 0; i < kZRing; ++i) {
+            if (half * 32 + 32 * kParts * i >= BLOCK_N) break;
             const uint32_t sl = (zc + i) % kZRing;
             mbar_arrive_expect_tx(&zb[sl], 2048);
-            tma_load_3d(zring + sl * 2048, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 64 * i, m_t * 128 + q * 32, net);
+            tma_load_3d(zring + sl * 2048, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 32 * kParts * i, m_t * 128 + q * 32, net);
           }
         }
       }
@@ -733,8 +833,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float* sx_cur = sxt + ((t - tile0) & 1) * 128 * (kMaxD + 1);
       float* sx_nxt = sxt + (((t - tile0) & 1) ^ 1) * 128 * (kMaxD + 1);
       if (MODE == TC_DGRAD_ENC && t == tile0) stage_x(t, sx_cur);
+      if (epi_tid == 0) TL((t - tile0) / tile_step, 6);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (epi_tid == 0) TL((t - tile0) / tile_step, 7);
 #pragma unroll 1
       for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
         uint32_t v[32];
@@ -818,9 +920,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0 && !DBG(4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
           // every lane holds its z values in registers: refill the slot with the tile kZRing ahead
-          if (lane == 0 && c + 64 * kZRing < BLOCK_N && !DBG(1)) {
+          if (lane == 0 && c + 32 * kParts * kZRing < BLOCK_N && !DBG(1)) {
             mbar_arrive_expect_tx(&zb[zsl], 2048);
-            tma_load_3d(zring + zsl * 2048, &map_o1, &zb[zsl], col0 + 64 * kZRing, m_t * 128 + q * 32, net);
+            tma_load_3d(zring + zsl * 2048, &map_o1, &zb[zsl], col0 + 32 * kParts * kZRing, m_t * 128 + q * 32, net);
           }
           ++zc;
 #pragma unroll
@@ -913,10 +1015,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      if (epi_tid == 0) TL((t - tile0) / tile_step, 10);
       tc_fence_before();
       if (CTA2) mbar_arrive_remote(&tempty[acc], 0);   // the leader's MMA warp owns both TMEMs' reuse
       else mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       if (MODE == TC_DGRAD_ENC) {
         // ---- feature-encode backward of this tile's 128 rows (same math
         // as encode_bwd_kernel<true>): a warp owns whole units, its lanes stride over the rows.
@@ -1012,25 +1115,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      if (MODE == TC_DGRAD_ACT) {
-        const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2)) * a.isf;     // sum dh*diff,  dh = acc*isf
-        const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2)) * a.isf;     // sum dz*z,     dz = dh*act'(z)
-        if (lane == 0) {
-          atomicAdd(&colacc[kAccCols], g_w * w_act * (1.f - w_act));
-          atomicAdd(&colacc[kAccCols + 1], (g_s / s_prev) * sigmoid_f(a.params[(size_t)net * a.P + a.off_ls_prev]));
-        }
-      }
     }
-    if (MODE == TC_FWD_HEAD && acc_net >= 0) {
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
-      float* g = a.gradp + (size_t)acc_net * a.P;
-      if (epi_tid < BLOCK_N) {
-        atomicAdd(g + a.off_bias + epi_tid, colacc[epi_tid]);
-        atomicAdd(g + dm.off_kernel[dm.L] + epi_tid, colacc[256 + epi_tid]);
-      }
-    }
+    if (MODE == TC_FWD_HEAD && acc_net >= 0) head_flush(acc_net);
     if (MODE == TC_DGRAD_ACT && acc_net >= 0) {
       // the CTA's last network: flush its partial sums
+      dact_scalars();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
       float* g = a.gradp + (size_t)acc_net * a.P;
       for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) atomicAdd(g + a.off_bias_prev + i, colacc[i]);
@@ -1225,7 +1314,34 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
 #ifdef BNF_TC_EXPERIMENT
   TcArgs ax = a;
   { const char* d = getenv("BNF_TC_DBG"); ax.dbg = d ? atoi(d) : 0; }
+  static long long* d_tl = nullptr;
+  const char* tle = getenv("BNF_TC_TL");            // = MODE number to trace (needs BNF_NO_GRAPH=1)
+  const bool trace = tle && atoi(tle) == MODE;
+  if (trace) {
+    if (!d_tl) cudaMalloc(&d_tl, 512 * 256 * sizeof(long long));
+    cudaMemsetAsync(d_tl, 0, 512 * 256 * sizeof(long long), st);
+    ax.tl = d_tl;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, ma, mb, om.o0, om.o1, ax, dmr);
+  if (trace) {
+    static int n_traced = 0;
+    cudaStreamSynchronize(st);
+    if (++n_traced == 5) {                          // one warm launch
+      static long long h[512 * 256];
+      cudaMemcpy(h, d_tl, sizeof(h), cudaMemcpyDeviceToHost);
+      for (int c : {0, 1, 2, 100, 147}) {
+        const long long t0 = h[(c * 16 + 0) * 16 + 15];
+        for (int ti = 0; ti < 6; ++ti) {
+          fprintf(stderr, "TL mode %d cta %3d tile %d:", MODE, c, ti);
+          for (int ev = 0; ev < 11; ++ev) {
+            const long long v = h[(c * 16 + ti) * 16 + ev];
+            fprintf(stderr, " %7lld", v ? v - t0 : -1);
+          }
+          fprintf(stderr, "\n");
+        }
+      }
+    }
+  }
 #else
   cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, ma, mb, om.o0, om.o1, a, dmr);
 #endif

@@ -1,0 +1,5 @@
+bash scripts/tmp/quick.sh 2>&1 | grep -v "^+\|^import\|^for line\|^    if\|^        d=\|^'"
+cp build_ab/libX.so bayesnf_b200/libbnf_sm100.so
+for m in 7 5; do
+BNF_NO_GRAPH=1 BNF_TC_TL=$m timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-profile 2>&1 | grep "^TL" | head -6
+done
