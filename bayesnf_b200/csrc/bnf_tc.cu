@@ -253,16 +253,12 @@ struct TcArgs {
 #endif
 
 // Epilogue warps per mode (ids 0..kEpi-1; kEpi/4 warps share one TMEM lane quarter and interleave
-// its 32-column chunks).  Measured (profiles/experiments/README.md, r1s): 16 warps for the forward
-// epilogue change nothing at W=256 (31.2 vs 31.3 us) -- that kernel is bound by writing z and h
-// (84 MB per layer at ~2.7 TB/s), not by epilogue latency -- and cost a ring stage at W=1024, so
-// every mode runs two warps per quarter.
-#ifdef BNF_EPI12
-// three warps per quarter for the two latency-bound fused epilogues (mode 5 = TC_DGRAD_ACT, 7 = TC_FWD_HEAD)
-__host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return (mode == 5 || mode == 7) ? 12 : 8; }
-#else
-__host__ __device__ constexpr int epi_warps_of(int /*mode*/, int /*a_mode*/) { return 8; }
-#endif
+// its 32-column chunks).  The epilogue warps run at ~0.2 IPC each (dependent MUFU/FMA chains, TMEM /
+// mbarrier / proxy-fence latencies), so warps per SM sub-partition are what hides latency; the
+// register file caps the count (12 warps <-> 146 registers/thread, 16 <-> 112 = spills).
+// Measured (profiles/experiments/README.md): TC_DGRAD_ACT with 12 warps: wind dgrad -8 %,
+// chickenpox -4 % (one ring stage less); TC_FWD / TC_FWD_HEAD: no change (HBM-write / MUFU bound).
+__host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return mode == 5 /*TC_DGRAD_ACT*/ ? 12 : 8; }
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 
 constexpr int kXTileBytes = 128 * kMaxD * 4;

@@ -118,9 +118,28 @@ class ClockSampler(threading.Thread):
             'reasons': sorted(self.reasons)}
 
 
-NCU_SUMMARY = {'chickenpox_map_e8': 'ncu_chickenpox_r1L_summary.csv', 'wind_map_e16': 'ncu_wind_tc_gemm_r1L_summary.csv'}
+NCU_SUMMARY = {'chickenpox_map_e8': 'ncu_chickenpox_r1u_summary.csv', 'wind_map_e16': 'ncu_wind_tc_gemm_r1u_summary.csv'}
 # kernel class -> template-argument substrings <BLOCK_N, A_MODE, MODE, CTA2> of its instantiations
-NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, ', ', 0, 0, '), 'tc_gemm_dgrad': (', 0, 5, ',), 'tc_gemm_wgrad': (', 1, 3, ',)}
+NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, ', ', 0, 0, '), 'tc_gemm_dgrad': (', 0, 5, ',), 'tc_gemm_wgrad': (', 1, 3, ',),
+               'tc_fwd_head': (', 3, 7, ',), 'tc_dgrad0_enc': (', 0, 6, ',)}
+
+
+def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head):
+  """Algorithmic FLOPs and HBM bytes PER STEP of every kernel class:
+  bf16 activations read/written once per producer/consumer, weights ignored (L2-resident)."""
+  a = 2 * rows * W            # bytes of one bf16 activation tensor [rows, W]
+  nf = L - 1 if fused_head else L          # launches of the plain forward kernel
+  return {
+      'tc_gemm_fwd': dict(flops=2.0 * rows * (F * W + (nf - 1) * W * W),
+                          bytes=2 * rows * Fp + nf * 2 * a + (nf - 1) * a),     # feat, (z,h) out, h in
+      'tc_fwd_head': dict(flops=2.0 * rows * (W * W + W), bytes=2 * a),          # h in, dU out
+      'tc_gemm_dgrad': dict(flops=2.0 * rows * (L - 1) * W * W, bytes=(L - 1) * 3 * a),   # dU in, z in, dU out
+      'tc_dgrad0_enc': dict(flops=2.0 * rows * F * W, bytes=a),
+      'tc_gemm_wgrad': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=2 * rows * Fp + a + (L - 1) * 2 * a),
+      'head_fused': dict(flops=2.0 * rows * W, bytes=3 * a),                     # h, z in, dU out
+      'map_update': dict(flops=0.0, bytes=32.0 * P_total),                       # p,g,m,v in; p,m,v out; bf16 restage
+      'encode': dict(flops=0.0, bytes=2.0 * rows * Fp),
+  }
 
 
 def ncu_traffic_gb(workload, kernel):
@@ -135,7 +154,7 @@ def ncu_traffic_gb(workload, kernel):
   ik, ir, iw = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
   scale = {'Gbyte': 1.0, 'Mbyte': 1e-3, 'Kbyte': 1e-6, 'byte': 1e-9}[units[ir]]
   vals = [(float(r[ir]) + float(r[iw])) * scale for r in rows[2:]
-          if any(pat in r[ik] for pat in NCU_PATTERN[kernel]) and r[ik].startswith('void tc_gemm_kernel<256')]
+          if any(pat in r[ik] for pat in NCU_PATTERN[kernel]) and 'tc_gemm_kernel<' in r[ik]]
   return max(vals) if vals else None      # the widest launch of that class (hidden layers)
 
 
@@ -376,30 +395,34 @@ def main():
     F, W, L = spec.num_features, wl['width'], wl['depth']
     Fp = spec.padded_features
     rows = E * S * B
-    gemm_flops = {   # algorithmic FLOPs per step of each GEMM class (true F, not padded)
-        'fwd': 2.0 * rows * (F * W + (L - 1) * W * W),
-        'dgrad': 2.0 * rows * (F * W + (L - 1) * W * W),
-        'wgrad': 2.0 * rows * (F * W + (L - 1) * W * W),
-    }
-    best = None
+    work = algorithmic_work(rows, F, Fp, W, L, E * S * spec.num_params, 'tc_fwd_head' in prof)
     for name, d in prof.items():
-      for key in gemm_flops:
-        if name.endswith(key) and 'gemm' in name:
-          tf = gemm_flops[key] / (d['ms_per_step'] * 1e-3) / 1e12
-          d['tflops'] = tf
-          if best is None or d['ms_per_step'] > prof[best]['ms_per_step']:
-            best = name
-    if best:
-      d = prof[best]
-      peak = pk['tflops_sustained'] if args.precision == 'bf16' else None
-      traffic = ncu_traffic_gb(args.workload, best) if args.precision == 'bf16' else None
-      avg_ms = d['ms_per_step'] / d['launches_per_step']
-      roof = {'bound': 'tensor', 'kernel': best, 'achieved': d['tflops'], 'peak': peak,
-              'unit': 'TFLOP/s', 'frac': (d['tflops'] / peak) if peak else None,
-              'traffic': traffic, 'traffic_unit': 'GB per launch (ncu dram read+write, hidden-layer launch)',
-              'hbm_frac_of_measured': (traffic / (avg_ms * 1e-3) / pk['hbm_gbs']) if traffic else None,
-              'peak_source': pk['source'] + ', sustained bf16', 'avg_launch_ms': avg_ms,
-              'note': 'small shapes (chickenpox) are latency-bound: both fractions are low'}
+      if name in work and work[name]['flops'] > 0:
+        d['tflops'] = work[name]['flops'] / (d['ms_per_step'] * 1e-3) / 1e12
+      if name in work:
+        d['algorithmic_gbs'] = work[name]['bytes'] / (d['ms_per_step'] * 1e-3) / 1e9
+    # the dominant kernel class of the step and the roofline that bounds it: tensor pipe when its
+    # algorithmic FLOPs at the measured bf16 peak take longer than its algorithmic bytes at the
+    # measured HBM bandwidth, else HBM
+    best = max((n for n in prof if n in work), key=lambda n: prof[n]['ms_per_step'], default=None)
+    if best and args.precision == 'bf16':
+      d, wk = prof[best], work[best]
+      n_l = d['launches_per_step']
+      avg_ms = d['ms_per_step'] / n_l
+      t_tensor = wk['flops'] / (pk['tflops_sustained'] * 1e12)
+      t_hbm = wk['bytes'] / (pk['hbm_gbs'] * 1e9)
+      traffic = ncu_traffic_gb(args.workload, best)
+      if t_tensor >= t_hbm:
+        ach, peak, unit, bound = d['tflops'], pk['tflops_sustained'], 'TFLOP/s', 'tensor'
+      else:
+        ach, peak, unit, bound = d['algorithmic_gbs'], pk['hbm_gbs'], 'GB/s', 'hbm'
+      roof = {'bound': bound, 'kernel': best, 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
+              'traffic': traffic, 'traffic_unit': 'GB per launch (ncu dram read+write of the widest launch, profiles/)',
+              'algorithmic_gb_per_launch': wk['bytes'] / n_l / 1e9,
+              'algorithmic_gflop_per_launch': wk['flops'] / n_l / 1e9,
+              'peak_source': pk['source'] + (', sustained bf16' if bound == 'tensor' else ', copy bandwidth'),
+              'avg_launch_ms': avg_ms,
+              'note': 'CUDA-event time per launch inside bench.py (profile pass); see DESIGN.md section 9'}
 
   # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
   cpu = None
