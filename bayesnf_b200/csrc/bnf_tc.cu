@@ -392,11 +392,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int total_tiles = a.n_net * tiles_per_net;
   const int kb_per_split = (a.k_blocks + a.k_splits - 1) / a.k_splits;
   // tile -> CTA mapping: round-robin, except the epilogues that keep per-network partial sums on
-  // chip (TC_DGRAD_ENC, TC_FWD_HEAD, single-n-tile TC_DGRAD_ACT): there a CTA takes a CONTIGUOUS
+  // chip or per-network constants staged (TC_DGRAD_ENC, TC_FWD_HEAD, single-n-tile TC_DGRAD_ACT /
+  // TC_FWD): there a CTA takes a CONTIGUOUS
   // range of tiles, i.e. mostly one network, and flushes its sums only when the network changes
   const int cta_id = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_ctas = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const bool contiguous = MODE == TC_DGRAD_ENC || MODE == TC_FWD_HEAD || (MODE == TC_DGRAD_ACT && a.n_tiles == 1);
+  const bool contiguous = MODE == TC_DGRAD_ENC || MODE == TC_FWD_HEAD ||
+                          ((MODE == TC_DGRAD_ACT || MODE == TC_FWD) && a.n_tiles == 1);
   const int tile0 = contiguous ? (int)((long long)total_tiles * cta_id / n_ctas) : cta_id;
   const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
   const int tile_step = contiguous ? 1 : n_ctas;
@@ -756,12 +758,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         continue;
       }
       if (MODE == TC_FWD) {
-        const float s_l = dv[kDvSLayer + a.layer];
-        c1 = s_l * a.isf;
-        w_act = dv[kDvActW];
-        if (epi_tid < BLOCK_N)
-          sb[epi_tid] = s_l * a.params[(size_t)net * a.P + a.off_bias + n_t * BLOCK_N + epi_tid];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
+        // per-(network, n-tile) constants: reloaded and restaged only when the key changes (with
+        // one n-tile the CTA's tiles are a contiguous range, i.e. mostly one network)
+        const int key = net * a.n_tiles + n_t;
+        if (key != acc_net) {
+          acc_net = key;
+          cbuf ^= 1;
+          const float s_l = dv[kDvSLayer + a.layer];
+          p_sprev = s_l * a.isf;
+          p_wact = dv[kDvActW];
+          if (epi_tid < BLOCK_N)
+            sbias[cbuf * 256 + epi_tid] = s_l * a.params[(size_t)net * a.P + a.off_bias + n_t * BLOCK_N + epi_tid];
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
+        }
+        c1 = p_sprev;
+        w_act = p_wact;
+        sb = sbias + cbuf * 256;
       }
       const int row = m_t * 128 + q * 32 + lane;
       const bool row_ok = row < a.m_valid;

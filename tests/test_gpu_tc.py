@@ -105,6 +105,30 @@ def test_bf16_tc_matches_bf16_simt(cuda, width, depth, n):
       assert float((a[2][j, lo:hi] - b[2][j, lo:hi]).abs().max()) <= 5e-2 * scale, (lo, hi)
 
 
+@pytest.mark.parametrize('width,depth,n,nets', [(256, 2, 10440, 8), (512, 3, 20000, 4), (128, 2, 30000, 5)])
+def test_bf16_tc_many_tiles_per_cta(cuda, width, depth, n, nets):
+  """BASELINE configs[1] at full size (8 members x 10 440 rows) and two larger shapes: every CTA
+  works through several tiles and several networks, so the epilogues' on-chip partial sums
+  (shared-memory column sums, per-lane register sums) are flushed on network changes, with both
+  tile->CTA mappings (contiguous at one n-tile, round-robin at W=512).  Same tolerances as
+  test_bf16_tc_matches_bf16_simt."""
+  from bayesnf_b200 import inference
+  cfg = _cfg(width, depth, n)
+  om, spec, P, xd, yd = _setup(cfg, n, nets)
+  out = {}
+  for prec in ('bf16', 'bf16_simt'):
+    eng = inference.Engine(spec, prec)
+    ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+    out[prec] = (ll.cpu(), grad.cpu())
+  a, b = out['bf16'], out['bf16_simt']
+  assert float(((a[0] - b[0]) / b[0]).abs().max()) <= 1e-2
+  parts = [(0, 3)] + [(o, o + (int(np.prod(s)) if s else 1)) for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+  for j in range(nets):
+    for lo, hi in parts:
+      scale = float(b[1][j, lo:hi].abs().max()) + 1e-3 * float(b[1][j].abs().max())
+      assert float((a[1][j, lo:hi] - b[1][j, lo:hi]).abs().max()) <= 5e-2 * scale, (j, lo, hi)
+
+
 @pytest.mark.parametrize('dist', ['NORMAL', 'ZINB'])
 def test_bf16_tc_vs_oracle(cuda, dist):
   """bf16 tensor-core path vs the f32 oracle: 3e-2 of scale (bf16 has 8 significand bits)."""
