@@ -407,6 +407,19 @@ def fit_vi(
   return surrogate, losses_np, spec.unflatten(samples.cpu().numpy()[None])
 
 
+def forward_bnf(features: ArrayT, observation_model: str, params: Sequence[np.ndarray],
+                model_args: dict[str, Any], precision: str | None = None) -> np.ndarray:
+  """`mlp.apply` of every member on `features` (the call inside models.make_likelihood_model,
+  models.py:157-160): returns the network outputs with shape `params[0].shape + (N,)`."""
+  spec = models.ModelSpec(**model_args, observation_model=observation_model)
+  eng = Engine(spec, precision)
+  x, _ = _to_device_data(features)
+  flat = spec.flatten(params)
+  nets = torch.as_tensor(flat.reshape(-1, spec.num_params)).to(eng.device).contiguous()
+  loc = eng.forward(nets, x)
+  return loc.reshape(tuple(flat.shape[:-1]) + (loc.shape[1],)).cpu().numpy()
+
+
 def predict_bnf(
     features: ArrayT,
     observation_model: str,

@@ -273,11 +273,22 @@ class BayesianNeuralFieldEstimator:
     raise NotImplementedError('Should be implemented by subclass')
 
   def likelihood_model(self, table: pd.DataFrame):
-    """Not provided: the reference returns a TFP distribution object
-    (spatiotemporal.py:433-468); out of scope for the hot path."""
-    raise NotImplementedError(
-        'likelihood_model() returns a tensorflow_probability object in the '
-        'reference and is outside the GPU hot path of bayesnf_b200.')
+    """Predictive distribution over new field values in `table` (spatiotemporal.py:433-468).
+
+    NOTE: Must be called after `fit`.  The reference returns
+    `tfd.Independent(Normal | NegativeBinomial | ZeroInflatedNegativeBinomial, 1)` with batch
+    shape `(num_devices, [num_samples,] members)` and event shape `(len(table),)`; this returns a
+    `distributions.PredictiveDistribution` with the same shapes and the methods `mean`, `stddev`,
+    `variance`, `log_prob`, `prob`, `sample` and `.distribution` (per-point `log_prob`, `cdf`,
+    `quantile`).  The network outputs come from the CUDA forward pass of this rank's members.
+    """
+    from . import distributions
+    test_data = self.data_handler.get_test(table)
+    predictions = inference.forward_bnf(
+        test_data, self.observation_model, self.params_, self._model_args(test_data.shape),
+        precision=self.precision)
+    return distributions.PredictiveDistribution(
+        self.observation_model, predictions, self.params_[0], self.params_[1], self.params_[2])
 
 
 class BayesianNeuralFieldMAP(BayesianNeuralFieldEstimator):

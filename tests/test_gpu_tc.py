@@ -264,6 +264,13 @@ def test_estimators_bf16_end_to_end(cuda):
   assert est.losses_[0, :, -1].mean() < est.losses_[0, :, 0].mean()
   means, q = est.predict(df.iloc[:200], quantiles=(0.1, 0.5, 0.9))
   assert means.shape == (1, 4, 200) and np.all(q[0] <= q[1]) and np.all(q[1] <= q[2])
+  # likelihood_model (spatiotemporal.py:433-468): batch (devices, members), event (rows,)
+  lm = est.likelihood_model(df.iloc[:200])
+  assert lm.batch_shape == (1, 4) and lm.event_shape == (200,)
+  np.testing.assert_allclose(lm.mean(), means, rtol=1e-6)
+  lp = lm.log_prob(df['y'].to_numpy()[:200])
+  assert lp.shape == (1, 4) and np.isfinite(lp).all()
+  np.testing.assert_allclose(lm.stddev()[..., 0], 0.01 + np.exp(est.params_[0]), rtol=1e-6)
   est = bayesnf_b200.BayesianNeuralFieldMLE(**kw).fit(df, seed=2, ensemble_size=2, num_epochs=40)
   assert est.losses_.shape == (1, 2, 40) and (est.losses_[0, :, -1] < est.losses_[0, :, 0]).all()
   est = bayesnf_b200.BayesianNeuralFieldVI(**kw).fit(df, seed=3, ensemble_size=2, num_epochs=2,
@@ -271,6 +278,8 @@ def test_estimators_bf16_end_to_end(cuda):
   assert est.losses_.shape == (1, 2, 2 * (len(df) // 480)) and np.isfinite(est.losses_).all()
   means, q = est.predict(df.iloc[:50])
   assert means.shape == (1, 3, 2, 50) and np.isfinite(q[0]).all()
+  lm = est.likelihood_model(df.iloc[:50])
+  assert lm.batch_shape == (1, 3, 2) and lm.sample(5, seed=0).shape == (5, 1, 3, 2, 50)
 
 
 @pytest.mark.parametrize('cta2', ['0', '1'])
