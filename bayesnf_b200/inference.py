@@ -246,8 +246,13 @@ def fit_map(
     precision: str | None = None,
     init_params: np.ndarray | None = None,
     batch_indices: np.ndarray | None = None,
+    batch_order: str = 'device',
 ) -> tuple[tuple[np.ndarray, ...], np.ndarray]:
   """Fit a BNF ensemble by MAP (prior_weight=1) or MLE (prior_weight=0).
+
+  ``batch_order='jax'`` replays the reference's minibatch row orders for this ``seed``
+  (threefry key tree of inference.py:571-618 restated in `jax_prng`; host-generated, so meant for
+  comparisons, not for throughput); the default draws them on the device.
 
   Reference: inference.py:376-458.  ``init_params`` ([members, P]) and
   ``batch_indices`` ([epochs, members, N] row orders) are test hooks that inject
@@ -273,8 +278,17 @@ def fit_map(
   target_scale = float(np.nanstd(np.asarray(target, dtype=np.float64)))
   lns_init = math.log(target_scale / 2.0)
 
+  if batch_order not in ('device', 'jax'):
+    raise ValueError(f'{batch_order=}')
   params_out, losses_out = [], []
   for i in range(num_splits):
+    if batch_order == 'jax' and batch_indices is None and batch_size < n_total:
+      from . import jax_prng
+      orders = jax_prng.map_batch_orders(jax_prng.prng_key(seed), n_dev, members, n_total, num_epochs,
+                                         split_index=i if num_splits > 1 else None)
+      jax_orders = orders[:, rank]                        # [epochs, members, N] of this rank
+    else:
+      jax_orders = None
     seed_i = fold_in(seed, i) if num_splits > 1 else seed
     init_seed, opt_seed = fold_in(seed_i, 0x1001), fold_in(seed_i, 0x1002)
     if init_params is not None:
@@ -299,6 +313,8 @@ def fit_map(
         if batch_indices is not None:
           perm = torch.as_tensor(np.asarray(batch_indices[ep], dtype=np.int32)).to(eng.device)
           perm = perm.reshape(-1, n_total)[i * members:(i + 1) * members].contiguous()
+        elif jax_orders is not None:
+          perm = torch.as_tensor(jax_orders[ep]).to(eng.device).contiguous()
         else:
           perm = _per_member_permutations(members, n_total, gen, eng.device)
         ls = eng.map_steps(p, m, v, step_count, x, y, perm, batch_size, n_total,

@@ -143,3 +143,46 @@ class ModelSpec:
                        f'got {len(params)}')
     lead = params[0].shape
     return np.concatenate([p.reshape(lead + (-1,)) for p in params], axis=-1)
+
+  # --- reference params tuple  <->  Flax variables dict --------------------------
+  def to_flax_variables(self, params: Sequence[np.ndarray]) -> tuple[tuple[np.ndarray, ...], dict]:
+    """Split a params tuple into what the reference's code paths consume: the three likelihood
+    scalars `(log_noise_scale, shape, inflated_loc_probs)` and the Flax variables dict
+    `{'params': {'Dense_0': {'bias', 'kernel'}, ..., 'feature_inv_sp_scale0': ..., ...}}` that
+    `tree_unflatten(tree_structure(mlp_template), params[3:])` builds (models.py:158-160).
+    Leading ensemble axes are kept on every leaf."""
+    if len(params) != 3 + len(self.leaf_names):
+      raise ValueError(f'expected {3 + len(self.leaf_names)} parameter leaves, got {len(params)}')
+    tree: dict = {}
+    for name, leaf in zip(self.leaf_names, params[3:]):
+      node = tree
+      *scopes, last = name.split('/')
+      for scope in scopes:
+        node = node.setdefault(scope, {})
+      node[last] = np.asarray(leaf)
+    return tuple(np.asarray(p) for p in params[:3]), {'params': tree}
+
+  def from_flax_variables(self, heads: Sequence[np.ndarray], variables: dict) -> tuple[np.ndarray, ...]:
+    """Inverse of :meth:`to_flax_variables`: leaves are taken in `jax.tree_util.tree_leaves` order
+    of the dict, i.e. keys sorted as strings at every level ('...scale10' before '...scale2'),
+    which is the order of the params tuple (models.py:99-103)."""
+    tree = variables.get('params', variables)
+
+    def leaves(node, prefix=''):
+      for key in sorted(node):
+        if isinstance(node[key], dict):
+          yield from leaves(node[key], prefix + key + '/')
+        else:
+          yield prefix + key, np.asarray(node[key])
+
+    named = list(leaves(tree))
+    if [n for n, _ in named] != self.leaf_names:
+      raise ValueError('Flax variables do not match this model: expected leaves '
+                       f'{self.leaf_names}, got {[n for n, _ in named]}')
+    for (name, leaf), shape in zip(named, self.leaf_shapes):
+      if tuple(leaf.shape[leaf.ndim - len(shape):]) != tuple(shape):
+        raise ValueError(f'leaf {name}: trailing shape {leaf.shape} does not end with {shape}')
+    if len(heads) != 3:
+      raise ValueError('heads must be (log_noise_scale, shape, inflated_loc_probs)')
+    return tuple(np.asarray(h) for h in heads) + tuple(leaf for _, leaf in named)
+

@@ -396,3 +396,23 @@ def test_nb_estimator_predict_api(cuda):
   means, q = est.predict(train, quantiles=(0.5, 0.9))
   assert means.shape == (1, 3, 100) and np.isfinite(means).all()
   assert q[0].shape == (100,) and np.all(q[0] <= q[1]) and np.all(q[0] == np.floor(q[0]))
+
+
+def test_fit_map_replays_reference_batch_orders(cuda):
+  """batch_order='jax': the minibatch row orders are those of the reference's threefry key tree
+  (jax_prng.map_batch_orders) -- identical to injecting them through the batch_indices hook."""
+  from bayesnf_b200 import inference, jax_prng
+  cfg = _cfgs()['small']
+  n = 96
+  x, y = _data(cfg, n)
+  om = O.OracleModel(**cfg)
+  P = _random_params(om, 3, y, seed=5).numpy()
+  seed = np.array([0, 9], dtype=np.uint32)
+  kw = dict(num_particles=3, learning_rate=0.01, num_epochs=3, batch_size=32, precision='fp32', init_params=P)
+  _, l_jax = inference.fit_map(x, y, seed, 'NORMAL', cfg, batch_order='jax', **kw)
+  orders = jax_prng.map_batch_orders(seed, 1, 3, n, 3)[:, 0]
+  _, l_inj = inference.fit_map(x, y, seed, 'NORMAL', cfg, batch_indices=orders, **kw)
+  np.testing.assert_array_equal(l_jax, l_inj)
+  _, l_dev = inference.fit_map(x, y, seed, 'NORMAL', cfg, **kw)
+  assert not np.array_equal(l_dev, l_jax)
+

@@ -152,3 +152,38 @@ def test_product_does_not_import_oracle():
       if f.endswith(('.py', '.cu', '.cuh', '.h')):
         src = open(os.path.join(root, f)).read()
         assert 'bnf_oracle' not in src and 'from oracle' not in src and 'import oracle' not in src, f
+
+
+def test_flax_variables_round_trip():
+  """params tuple <-> Flax variables dict: the dict's sorted-key leaf order
+  IS the tuple order, including the string sort that puts '...scale10' before '...scale2'."""
+  from bayesnf_b200 import models
+  spec = models.ModelSpec(width=64, depth=2, input_scales=[99., 1, 1], num_seasonal_harmonics=[2, 3],
+                          seasonality_periods=[7., 30.], init_x=(100, 3), fourier_degrees=[3, 2, 2],
+                          interactions=[[1, 2]])
+  rng = np.random.default_rng(0)
+  flat = rng.normal(size=(1, 4, spec.num_params)).astype(np.float32)
+  params = spec.unflatten(flat)
+  heads, variables = spec.to_flax_variables(params)
+  tree = variables['params']
+  assert set(tree['Dense_0']) == {'bias', 'kernel'} and tree['Dense_0']['kernel'].shape == (1, 4, 28, 64)
+  assert tree['Dense_2']['kernel'].shape == (1, 4, 64, 1) and tree['log_scale_adjustment'].shape == (1, 4, 3)
+  assert tree['feature_inv_sp_scale5'].shape == (1, 4) and len(heads) == 3
+  back = spec.from_flax_variables(heads, variables)
+  assert len(back) == len(params)
+  for a, b in zip(back, params):
+    np.testing.assert_array_equal(a, b)
+  np.testing.assert_array_equal(spec.flatten(back), flat)
+  with pytest.raises(ValueError):
+    spec.from_flax_variables(heads, {'params': {k: v for k, v in tree.items() if k != 'Dense_1'}})
+  # 12 hidden layers: 'Dense_10' sorts before 'Dense_2' (string order of tree_leaves)
+  deep = models.ModelSpec(width=64, depth=12, input_scales=[9.], num_seasonal_harmonics=[], seasonality_periods=[],
+                          init_x=(10, 1), fourier_degrees=[2], interactions=np.zeros((0, 2), int))
+  names = deep.leaf_names
+  assert names.index('Dense_10/bias') < names.index('Dense_2/bias')
+  assert names.index('inv_sp_layer_scale10') < names.index('inv_sp_layer_scale2')
+  p2 = deep.unflatten(rng.normal(size=(2, deep.num_params)).astype(np.float32))
+  h2, v2 = deep.to_flax_variables(p2)
+  for a, b in zip(deep.from_flax_variables(h2, v2), p2):
+    np.testing.assert_array_equal(a, b)
+
