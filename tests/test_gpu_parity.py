@@ -415,3 +415,36 @@ def test_fit_map_replays_reference_batch_orders(cuda):
   np.testing.assert_allclose(l_jax, l_inj, rtol=1e-5)     # same orders; f32 atomics reorder sums
   assert np.isfinite(l_jax).all() and l_jax.shape == (1, 3, 3)
 
+
+@pytest.mark.parametrize('prec,tol', [('fp32', 5e-5), ('bf16', 2e-2)])
+def test_full_size_additivity_and_permutation_invariance(cuda, prec, tol):
+  """Size-independent properties at BASELINE configs[1] (W256 L2, 8 members, N = 10 440), where
+  the oracle is too slow to be the checker: the log-likelihood and its gradient are SUMS over
+  rows (models.py:157-164, Independent(..., 1)), so (i) the values on two disjoint index halves
+  add up to the full-batch values and (ii) a permutation of the rows changes nothing.  fp32:
+  reduction-order noise only; bf16: the per-row values are identical, only f32 sums reorder, but
+  small gradient leaves are cancellation-prone, hence the tolerance relative to the leaf scale."""
+  from bayesnf_b200 import inference
+  cfg = dict(_cfgs()['chickenpox'])
+  n = 10440
+  cfg['init_x'] = (n, 3)
+  cfg['input_scales'] = [521.0, 1, 1]
+  x, y = _data(cfg, n)
+  om = O.OracleModel(**cfg)
+  P = _random_params(om, 8, y, seed=11).to(cuda)
+  eng, spec = _engine(cfg, 'NORMAL', prec)
+  xd, yd = inference._to_device_data(x, y)
+  ll, g = eng.loglik_grad(P, xd, yd)
+  rng = np.random.default_rng(1)
+  perm = rng.permutation(n).astype(np.int32)
+  full = torch.tensor(np.tile(perm, (8, 1)), device=cuda)
+  ll_p, g_p = eng.loglik_grad(P, xd, yd, idx=full)
+  half = n // 2
+  ll_a, g_a = eng.loglik_grad(P, xd, yd, idx=full[:, :half].contiguous())
+  ll_b, g_b = eng.loglik_grad(P, xd, yd, idx=full[:, half:].contiguous())
+  scale = g.abs().amax(dim=1, keepdim=True)
+  assert float(((ll_p - ll) / ll).abs().max()) <= tol
+  assert float(((ll_a + ll_b - ll) / ll).abs().max()) <= tol
+  assert float(((g_p - g).abs() / scale).max()) <= tol
+  assert float(((g_a + g_b - g).abs() / scale).max()) <= tol
+
