@@ -6,7 +6,7 @@ cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest.log
 tail -8 gpurun_out/pytest.log
-python scripts/tmp/diag1.py 2>&1 | tail -12
+python scripts/dev/diag1.py 2>&1 | tail -12
 timeout 300 python bench.py --steps 300 --warmup 20 > gpurun_out/bench_cp_default.json 2> gpurun_out/bench_cp_default.err
 BNF_PDL=0 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/bench_cp_nopdl.json 2> gpurun_out/bench_cp_nopdl.err
 BNF_LEGACY_STEP=1 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/bench_cp_legacy.json 2> gpurun_out/bench_cp_legacy.err
