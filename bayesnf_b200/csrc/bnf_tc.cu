@@ -258,7 +258,13 @@ struct TcArgs {
 // register file caps the count (12 warps <-> 146 registers/thread, 16 <-> 112 = spills).
 // Measured (profiles/experiments/README.md): TC_DGRAD_ACT with 12 warps: wind dgrad -8 %,
 // chickenpox -4 % (one ring stage less); TC_FWD / TC_FWD_HEAD: no change (HBM-write / MUFU bound).
+#ifdef BNF_FWD_EPI12   // experiment: three warps per quarter for the plain forward epilogue as well
+__host__ __device__ constexpr int epi_warps_of(int mode, int a_mode) {
+  return (mode == 5 /*TC_DGRAD_ACT*/ || (mode == 0 /*TC_FWD*/ && a_mode != 2)) ? 12 : 8;
+}
+#else
 __host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return mode == 5 /*TC_DGRAD_ACT*/ ? 12 : 8; }
+#endif
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 
 constexpr int kXTileBytes = 128 * kMaxD * 4;
@@ -289,7 +295,9 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
       MODE == TC_FWD_HEAD ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : 4)) :
       MODE == TC_DGRAD_ACT ? (epi_warps_of(MODE, A_MODE) > 8 ? (CTA2 ? 4 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6)))
                                                             : (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))) :
-      (A_MODE == 2 ? 2 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
+      A_MODE == 2 ? 2 :
+      (epi_warps_of(MODE, A_MODE) > 8 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))
+                                      : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kEpi = epi_warps_of(MODE, A_MODE);
   static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
