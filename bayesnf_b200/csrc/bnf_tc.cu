@@ -1,15 +1,17 @@
 // tcgen05 GEMMs of the dense stack (bf16 operands, f32 accumulation in TMEM).
 //
-// One persistent, warp-specialised kernel template serves the three GEMMs of a
-// hidden layer (models.py:263-268 forward and its jax.value_and_grad backward):
-//   fwd   : Z[b,n]  = sum_k A[b,k]  * Wt[n,k]      A,Wt K-major      (+ bias/scale/activation epilogue)
-//   dgrad : dH[b,k] = sum_n dU[b,n] * Wn[k,n]      dU,Wn K-major
-//   wgrad : dK[k,n] = sum_b A[b,k]  * dU[b,n]      both MN-major (no transposed copies in HBM)
-// Per CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
-// tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> global).
-// smem ring of kStages {A 128x64, B BLOCK_Nx64} bf16 tiles in the 128B-swizzle
-// canonical layout written by TMA; two TMEM accumulator stages so the epilogue
-// of tile i overlaps the MMAs of tile i+1.
+// One persistent, warp-specialised kernel template serves the GEMMs of a hidden layer
+// (models.py:263-268 forward and its jax.value_and_grad backward), one instantiation per
+// epilogue MODE:
+//   fwd   : Z[b,n]  = sum_k A[b,k]  * K[k,n]       A K-major, K MN-major   TC_FWD / TC_FWD_HEAD
+//   dgrad : dH[b,k] = sum_n dU[b,n] * K[k,n]       dU, K K-major           TC_DGRAD_ACT / TC_DGRAD_ENC
+//   wgrad : dK[k,n] = sum_b A[b,k]  * dU[b,n]      both MN-major           TC_WGRAD
+// Per CTA: warps 0..kEpi-1 = epilogue (tcgen05.ld -> registers -> fused math -> swizzled smem
+// staging -> TMA store), then the TMA producer warp and the TMEM allocator + tcgen05.mma issuer
+// warp (highest warp ids = highest issue priority).  smem ring of kStages {A 128x64, B BLOCK_Nx64}
+// bf16 tiles in the 128B-swizzle canonical layout written by TMA; two TMEM accumulator stages so
+// the epilogue of tile i overlaps the MMAs of tile i+1.  DESIGN.md section 3.1 lists what each
+// epilogue fuses and the measurements behind its structure.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -533,10 +535,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp < kEpi) {
-    // ===================== epilogue (warps 0..7) =====================
-    // warp%4 selects the TMEM lane quarter it may read; the two warps of a quarter
-    // take alternate 32-column chunks, so every SM sub-partition has two epilogue
-    // warps to hide tcgen05.ld / MUFU / store latency behind each other.
+    // ===================== epilogue (warps 0..kEpi-1) =====================
+    // warp%4 selects the TMEM lane quarter it may read; the kParts warps of a quarter take
+    // interleaved 32-column chunks, so every SM sub-partition has two or three epilogue warps to
+    // hide tcgen05.ld / MUFU / store latency behind each other.
     const int q = warp & 3;
     const int half = warp >> 2;        // which of the quarter's kParts warps: column chunks half, half+kParts, ...
     const int epi_tid = threadIdx.x;
