@@ -13,7 +13,9 @@ across ranks with NO data-path collective (weak scaling: 8 members per GPU).
 
 The line printed by rank 0 carries: metric/value (whole-job samples/s with
 inputs resident in HBM), e2e (same metric through the public Engine API with
-pinned-host inputs copied every step and the loss read back every step),
+pinned-host inputs copied every step and the loss read back every step -- `value`
+with the reads pipelined behind the steps like a fit() call, `per_step_sync_value`
+with the host blocking on every step's loss),
 roofline (dominant kernel, CUDA-event timed inside this script),
 cpu_baseline (the torch-CPU oracle on a bounded sample; "port": the reference's
 JAX path cannot be installed here), clocks, gpu_launches.
@@ -360,24 +362,45 @@ def main():
   xe, ye = torch.empty_like(xd), torch.empty_like(yd)
   k_e2e = max(5, min(args.steps, 100))
 
-  def e2e_step():
+  # Every step copies its inputs from pinned host memory and reads its loss back to the host.
+  # Two ways to consume the result: (a) pipelined -- the D2H read of step i is enqueued behind
+  # step i, the host goes on enqueueing step i+1 and synchronises once at the end (how a fit()
+  # call behaves: the reference's jitted scan returns the losses after the loop, inference.py:
+  # 608-614); (b) the host blocks on every step's loss before launching the next one.
+  loss_host = torch.empty((k_e2e, E), dtype=torch.float32).pin_memory()
+
+  def e2e_enqueue(i):
     xe.copy_(xh, non_blocking=True)
     ye.copy_(yh, non_blocking=True)
     ls = run(1, xe, ye)
-    return ls.cpu()
+    loss_host[i].copy_(ls.reshape(-1, E)[-1], non_blocking=True)
 
-  for _ in range(3):
-    e2e_step()
-  barrier()
-  t0 = time.perf_counter()
-  for _ in range(k_e2e):
-    e2e_step()
-  barrier()
-  e2e_s = time.perf_counter() - t0
-  t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-  e2e_val = world * E * S * B * k_e2e / float(t_e[0])
+  def timed(fn):
+    barrier()
+    t0 = time.perf_counter()
+    fn()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+  def pipelined():
+    for i in range(k_e2e):
+      e2e_enqueue(i)
+
+  def blocking():
+    for i in range(k_e2e):
+      e2e_enqueue(i)
+      torch.cuda.current_stream().synchronize()      # the loss of step i is on the host
+
+  for i in range(3):
+    e2e_enqueue(i)
+  e2e_pipe_s = timed(pipelined)
+  assert torch.isfinite(loss_host).all(), 'non-finite loss in the end-to-end region'
+  e2e_sync_s = timed(blocking)
+  e2e_val = world * E * S * B * k_e2e / e2e_pipe_s
+  e2e_sync_val = world * E * S * B * k_e2e / e2e_sync_s
 
   # ---- per-kernel CUDA-event timing (separate short run; not the headline) ----
   prof, roof = {}, None
@@ -454,7 +477,10 @@ def main():
         'samples_definition': 'members x MC draws x batch rows per second' if is_vi else 'members x batch rows per second',
         'e2e': {'value': e2e_val, 'unit': 'samples/s', 'steps': k_e2e,
                 'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4),
-                'd2h_bytes_per_step': int(E * 4)},
+                'd2h_bytes_per_step': int(E * 4),
+                'mode': 'inputs H2D from pinned memory and the loss D2H every step; reads pipelined '
+                        'behind the steps, one host synchronisation at the end',
+                'per_step_sync_value': e2e_sync_val},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
         'roofline': roof,
