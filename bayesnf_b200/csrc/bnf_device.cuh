@@ -195,6 +195,23 @@ __device__ __forceinline__ void warp_transpose_sum(float (&v)[32], int lane) {
   }
 }
 
+// 16-column variant: lane r holds 16 values of row r; after 4 halving steps and one pair add,
+// lanes 2c and 2c+1 both hold sum_r v_r[c] in v[0]  (column = lane >> 1).
+__device__ __forceinline__ void warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int hh = 8; hh >= 1; hh >>= 1) {
+    const int bit = hh << 1;                       // lane bit that picks the half kept
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < hh; ++i) {
+      const float send = up ? v[i] : v[i + hh];
+      const float keep = up ? v[i + hh] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 // sin/cos for the bf16 path with arguments up to ~1e5 rad (seasonal features): one exact
 // f32 range reduction to [-pi, pi] (two-constant Cody-Waite) and the MUFU approximations.
 // Absolute error ~1e-6 + |x|*6e-8 (the latter is the rounding of the f32 argument itself,

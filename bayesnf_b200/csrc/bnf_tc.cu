@@ -205,6 +205,23 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// 16-column variants (BNF_EPI16 epilogues: half the live registers per step)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 128B swizzle, version 1
@@ -260,17 +277,29 @@ struct TcArgs {
 // register file caps the count (12 warps <-> 146 registers/thread, 16 <-> 112 = spills).
 // Measured (profiles/experiments/README.md): TC_DGRAD_ACT with 12 warps: wind dgrad -8 %,
 // chickenpox -4 % (one ring stage less); TC_FWD / TC_FWD_HEAD: no change (HBM-write / MUFU bound).
-#ifdef BNF_FWD_EPI12   // experiment: three warps per quarter for the plain forward epilogue as well
+#ifdef BNF_EPI16
+// EXPERIMENT (not validated on hardware yet): sixteen epilogue warps
+// (four per SM sub-partition) for the three activation epilogues.  To fit 576 threads in the
+// register file (<= 112 registers) every 32-column chunk is processed as two 16-column halves
+// (tcgen05.ld/st .x16, 16-value transposes); the staging tiles, TMA stores and the z ring keep
+// their 32x32 shape.
+constexpr bool kEpi16 = true;
+__host__ __device__ constexpr int epi_warps_of(int mode, int a_mode) {
+  return ((mode == 5 /*TC_DGRAD_ACT*/ || mode == 7 /*TC_FWD_HEAD*/ || mode == 0 /*TC_FWD*/) && a_mode != 2) ? 16 : 8;
+}
+#elif defined(BNF_FWD_EPI12)   // experiment: three warps per quarter for the plain forward epilogue as well
+constexpr bool kEpi16 = false;
 __host__ __device__ constexpr int epi_warps_of(int mode, int a_mode) {
   return (mode == 5 /*TC_DGRAD_ACT*/ || (mode == 0 /*TC_FWD*/ && a_mode != 2)) ? 12 : 8;
 }
 #else
+constexpr bool kEpi16 = false;
 __host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return mode == 5 /*TC_DGRAD_ACT*/ ? 12 : 8; }
 #endif
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 
 constexpr int kXTileBytes = 128 * kMaxD * 4;
-constexpr int kBarBytes = 512;                     // mbarriers + TMEM base slot
+constexpr int kBarBytes = kEpi16 ? 1024 : 512;     // mbarriers + TMEM base slot
 constexpr int kZRing = 2;                          // TC_DGRAD_ACT: per-warp ring of 32x32 z tiles
 constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer whose bias sums stay in smem
 // A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
@@ -293,13 +322,17 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
   static constexpr int kStgWarp = MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096;
+  static constexpr int kEpiW = epi_warps_of(MODE, A_MODE);
   static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
-      MODE == TC_FWD_HEAD ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : 4)) :
-      MODE == TC_DGRAD_ACT ? (epi_warps_of(MODE, A_MODE) > 8 ? (CTA2 ? 4 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6)))
-                                                            : (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))) :
+      MODE == TC_FWD_HEAD ? (kEpiW > 12 ? (CTA2 ? 2 : (BLOCK_N == 256 ? 1 : (BLOCK_N == 128 ? 3 : 4)))
+                                        : (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : 4))) :
+      MODE == TC_DGRAD_ACT ? (kEpiW > 12 ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 5))) :
+                              kEpiW > 8 ? (CTA2 ? 4 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6)))
+                                        : (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))) :
       A_MODE == 2 ? 2 :
-      (epi_warps_of(MODE, A_MODE) > 8 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))
-                                      : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
+      (kEpiW > 12 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 6))) :
+       kEpiW > 8 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))
+                 : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kEpi = epi_warps_of(MODE, A_MODE);
   static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
   static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
@@ -563,19 +596,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // tiles and reduced only when the network changes: column sums (lane L <-> column c+L of this
     // warp's chunk i) of dU (bias gradient) and r*h (Dense_L kernel), and the scalar gradients
     constexpr int kHeadChunks = MODE == TC_FWD_HEAD ? (BLOCK_N / 32 + kParts - 1) / kParts : 1;
-    float hcol_b[kHeadChunks], hcol_k[kHeadChunks], hsc[7];
+    // (kEpi16: one slot per 16-column half; lanes 2c and 2c+1 both hold column c of the half)
+    constexpr int kHeadSlots = (kEpi16 && MODE == TC_FWD_HEAD) ? 2 * kHeadChunks : kHeadChunks;
+    float hcol_b[kHeadSlots], hcol_k[kHeadSlots], hsc[7];
 #pragma unroll
-    for (int i = 0; i < kHeadChunks; ++i) { hcol_b[i] = 0.f; hcol_k[i] = 0.f; }
+    for (int i = 0; i < kHeadSlots; ++i) { hcol_b[i] = 0.f; hcol_k[i] = 0.f; }
 #pragma unroll
     for (int i = 0; i < 7; ++i) hsc[i] = 0.f;
     auto head_flush = [&](int fnet) {
       float* g = a.gradp + (size_t)fnet * a.P;
 #pragma unroll
-      for (int i = 0; i < kHeadChunks; ++i) {
-        const int c = half * 32 + i * 32 * kParts;
-        if (c < BLOCK_N) {
-          atomicAdd(g + a.off_bias + c + lane, hcol_b[i]);
-          atomicAdd(g + dm.off_kernel[dm.L] + c + lane, hcol_k[i] * (h_sout * dm.inv_sqrt_W));
+      for (int i = 0; i < kHeadSlots; ++i) {
+        if constexpr (kEpi16 && MODE == TC_FWD_HEAD) {
+          const int c = half * 32 + (i >> 1) * 32 * kParts + 16 * (i & 1) + (lane >> 1);
+          if (half * 32 + (i >> 1) * 32 * kParts < BLOCK_N && (lane & 1) == 0) {
+            atomicAdd(g + a.off_bias + c, hcol_b[i]);
+            atomicAdd(g + dm.off_kernel[dm.L] + c, hcol_k[i] * (h_sout * dm.inv_sqrt_W));
+          }
+        } else {
+          const int c = half * 32 + i * 32 * kParts;
+          if (c < BLOCK_N) {
+            atomicAdd(g + a.off_bias + c + lane, hcol_b[i]);
+            atomicAdd(g + dm.off_kernel[dm.L] + c + lane, hcol_k[i] * (h_sout * dm.inv_sqrt_W));
+          }
         }
         hcol_b[i] = 0.f; hcol_k[i] = 0.f;
       }
@@ -661,6 +704,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         f32x2 dot2 = 0ull, gw2 = 0ull, gs2 = 0ull;
 #pragma unroll 1
         for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
+          if constexpr (kEpi16) {
+            uint8_t* ht = hw_scr + ((c - half * 32) / (32 * kParts)) * 2048 + lane * 64;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ch = c + 16 * hh;
+              uint32_t v[16], hv[8];
+              tmem_ld16(tacc + (uint32_t)ch, v);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(hsb + ch + j);
+                const float4 k4 = *reinterpret_cast<const float4*>(kos + ch + j);
+#pragma unroll
+                for (int jj = 0; jj < 4; jj += 2) {
+                  const f32x2 b2 = jj ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y);
+                  const f32x2 k2 = jj ? f2_pack(k4.z, k4.w) : f2_pack(k4.x, k4.y);
+                  const f32x2 z2 = f2_fma(f2_pack(v[j + jj], v[j + jj + 1]), cz2, b2);
+                  f32x2 d2, h2;
+                  const f32x2 da2 = act_grad_fast2(z2, ak, &d2, &h2);
+                  const f32x2 kd2 = f2_mul(k2, da2);
+                  dot2 = f2_fma(h2, k2, dot2);
+                  gw2 = f2_fma(k2, d2, gw2);
+                  gs2 = f2_fma(kd2, z2, gs2);
+                  v[j + jj] = __float_as_uint(f2_lo(kd2)); v[j + jj + 1] = __float_as_uint(f2_hi(kd2));
+                  hv[(j + jj) >> 1] = f2_to_bf16x2(h2);
+                }
+              }
+              tmem_st16(tacc + (uint32_t)ch, v);
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2)
+                *reinterpret_cast<uint4*>(ht + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(hv[4 * k2], hv[4 * k2 + 1], hv[4 * k2 + 2], hv[4 * k2 + 3]);
+            }
+            continue;
+          }
           uint32_t v[32], hv[16];
           tmem_ld32(tacc + (uint32_t)c, v);
 #pragma unroll
@@ -712,6 +789,47 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int ci = 0; ci < kHeadChunks; ++ci) {
           const int c = half * 32 + ci * 32 * kParts;
           if (c >= BLOCK_N) break;
+          if constexpr (kEpi16) {
+            const uint8_t* ht = hw_scr + ci * 2048 + lane * 64;
+            uint8_t* stg = staging + warp * Cfg::kStgWarp;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16], hv[8], pk[8];
+              float du[16], gk[16];
+              tmem_ld16(tacc + (uint32_t)(c + 16 * hh), v);
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const uint4 q4 = *reinterpret_cast<const uint4*>(ht + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4));
+                hv[4 * k2] = q4.x; hv[4 * k2 + 1] = q4.y; hv[4 * k2 + 2] = q4.z; hv[4 * k2 + 3] = q4.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const f32x2 du2 = f2_mul(f2_pack(v[j], v[j + 1]), rks2);
+                const uint32_t hb = hv[j >> 1];
+                const f32x2 gk2 = f2_mul(f2_pack(hb << 16, hb & 0xffff0000u), rr2);      // r * h
+                du[j] = f2_lo(du2); du[j + 1] = f2_hi(du2);
+                gk[j] = f2_lo(gk2); gk[j + 1] = f2_hi(gk2);
+                pk[j >> 1] = f2_to_bf16x2(du2);
+              }
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pk[4 * k2], pk[4 * k2 + 1], pk[4 * k2 + 2], pk[4 * k2 + 3]);
+              warp_transpose_sum16(du, lane);
+              warp_transpose_sum16(gk, lane);
+              hcol_b[2 * ci + hh] += du[0];
+              hcol_k[2 * ci + hh] += gk[0];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_o0, stg, c, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+          }
           uint32_t v[32], hv[16];
           tmem_ld32(tacc + (uint32_t)c, v);
           const uint8_t* ht = hw_scr + ci * 2048 + lane * 64;
@@ -857,6 +975,99 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (epi_tid == 0) TL((t - tile0) / tile_step, 7);
 #pragma unroll 1
       for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
+        if constexpr (kEpi16 && A_MODE != 2 && (MODE == TC_FWD || MODE == TC_DGRAD_ACT)) {
+          // ---- sixteen-warp variant: the 32x32 chunk as two 16-column halves (same staging tile,
+          // same TMA store / z ring; half the live registers)
+          const int col0 = n_t * BLOCK_N + c;
+          const uint32_t tchunk = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c);
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
+          const ActConst2 ak(w_act);
+          if constexpr (MODE == TC_FWD) {
+            const f32x2 c12 = f2_dup(c1);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16], zp[8], hp[8];
+              tmem_ld16(tchunk + (uint32_t)(16 * hh), v);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 16 * hh + j);
+#pragma unroll
+                for (int jj = 0; jj < 4; jj += 2) {
+                  const f32x2 z2 = f2_fma(f2_pack(v[j + jj], v[j + jj + 1]), c12, jj ? f2_pack(b4.z, b4.w) : f2_pack(b4.x, b4.y));
+                  zp[(j + jj) >> 1] = f2_to_bf16x2(z2);
+                  hp[(j + jj) >> 1] = f2_to_bf16x2(act_fast2(z2, ak));
+                }
+              }
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int off = lane * 64 + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4);
+                *reinterpret_cast<uint4*>(stg + off) = make_uint4(hp[4 * k2], hp[4 * k2 + 1], hp[4 * k2 + 2], hp[4 * k2 + 3]);
+                if (a.out0)
+                  *reinterpret_cast<uint4*>(stg + 2048 + off) = make_uint4(zp[4 * k2], zp[4 * k2 + 1], zp[4 * k2 + 2], zp[4 * k2 + 3]);
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_o1, stg, col0, m_t * 128 + q * 32, net);
+              if (a.out0) tma_store_3d(&map_o0, stg + 2048, col0, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else {
+            const uint32_t zsl = zc % kZRing;
+            mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
+            const uint8_t* zt = zring + zsl * 2048 + lane * 64;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t v[16], zw[8], pk[8];
+              float du[16];
+              tmem_ld16(tchunk + (uint32_t)(16 * hh), v);
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const uint4 q4 = *reinterpret_cast<const uint4*>(zt + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4));
+                zw[4 * k2] = q4.x; zw[4 * k2 + 1] = q4.y; zw[4 * k2 + 2] = q4.z; zw[4 * k2 + 3] = q4.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const uint32_t zb = zw[j >> 1];
+                const f32x2 z2 = f2_pack(zb << 16, zb & 0xffff0000u);
+                const f32x2 v2 = f2_pack(v[j], v[j + 1]);
+                f32x2 d2;
+                const f32x2 da2 = act_grad_fast2(z2, ak, &d2);
+                const f32x2 x2 = f2_mul(v2, da2);
+                gw2 = f2_fma(v2, d2, gw2);
+                gs2 = f2_fma(x2, z2, gs2);
+                const f32x2 du2 = f2_mul(x2, cdu2);
+                du[j] = f2_lo(du2);
+                du[j + 1] = f2_hi(du2);
+                pk[j >> 1] = f2_to_bf16x2(du2);
+              }
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2)
+                *reinterpret_cast<uint4*>(stg + lane * 64 + (((2 * hh + k2) ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pk[4 * k2], pk[4 * k2 + 1], pk[4 * k2 + 2], pk[4 * k2 + 3]);
+              warp_transpose_sum16(du, lane);
+              if ((lane & 1) == 0) atomicAdd(&colacc[col0 + 16 * hh + (lane >> 1)], du[0]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              // every lane has read its z values (syncwarp above): refill the slot kZRing ahead
+              if (c + 32 * kParts * kZRing < BLOCK_N) {
+                mbar_arrive_expect_tx(&zb[zsl], 2048);
+                tma_load_3d(zring + zsl * 2048, &map_o1, &zb[zsl], col0 + 32 * kParts * kZRing, m_t * 128 + q * 32, net);
+              }
+            }
+            ++zc;
+          }
+          continue;
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
