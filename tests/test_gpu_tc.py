@@ -80,7 +80,7 @@ def _setup(cfg, n, nets, dist='NORMAL'):
 
 
 @pytest.mark.parametrize('width,depth,n', [(256, 2, 100), (256, 2, 1000), (128, 3, 333), (512, 2, 300),
-                                           (64, 2, 200)])
+                                           (64, 2, 200), (1024, 3, 700)])
 def test_bf16_tc_matches_bf16_simt(cuda, width, depth, n):
   """Same bf16 storage, tensor cores vs SIMT f32 FMA: differences are only the
   accumulation order and the bf16 rounding of the staged weights and of dh -> 1e-2 of scale on values,
