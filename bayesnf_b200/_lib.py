@@ -40,8 +40,8 @@ class PlanInfo(C.Structure):
               ('num_feature_groups', C.c_int32), ('sm_count', C.c_int32)]
 
 
-# name -> (restype, argtypes); this table is also what tests/test_abi.py checks
-# against the declarations in include/bnf.h.
+# name -> (restype, argtypes); tests/test_host_logic.py::test_header_symbols_exported_and_bound
+# checks this table against the declarations in include/bnf.h.
 _P, _I32, _I64, _U64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 SIGNATURES = {
     'bnf_abi_version': (C.c_int, []),
@@ -66,6 +66,7 @@ SIGNATURES = {
     'bnf_nb_mixture_quantiles': (C.c_int, [_P, _P, _P, _I32, _I32, C.POINTER(C.c_double), _I32, _P, _P,
                                            _P, _SZ, _P]),
     'bnf_debug_gemm': (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+    'bnf_debug_philox': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     'bnf_debug_launch_count': (C.c_uint64, []),
     'bnf_debug_profile': (C.c_int, [_I32]),
     'bnf_debug_profile_report': (C.c_int, [C.c_char_p, _I32]),

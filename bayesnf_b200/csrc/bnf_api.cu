@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "bnf_device.cuh"
 #include "bnf_kernels.h"
 #include "bnf_prof.h"
 #include "bnf_tc.h"
@@ -441,9 +442,11 @@ extern "C" int bnf_loglik_grad(const bnf_plan_t* p, int32_t prec, const float* p
 }
 
 // Signature of a captured MAP step: every pointer / scalar baked into the graph's kernel nodes.
+// (The loss buffer is NOT baked: map_update_kernel reads its address from the workspace, where the
+// prologue of every call stores it -- callers may pass a fresh buffer per call and still replay.)
 struct MapGraphKey {
   const void* params; const void* am; const void* av; const void* step_count; const void* x;
-  const void* y; const void* out_loss; const void* ws;
+  const void* y; const void* ws;
   int prec, n_net, B, n_total; float lr, pw; int flags, pad;
   bool operator==(const MapGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
 };
@@ -475,6 +478,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   const float c_ll = (float)((double)n_total / (double)B);  // target.shape[0] / batch_size
   int32_t* slot = (int32_t*)(w.mm + 8);                      // loss-row cursor
   unsigned int* counter = (unsigned int*)(w.mm + 9);         // map_update's block ticket
+  float** loss_slot = (float**)(w.mm + 10);                  // device copy of `out_loss` (8-byte aligned)
   const bool tc = prec == BNF_PREC_BF16;
   // Paths that read the transposed weight copy (fused-encode experiment, BNF_FWD_WT=1) keep the
   // round-1 step (prep + cast every step): the fused update only maintains the natural copy.
@@ -499,7 +503,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
 
   // ---- prologue (once per call): zeroed accumulators, derived scalars, bf16 weight copies ----
   CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
-  launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st);
+  launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st, loss_slot, out_loss);
   if (tc) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
   CUK();
 
@@ -510,7 +514,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
     PdlScope pdl(true);
     int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, /*prepped=*/true);
     if (r) return r;
-    launch_map_update(m, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, w.ll, out_loss,
+    launch_map_update(m, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, w.ll, loss_slot,
                       slot, counter, w.derived, tc ? w.wn : nullptr, tc ? tc_weight_elems(m) : 0, n_net, s);
     return BNF_OK;
   };
@@ -521,7 +525,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   MapGraphKey key;
   memset(&key, 0, sizeof(key));
   key.params = params; key.am = am; key.av = av; key.step_count = step_count; key.x = x; key.y = y;
-  key.out_loss = out_loss; key.ws = ws; key.prec = prec; key.n_net = n_net; key.B = B; key.n_total = n_total;
+  key.ws = ws; key.prec = prec; key.n_net = n_net; key.B = B; key.n_total = n_total;
   key.lr = lr; key.pw = prior_weight; key.flags = (pdl_scope_would_enable() ? 1 : 0) | (need_wt() ? 2 : 0);
   if (use_graph) {
     MapGraphKey* cached = (MapGraphKey*)p->graph_key;
@@ -674,6 +678,13 @@ extern "C" int bnf_mixture_quantiles(const float* means, const float* scales, in
   launch_quantiles(means, scales, M, N, q, nq, approximate != 0, nd.data(), out, (float*)ws, (cudaStream_t)stream);
   CUK();
   return BNF_OK;
+}
+
+// host-side evaluation of the device RNG's block function (known-answer test without a GPU)
+extern "C" void bnf_debug_philox(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4) {
+  const uint4 r = bnf::philox4x32_10(make_uint4(counter4[0], counter4[1], counter4[2], counter4[3]),
+                                     make_uint2(key2[0], key2[1]));
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
 extern "C" int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c, int32_t n_net,

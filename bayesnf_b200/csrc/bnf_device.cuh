@@ -295,6 +295,35 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
   return __float2bfloat16_rn(v);
 }
 
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al., SC'11) --------------------------------
+// One call maps a 128-bit counter + 64-bit key to four independent 32-bit words; every consumer
+// below gives each output element its OWN counter block, so draws never share words.
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {   // (0, 1]
+  return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+// four standard normals from one Philox block (two Box-Muller pairs)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream, uint64_t block) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)block, (uint32_t)(block >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float r0 = sqrtf(-2.f * logf(u32_to_unit(r.x))), r1 = sqrtf(-2.f * logf(u32_to_unit(r.z)));
+  float s0, c0, s1, c1;
+  sincosf(6.283185307179586f * u32_to_unit(r.y), &s0, &c0);
+  sincosf(6.283185307179586f * u32_to_unit(r.w), &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -2,8 +2,6 @@
 // mode), head / likelihood, activation backward, encode backward, prior + Adam,
 // VI sampling / gradient assembly, mixture quantiles.  The bf16 tcgen05 GEMMs
 // live in bnf_tc.cu and share every non-GEMM kernel in this file.
-#include <curand_kernel.h>
-
 #include <atomic>
 #include <cfloat>
 #include <cstdio>
@@ -40,10 +38,11 @@ __device__ __forceinline__ void prep_one(const DevModel& m, const float* p, floa
 }
 
 // zero_acc (optional): [ll | prior] accumulators of n_net floats each at zero_acc / zero_acc2,
-// zero_cursors (optional): two int32 cursors -- the prologue of bnf_map_steps in one launch.
+// zero_cursors (optional): two int32 cursors; loss_slot (optional): where map_update_kernel finds
+// the loss buffer of the current call -- the prologue of bnf_map_steps in one launch.
 __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* params,
                             float* __restrict__ derived, int n_net, float* zero_acc, float* zero_acc2,
-                            int32_t* zero_cursors) {
+                            int32_t* zero_cursors, float** loss_slot, float* out_loss) {
   pdl_enter(params, derived, zero_acc, zero_acc2, zero_cursors);
   int net = blockIdx.x;
   if (net >= n_net) return;
@@ -51,6 +50,9 @@ __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* par
     if (zero_acc) zero_acc[net] = 0.f;
     if (zero_acc2) zero_acc2[net] = 0.f;
     if (net == 0 && zero_cursors) { zero_cursors[0] = 0; zero_cursors[1] = 0; }
+    // the loss buffer of THIS call: map_update_kernel reads the pointer from device memory, so a
+    // cached CUDA graph of the step does not bake the caller's output buffer into its nodes
+    if (net == 0 && loss_slot) *loss_slot = out_loss;
   }
   prep_one(m, params + (size_t)net * m.P, derived + (size_t)net * kDerivedStride, threadIdx.x);
 }
@@ -961,12 +963,12 @@ template <bool FAST>
 __global__ void __launch_bounds__(256)
 map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __restrict__ am,
                   float* __restrict__ av, float* __restrict__ grad, int32_t* step_count, float c_ll,
-                  float prior_weight, float lr, float* prior, float* ll, float* __restrict__ out_loss,
+                  float prior_weight, float lr, float* prior, float* ll, float* const* loss_slot,
                   int32_t* slot, unsigned int* counter, float* __restrict__ derived,
                   __nv_bfloat16* __restrict__ wn, size_t w_per_net, int n_net) {
   __shared__ float pred[8];
   __shared__ int s_last;
-  pdl_enter(params, am, av, grad, step_count, prior, ll, out_loss, slot, counter, derived, wn);
+  pdl_enter(params, am, av, grad, step_count, prior, ll, loss_slot, slot, counter, derived, wn);
   const int net = blockIdx.y, P = m.P;
   const int t = __ldcg(step_count) + 1;
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
@@ -1063,6 +1065,7 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
   if (!s_last) return;
   __threadfence();
   const int row = __ldcg(slot);
+  float* out_loss = reinterpret_cast<float*>(__ldcg(reinterpret_cast<const unsigned long long*>(loss_slot)));
   for (int j = threadIdx.x; j < n_net; j += blockDim.x) {
     const float l = __ldcg(ll + j), pr = __ldcg(prior + j);
     out_loss[(size_t)row * n_net + j] = prior_weight == 0.f ? -(l * c_ll) : -(l * c_ll + pr * prior_weight);
@@ -1082,25 +1085,31 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
 // =============================================================================
 // VI (inference.py:687-739)
 // =============================================================================
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t subseq, uint64_t offset) {
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, subseq, offset, &st);
-  return curand_normal(&st);
-}
-
-// z[s,e,p] = mu[e,p] + sigma[e,p]*eps[s,e,p] ; eps drawn here when eps_in == NULL
+// z[s,e,p] = mu[e,p] + sigma[e,p]*eps[s,e,p] ; eps drawn here when eps_in == NULL: a thread owns
+// four consecutive elements = the four normals of ONE Philox block (counter = element index / 4),
+// so no two elements share a random word (mean-field draws must be independent).
 __global__ void __launch_bounds__(256)
 vi_sample_kernel(int P, int E, int S, const float* __restrict__ mu, const float* __restrict__ rho,
                  const float* __restrict__ eps_in, float* __restrict__ eps_out, uint64_t seed,
                  uint64_t stream_id, float* __restrict__ z) {
-  const size_t total = (size_t)S * E * P;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const size_t ep = i % ((size_t)E * P);
-    float e = eps_in ? eps_in[i] : philox_normal(seed, stream_id, i);
-    if (eps_out) eps_out[i] = e;
-    const float sg = 1e-4f + softplus_f(rho[ep]);
-    z[i] = mu[ep] + sg * e;
+  const size_t total = (size_t)S * E * P, EP = (size_t)E * P;
+  const size_t groups = (total + 3) / 4;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    float e4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!eps_in) {
+      const float4 n4 = philox_normal4(seed, stream_id, g);
+      e4[0] = n4.x; e4[1] = n4.y; e4[2] = n4.z; e4[3] = n4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = 4 * g + k;
+      if (i >= total) break;
+      const size_t ep = i % EP;
+      const float e = eps_in ? eps_in[i] : e4[k];
+      if (eps_out) eps_out[i] = e;
+      const float sg = 1e-4f + softplus_f(rho[ep]);
+      z[i] = mu[ep] + sg * e;
+    }
   }
 }
 
@@ -1175,12 +1184,17 @@ init_params_kernel(const __grid_constant__ DevModel m, float lns_init, uint64_t 
     float v = 0.f;
     if (i == 0) v = lns_init;
     else if (is_kernel) {
-      curandStatePhilox4_32_10_t st;
-      curand_init(seed, (uint64_t)(first_member + net), (uint64_t)i * 16, &st);
-      // rejection sampling on the Philox stream of this (member, parameter)
-      v = curand_normal(&st);
-      for (int it = 0; it < 14 && fabsf(v) > 2.f; ++it) v = curand_normal(&st);
-      if (fabsf(v) > 2.f) v = 0.f;  // p ~ 0.0455^15: unreachable in practice
+      // rejection sampling on the Philox blocks of this (member, parameter): stream = global
+      // member id, block = (parameter, attempt group)
+      bool found = false;
+      for (int blk = 0; blk < 4 && !found; ++blk) {
+        const float4 n4 = philox_normal4(seed, (uint64_t)(first_member + net), ((uint64_t)i << 2) | (uint64_t)blk);
+        const float c[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!found && fabsf(c[k]) <= 2.f) { v = c[k]; found = true; }
+      }
+      // all 16 candidates outside [-2,2] has probability 0.0455^16: v stays 0
     }
     p[i] = v;
   }
@@ -1391,21 +1405,27 @@ nb_quantile_kernel(const float* __restrict__ loc, const float* __restrict__ shap
 // host-side launch wrappers
 // =============================================================================
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, float* zero_acc,
-                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st) {
+                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st, float** loss_slot, float* out_loss) {
   BNF_PROF("prep", st);
-  launch_k(prep_kernel, dim3(n_net), dim3(32), 0, st, m, params, derived, n_net, zero_acc, zero_acc2, zero_cursors);
+  launch_k(prep_kernel, dim3(n_net), dim3(32), 0, st, m, params, derived, n_net, zero_acc, zero_acc2, zero_cursors,
+           loss_slot, out_loss);
 }
 
 // rows per block such that n_net * ceil(B / R) blocks fill a whole number of waves of
 // (SM count * blocks_per_sm) resident blocks, with min_rows <= R <= max_rows
-static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int max_rows) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+static int sm_count_cached() {     // per device: a process may move between GPUs
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
+  return sms[dev];
+}
+static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int max_rows) {
+  const int sms = sm_count_cached();
   const long long slots = (long long)sms * blocks_per_sm;
   for (int w = 1; w <= 1024; ++w) {
     const int nb = (int)(slots * w / n_net);     // blocks per network in w waves
@@ -1486,11 +1506,15 @@ bool launch_head_fused(const DevModel& m, const float* params, const float* deri
   if (G > 256 || 256 % G != 0) return false;
   const size_t smem = (size_t)(kHeadFusedMaxRows + 3 * m.W) * sizeof(float);
   // rows per block: the smallest whole number of waves of resident blocks that keeps R <= max
-  static int occ_cache[2] = {0, 0}, w_cache[2] = {0, 0};
+  static int occ_cache[2] = {0, 0}, w_cache[2] = {0, 0}, dev_cache[2] = {-1, -1};
   int& occ = occ_cache[sizeof(T) == 4 ? 0 : 1];
   int& w_of = w_cache[sizeof(T) == 4 ? 0 : 1];
-  if (!occ || w_of != m.W) {
+  int& dev_of = dev_cache[sizeof(T) == 4 ? 0 : 1];
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  if (!occ || w_of != m.W || dev_of != dev_now) {   // the smem attribute is per device
     w_of = m.W;
+    dev_of = dev_now;
     if (smem > 48 * 1024) cudaFuncSetAttribute(head_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel<T>, 256, smem);
     if (occ < 1) occ = 1;
@@ -1578,16 +1602,10 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
 }
 void launch_map_update(const DevModel& m, float* params, float* am, float* av, float* grad,
                        int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
-                       float* ll, float* out_loss, int32_t* slot, unsigned int* counter, float* derived,
+                       float* ll, float* const* loss_slot, int32_t* slot, unsigned int* counter, float* derived,
                        __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st) {
   // about one wave of resident blocks in total: every block pays one fence + one ticket atomic
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = sm_count_cached();
   int bx = (sms * 8 + n_net - 1) / n_net;
   const int bmax = (m.P + 255) / 256;
   if (bx > bmax) bx = bmax;
@@ -1595,10 +1613,10 @@ void launch_map_update(const DevModel& m, float* params, float* am, float* av, f
   BNF_PROF("map_update", st);
   if (wn)
     launch_k(map_update_kernel<true>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
-             prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
+             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, n_net);
   else
     launch_k(map_update_kernel<false>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
-             prior_weight, lr, prior, ll, out_loss, slot, counter, derived, wn, w_per_net, n_net);
+             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, n_net);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st) {
@@ -1608,7 +1626,7 @@ void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll,
 
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,
                       float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st) {
-  size_t total = (size_t)S * E * P;
+  size_t total = ((size_t)S * E * P + 3) / 4;     // four elements per thread
   int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   BNF_PROF("vi_sample", st);
   vi_sample_kernel<<<blocks, 256, 0, st>>>(P, E, S, mu, rho, eps_in, eps_out, seed, stream_id, z);

@@ -10,7 +10,8 @@ namespace bnf {
 // derived scalars of every network; optionally also zeroes two n_net-float accumulators and
 // two int32 cursors (the MAP prologue)
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, float* zero_acc,
-                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st);
+                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st, float** loss_slot = nullptr,
+                 float* out_loss = nullptr);
 
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
@@ -49,7 +50,7 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
 // fused tail of a MAP step (adam + grad zero + bf16 restage + loss row + ticks + next derived)
 void launch_map_update(const DevModel& m, float* params, float* am, float* av, float* grad,
                        int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
-                       float* ll, float* out_loss, int32_t* slot, unsigned int* counter, float* derived,
+                       float* ll, float* const* loss_slot, int32_t* slot, unsigned int* counter, float* derived,
                        __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st);
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st);

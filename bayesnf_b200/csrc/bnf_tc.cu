@@ -56,31 +56,34 @@ cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict_
                     bf16* __restrict__ wt, bf16* __restrict__ wn, size_t per_net) {
   __shared__ float tile[32][33];
   pdl_enter(params, wt, wn);
-  const int net = blockIdx.z / m.L, layer = blockIdx.z % m.L;
-  const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
+  const int net = blockIdx.z;    // (the layers are looped over here: gridDim.z <= 65535 networks)
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
-  if (k0 >= Kp) return;
-  const float* src = params + (size_t)net * m.P + m.off_kernel[layer];
-  const size_t base = (size_t)net * per_net + (layer == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(layer - 1) * m.W * m.W);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int r = ty; r < 32; r += 8) {
-    int k = k0 + r, n = n0 + tx;
-    float v = (k < Kin && n < m.W) ? src[(size_t)k * m.W + n] : 0.f;
-    tile[r][tx] = v;
-    if (k < Kp && n < m.W) wn[base + (size_t)k * m.W + n] = __float2bfloat16_rn(v);
-  }
-  if (wt == nullptr) return;     // forward reads wn MN-major: no transposed copy
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    int n = n0 + r, k = k0 + tx;
-    if (n < m.W && k < Kp) wt[base + (size_t)n * Kp + k] = __float2bfloat16_rn(tile[tx][r]);
+  for (int layer = 0; layer < m.L; ++layer) {
+    const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
+    if (k0 >= Kp) continue;      // block-uniform
+    const float* src = params + (size_t)net * m.P + m.off_kernel[layer];
+    const size_t base = (size_t)net * per_net + (layer == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(layer - 1) * m.W * m.W);
+    for (int r = ty; r < 32; r += 8) {
+      int k = k0 + r, n = n0 + tx;
+      float v = (k < Kin && n < m.W) ? src[(size_t)k * m.W + n] : 0.f;
+      tile[r][tx] = v;
+      if (k < Kp && n < m.W) wn[base + (size_t)k * m.W + n] = __float2bfloat16_rn(v);
+    }
+    if (wt == nullptr) continue;   // forward reads wn MN-major: no transposed copy
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      int n = n0 + r, k = k0 + tx;
+      if (n < m.W && k < Kp) wt[base + (size_t)n * Kp + k] = __float2bfloat16_rn(tile[tx][r]);
+    }
+    __syncthreads();
   }
 }
 
 // wt may be NULL (only the natural-layout copy is needed)
 void tc_cast_weights(const DevModel& m, const float* params, bf16* wt, bf16* wn, int n_net, cudaStream_t st) {
   int kmax = m.Fp > m.W ? m.Fp : m.W;
-  dim3 grid((m.W + 31) / 32, (kmax + 31) / 32, n_net * m.L);
+  dim3 grid((m.W + 31) / 32, (kmax + 31) / 32, n_net);
   BNF_PROF("cast_weights", st);
   launch_k(cast_weights_kernel, grid, dim3(256), 0, st, m, params, wt, wn, tc_weight_elems(m));
 }
@@ -1508,11 +1511,14 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
                        const DevModel* dm) {
   using Cfg = TcCfg<BLOCK_N, MN, CTA2, MODE>;
   static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute is per DEVICE: a process that moves to another GPU must set it there too
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
       return tc_fail(BNF_ERR_CUDA, "cudaFuncSetAttribute(smem) failed");
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   const int m_units = CTA2 ? (a.m_tiles + 1) / 2 : a.m_tiles;
   long long total = (long long)a.n_net * m_units * a.n_tiles * a.k_splits;

@@ -212,6 +212,10 @@ int bnf_nb_mixture_quantiles(const float* loc, const float* shape_raw, const flo
  * A, B are bf16.  Used by tests/test_gpu_tc.py against a plain f32 matmul.      */
 int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c,
                    int32_t n_networks, int32_t m, int32_t n, int32_t k, void* stream);
+/* Philox4x32-10 block function of the device RNG (init / VI draws / minibatch permutations),
+ * evaluated on the HOST: counter4 -> out4 under key2.  Known-answer tested against the
+ * Random123 vectors without a GPU.                                              */
+void bnf_debug_philox(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4);
 /* Kernel launches issued by this library since load (all threads).             */
 uint64_t bnf_debug_launch_count(void);
 /* enable != 0: bracket every kernel launch with CUDA events on its stream (and
