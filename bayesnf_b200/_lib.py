@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'libbnf_sm100.so')
 
 BNF_ABI_VERSION = 1
 NORMAL, NB, ZINB = 0, 1, 2
-PREC_FP32, PREC_BF16, PREC_BF16_SIMT = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16_SIMT, PREC_BF16X3 = 0, 1, 2, 3
 WS_FORWARD, WS_GRAD, WS_MAP, WS_VI = 0, 1, 2, 3
 ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_UNSUPPORTED = 1, 2, 3, 4
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     'bnf_plan_info': (C.c_int, [_P, C.POINTER(PlanInfo)]),
     'bnf_plan_leaf': (C.c_int, [_P, _I32, C.c_char_p, _I32, C.POINTER(_I64),
                                 C.POINTER(_I32), C.POINTER(_I32)]),
+    'bnf_precision_supported': (C.c_int, [_P, _I32]),
     'bnf_workspace_bytes': (_SZ, [_P, _I32, _I32, _I32, _I32]),
     'bnf_forward': (C.c_int, [_P, _I32, _P, _I32, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     'bnf_loglik_grad': (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),

@@ -231,7 +231,10 @@ struct Ws {
 
 Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
   const DevModel& m = p->m;
-  const size_t ts = prec == BNF_PREC_FP32 ? 4 : 2;
+  const bool x3 = prec == BNF_PREC_BF16X3;
+  // bytes per element: f32 / bf16 / three bf16 planes (bf16x3 GEMM operands; its z stays f32)
+  const size_t ts = prec == BNF_PREC_FP32 ? 4 : (x3 ? 6 : 2);
+  const size_t tz = x3 ? 4 : ts;
   Carver c(base);
   Ws w;
   memset(&w, 0, sizeof(w));
@@ -241,7 +244,7 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
   const bool g = mode != BNF_WS_FORWARD;
   for (int l = 0; l < m.L; ++l) {
     if (g) {
-      w.z[l] = c.take(rows * m.W * ts);
+      w.z[l] = c.take(rows * m.W * tz);
       w.h[l] = c.take(rows * m.W * ts);
     } else {
       w.z[l] = nullptr;
@@ -256,7 +259,7 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
     w.r = (float*)c.take(rows * 4);
     w.dU[0] = c.take(rows * m.W * ts);
     w.dU[1] = m.L > 1 ? c.take(rows * m.W * ts) : w.dU[0];
-    w.dfeat = (float*)c.take(rows * m.Fp * 4);
+    w.dfeat = x3 ? nullptr : (float*)c.take(rows * m.Fp * 4);   // bf16x3: dfeat never leaves the SM
   }
   if (mode == BNF_WS_MAP || mode == BNF_WS_VI) w.grad = (float*)c.take((size_t)n_net * m.P * 4);
   if (mode == BNF_WS_VI) {
@@ -268,6 +271,8 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
     size_t per = tc_weight_elems(m);
     w.wt = (bf16*)c.take((size_t)n_net * per * 2);
     w.wn = (bf16*)c.take((size_t)n_net * per * 2);
+  } else if (x3) {
+    w.wn = (bf16*)c.take((size_t)n_net * tc_weight_elems(m) * 6);   // [layer][Kp][3*W]
   }
   w.bytes = c.off;
   return w;
@@ -275,13 +280,19 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
 
 int check_common(const bnf_plan* p, int prec, int n_net, int B) {
   if (!p) return fail(BNF_ERR_INVALID, "null plan");
-  if (prec < 0 || prec > 2) return fail(BNF_ERR_INVALID, "unknown precision %d", prec);
+  if (prec < 0 || prec > 3) return fail(BNF_ERR_INVALID, "unknown precision %d", prec);
   if (n_net < 1 || B < 1) return fail(BNF_ERR_INVALID, "n_networks and batch_rows must be positive");
   if (n_net > 65535) return fail(BNF_ERR_INVALID, "n_networks must be <= 65535");
   if ((double)n_net * B * std::max(p->m.W, p->m.Fp) > 9.0e18) return fail(BNF_ERR_INVALID, "problem too large");
-  if (prec == BNF_PREC_BF16) {
+  if (prec == BNF_PREC_BF16 || prec == BNF_PREC_BF16X3) {
     const char* why = tc_unsupported_reason(p->m);
-    if (why) return fail(BNF_ERR_UNSUPPORTED, "bf16 tcgen05 path: %s", why);
+    if (why) return fail(BNF_ERR_UNSUPPORTED, "tcgen05 path: %s", why);
+  }
+  if (prec == BNF_PREC_BF16X3) {
+    // the split-operand mode exists only with its fused epilogues
+    if (!head_fused_x3_supported(p->m)) return fail(BNF_ERR_UNSUPPORTED, "bf16x3 needs a width in {64, 128, 256, 512, 1024}");
+    if (p->m.W > 1024) return fail(BNF_ERR_UNSUPPORTED, "bf16x3 needs width <= 1024");
+    if (p->m.Fp > 128) return fail(BNF_ERR_UNSUPPORTED, "bf16x3 needs <= 128 encoded features");
   }
   return BNF_OK;
 }
@@ -302,6 +313,53 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
   // prepped: the derived scalars and the bf16 weight copies are already current (the fused MAP
   // update of the previous step wrote them)
   const DevModel& m = p->m;
+  if (prec == BNF_PREC_BF16X3) {
+    // ---- split-operand tensor-core mode (f32-parity): feat / h / dU are rows of three bf16 planes,
+    // z is f32; same kernel sequence as the bf16 mode without TC_FWD_HEAD
+    if constexpr (sizeof(T) == 2) {
+      const bool g = grad != nullptr;
+      if (!prepped) {
+        launch_prep(m, params, w.derived, n_net, nullptr, nullptr, nullptr, st);
+        tc_cast_weights_x3(m, params, w.wn, n_net, st);
+      }
+      launch_encode_x3(m, w.derived, x, idx, idx_stride, B, (bf16*)w.feat, n_net, st);
+      for (int l = 0; l < m.L; ++l) {
+        const bf16* a_in = l == 0 ? (const bf16*)w.feat : (const bf16*)w.h[l - 1];
+        int rc = tc_fwd_layer(p, l, params, w.derived, a_in, nullptr, w.wn, nullptr, (bf16*)w.h[l], n_net, B, st,
+                              true, g ? (float*)w.z[l] : nullptr);
+        if (rc) return fail(rc, "tc_fwd_layer (bf16x3) failed: %s", tc_last_error());
+      }
+      if (!(g && ll)) {
+        launch_head_x3(m, params, w.derived, (const bf16*)w.h[m.L - 1], y, idx, idx_stride, B, out_loc,
+                       ll ? w.opre : nullptr, ll ? w.r : nullptr, ll, nullptr, n_net, st);
+        CUK();
+        if (!g) return BNF_OK;
+        return fail(BNF_ERR_INVALID, "gradient without log-likelihood output");
+      }
+      int cur = 0;
+      if (!launch_head_fused_x3(m, params, w.derived, (const bf16*)w.h[m.L - 1], (const float*)w.z[m.L - 1], y, idx,
+                                idx_stride, B, (bf16*)w.dU[cur], ll, grad, n_net, st))
+        return fail(BNF_ERR_UNSUPPORTED, "bf16x3 head kernel does not support this width");
+      for (int l = m.L - 1; l >= 0; --l) {
+        const bf16* a_in = l == 0 ? (const bf16*)w.feat : (const bf16*)w.h[l - 1];
+        int rc = tc_wgrad(p, l, a_in, (const bf16*)w.dU[cur], grad, n_net, B, st, true);
+        if (rc) return fail(rc, "tc_wgrad (bf16x3) failed: %s", tc_last_error());
+        if (l > 0) {
+          rc = tc_dgrad_act_x3(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], (const float*)w.z[l - 1],
+                               params, w.derived, grad, n_net, B, st);
+          if (rc) return fail(rc, "tc_dgrad_act (bf16x3) failed: %s", tc_last_error());
+          cur ^= 1;
+        } else {
+          rc = tc_dgrad0_enc(p, w.wn, (const bf16*)w.dU[cur], x, idx, idx_stride, params, w.derived, grad, n_net, B, st, true);
+          if (rc) return fail(rc, "tc_dgrad0_enc (bf16x3) failed: %s", tc_last_error());
+        }
+      }
+      CUK();
+      return BNF_OK;
+    } else {
+      return fail(BNF_ERR_INVALID, "internal: bf16x3 runs on bf16 planes");
+    }
+  }
   const bool tc = prec == BNF_PREC_BF16;
   if (!prepped) launch_prep(m, params, w.derived, n_net, nullptr, nullptr, nullptr, st);
   // BNF_FUSED_ENCODE=1: encoder warps generate the A tile in shared memory (`feat` is written as a
@@ -404,6 +462,10 @@ int run_net_any(const bnf_plan* p, int prec, const float* params, int n_net, con
 }
 }  // namespace
 
+extern "C" int bnf_precision_supported(const bnf_plan_t* p, int32_t prec) {
+  return check_common(p, prec, 1, 1);
+}
+
 extern "C" size_t bnf_workspace_bytes(const bnf_plan_t* p, int32_t prec, int32_t n_net, int32_t B,
                                       int32_t mode) {
   if (!p || n_net < 1 || B < 1) return 0;
@@ -479,6 +541,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   int32_t* slot = (int32_t*)(w.mm + 8);                      // loss-row cursor
   unsigned int* counter = (unsigned int*)(w.mm + 9);         // map_update's block ticket
   float** loss_slot = (float**)(w.mm + 10);                  // device copy of `out_loss` (8-byte aligned)
+  const bool x3 = prec == BNF_PREC_BF16X3;
   const bool tc = prec == BNF_PREC_BF16;
   // Paths that read the transposed weight copy (fused-encode experiment, BNF_FWD_WT=1) keep the
   // round-1 step (prep + cast every step): the fused update only maintains the natural copy.
@@ -505,6 +568,7 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
   launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st, loss_slot, out_loss);
   if (tc) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
+  if (x3) tc_cast_weights_x3(m, params, w.wn, n_net, st);
   CUK();
 
   // One training step: encode -> fwd GEMMs -> head -> bwd GEMMs -> encode_bwd -> fused update.
@@ -515,7 +579,8 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
     int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, /*prepped=*/true);
     if (r) return r;
     launch_map_update(m, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, w.ll, loss_slot,
-                      slot, counter, w.derived, tc ? w.wn : nullptr, tc ? tc_weight_elems(m) : 0, n_net, s);
+                      slot, counter, w.derived, (tc || x3) ? w.wn : nullptr, (tc || x3) ? tc_weight_elems(m) : 0,
+                      x3 ? 3 : 1, n_net, s);
     return BNF_OK;
   };
 

@@ -101,6 +101,50 @@ __device__ __forceinline__ float act_grad_fast(float z, float w, float* diff) {
   const float dt = fmaf(-t, t, 1.f);
   return fmaf(w, delu - dt, dt);
 }
+// ---- bf16x3 (f32-parity tensor-core) mode ----------------------------------------------------
+// Activation with f32-class accuracy at MUFU cost: one ex2 and one rcp per element.
+//   ea = e^-|z| (ex2.approx: 2 ulp), q = ea^2, tanh|z| = 1 - 2q/(1+q) (rcp.approx: 1 ulp),
+//   elu = z > 0 ? z : ea - 1, elu' = z > 0 ? 1 : ea.
+// Absolute error <= ~3e-7 on h, act' and diff (|h| is O(1); the parity bar is 1e-5 of the output
+// scale), no overflow for any finite z (ea <= 1).
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// returns act'(z); *diff = elu(z) - tanh(z); *h = act(z)
+__device__ __forceinline__ float act_grad_x3(float z, float w, float* diff, float* h) {
+  const float ea = ex2_fast(-fabsf(z) * 1.4426950408889634f);
+  const float q = ea * ea;
+  const float t = copysignf(fmaf(-2.f * q, rcp_fast(1.f + q), 1.f), z);
+  const bool pos = z > 0.f;
+  const float elu = pos ? z : ea - 1.f;
+  const float delu = pos ? 1.f : ea;
+  const float d = elu - t;
+  *diff = d;
+  *h = fmaf(w, d, t);
+  const float dt = fmaf(-t, t, 1.f);
+  return fmaf(w, delu - dt, dt);
+}
+// Two f32 values -> their three bf16 planes, packed (lo = a, hi = b) per plane:
+// p0 = bf16(v), p1 = bf16(v - p0), p2 = bf16(v - p0 - p1); the subtractions are exact in f32.
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t* p0, uint32_t* p1, uint32_t* p2) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(a, b);
+  const uint32_t u0 = *reinterpret_cast<uint32_t*>(&t0);
+  const float ra = a - __uint_as_float(u0 << 16), rb = b - __uint_as_float(u0 & 0xffff0000u);
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(ra, rb);
+  const uint32_t u1 = *reinterpret_cast<uint32_t*>(&t1);
+  const float sa = ra - __uint_as_float(u1 << 16), sb = rb - __uint_as_float(u1 & 0xffff0000u);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(sa, sb);
+  *p0 = u0; *p1 = u1; *p2 = *reinterpret_cast<uint32_t*>(&t2);
+}
+__device__ __forceinline__ void split3_one(float a, __nv_bfloat16* p0, __nv_bfloat16* p1, __nv_bfloat16* p2) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(a);
+  const float r = a - __bfloat162float(h0);
+  const __nv_bfloat16 h1 = __float2bfloat16_rn(r);
+  *p0 = h0; *p1 = h1; *p2 = __float2bfloat16_rn(r - __bfloat162float(h1));
+}
+
 // ---- packed f32x2 arithmetic (sm_100: FFMA2 on a 64-bit register pair) ---------------------
 // The tcgen05 epilogues are bound by the fma pipe (a 3-register FFMA has a reciprocal throughput
 // of 2 cycles per SMSP) and by issue slots; FFMA2 does two lanes' worth of work per issue, so the

@@ -64,10 +64,13 @@ __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* par
 // =============================================================================
 constexpr int kEncRows = 32;
 
-template <typename T>
+// X3 (T = bf16): accurate trig, every feature stored as its three bf16 planes, row layout
+// [plane 0: Fp | plane 1: Fp | plane 2: Fp] (the split A operand of the bf16x3 Dense_0 GEMM).
+template <typename T, bool X3 = false>
 __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* __restrict__ derived,
                               const float* __restrict__ x, const int32_t* __restrict__ idx,
                               int64_t idx_stride, int B, T* __restrict__ feat) {
+  constexpr bool FAST = FastMath<T>::value && !X3;
   extern __shared__ float tile[];  // [kEncRows][Fp+1]
   pdl_enter(derived, x, idx, feat);
   const int net = blockIdx.y;
@@ -93,14 +96,14 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
       float sx = xr[i] / dv[kDvDenom + i];
       float c = two_pi * (float)(1 << d);
       float sn, cs;
-      if (FastMath<T>::value) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
+      if (FAST) sincos_reduced(c * sx, &sn, &cs); else sincosf(c * sx, &sn, &cs);
       const float den = (float)(d + 1), s = dv[kDvSFourier + i];
       trow[m.fourier_col[i] + d] = (cs / den) * s;
       trow[m.fourier_col[i] + deg + d] = (sn / den) * s;
     } else if (ui.kind == 2) {
       const int k = ui.a;
       float sn, cs;
-      if (FastMath<T>::value) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
+      if (FAST) sincos_reduced(m.seasonal_w[k] * xr[0], &sn, &cs); else sincosf(m.seasonal_w[k] * xr[0], &sn, &cs);
       const float s = dv[kDvSSeas], hk = m.seasonal_h[k];
       trow[m.col_seasonal + k] = (cs / hk) * s;
       trow[m.col_seasonal + m.n_seasonal + k] = (sn / hk) * s;
@@ -113,10 +116,19 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
   }
   __syncthreads();
   const int rows = min(kEncRows, B - row0);
-  T* out = feat + ((size_t)net * B + row0) * m.Fp;
-  for (int e = threadIdx.x; e < rows * m.Fp; e += blockDim.x) {
-    int r = e / m.Fp, c = e % m.Fp;
-    out[e] = from_f<T>(tile[r * ld + c]);
+  if constexpr (X3) {
+    __nv_bfloat16* out = feat + ((size_t)net * B + row0) * 3 * m.Fp;
+    for (int e = threadIdx.x; e < rows * m.Fp; e += blockDim.x) {
+      int r = e / m.Fp, c = e % m.Fp;
+      __nv_bfloat16* o = out + (size_t)r * 3 * m.Fp + c;
+      split3_one(tile[r * ld + c], o, o + m.Fp, o + 2 * m.Fp);
+    }
+  } else {
+    T* out = feat + ((size_t)net * B + row0) * m.Fp;
+    for (int e = threadIdx.x; e < rows * m.Fp; e += blockDim.x) {
+      int r = e / m.Fp, c = e % m.Fp;
+      out[e] = from_f<T>(tile[r * ld + c]);
+    }
   }
 }
 
@@ -418,7 +430,8 @@ void launch_wgrad_simt(const DevModel& m, int layer, const T* a_in, int Kin, int
 // one warp per row.  Accumulates loglik and the scalar-head gradients.
 // =============================================================================
 constexpr int kHeadRows = 256;
-template <typename T>
+// NP = 3 (T = bf16): h rows hold three bf16 planes [W | W | W] whose sum is the f32 value (bf16x3 mode)
+template <typename T, int NP = 1>
 __global__ void __launch_bounds__(256)
 head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
             const float* __restrict__ derived, const T* __restrict__ h, const float* __restrict__ y_all,
@@ -448,16 +461,26 @@ head_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params
       for (int u = 0; u < 4; ++u) {
         const int b = base + j0 + u;
         if (b < B) {
-          const T* hr = h + ((size_t)net * B + b) * m.W;
+          const T* hr = h + ((size_t)net * B + b) * NP * m.W;
           if (m.W % VEC == 0) {
             for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
-              alignas(16) T hv[VEC];
-              *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+              float hf[VEC];
 #pragma unroll
-              for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), Ko[n + k], dot[u]);
+              for (int pl = 0; pl < NP; ++pl) {
+                alignas(16) T hv[VEC];
+                *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + pl * m.W + n);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) hf[k] = pl == 0 ? to_f<T>(hv[k]) : hf[k] + to_f<T>(hv[k]);
+              }
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) dot[u] = fmaf(hf[k], Ko[n + k], dot[u]);
             }
           } else {
-            for (int n = lane; n < m.W; n += 32) dot[u] = fmaf(to_f<T>(hr[n]), Ko[n], dot[u]);
+            for (int n = lane; n < m.W; n += 32) {
+              float hf = to_f<T>(hr[n]);
+              for (int pl = 1; pl < NP; ++pl) hf += to_f<T>(hr[pl * m.W + n]);
+              dot[u] = fmaf(hf, Ko[n], dot[u]);
+            }
           }
         }
       }
@@ -712,21 +735,26 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
 // Same math as head_kernel + act_bwd_vec_kernel<.., true>.
 // =============================================================================
 constexpr int kHeadFusedMaxRows = 512;   // rows per block are chosen at launch so the grid is whole waves
-template <typename T>
+// X3 (T = bf16, bf16x3 mode): h and dU rows hold three bf16 planes [W | W | W], z is f32
+// (`z` then points to floats), accurate activation math.
+template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256)
 head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
-                  const float* __restrict__ derived, const T* __restrict__ h, const T* __restrict__ z,
+                  const float* __restrict__ derived, const T* __restrict__ h, const void* __restrict__ z_any,
                   const float* __restrict__ y_all, const int32_t* __restrict__ idx, int64_t idx_stride,
                   int B, int R /* rows per block */, T* __restrict__ dU, float* __restrict__ ll,
                   float* __restrict__ grad) {
   constexpr int VEC = 16 / sizeof(T);
-  constexpr bool FAST = FastMath<T>::value;
+  constexpr bool FAST = FastMath<T>::value && !X3;
+  constexpr int NP = X3 ? 3 : 1;
+  const T* z = static_cast<const T*>(z_any);
+  const float* zf = static_cast<const float*>(z_any);
   extern __shared__ float fsm[];
   float* rs = fsm;                              // [R] r = dlogp/do of this block's rows
   float* colsum = fsm + kHeadFusedMaxRows;      // [2W] bias / Dense_L kernel column sums
   float* kos = colsum + 2 * m.W;                // [W] Dense_L kernel
   __shared__ float hred[8][8];
-  pdl_enter(params, derived, h, z, y_all, idx, dU, ll, grad);
+  pdl_enter(params, derived, h, z, zf, y_all, idx, dU, ll, grad);
   const int net = blockIdx.y;
   const int b0 = blockIdx.x * R, b1 = min(B, b0 + R);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -748,15 +776,21 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
       for (int u = 0; u < 4; ++u) {
         const int b = base + j0 + u;
         if (b < b1) {
-          const T* hr = h + ((size_t)net * B + b) * m.W;
+          const T* hr = h + ((size_t)net * B + b) * NP * m.W;
           for (int n = lane * VEC; n < m.W; n += 32 * VEC) {
-            alignas(16) T hv[VEC];
+            float hf[VEC];
             alignas(16) float kk[VEC];
-            *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + n);
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+              alignas(16) T hv[VEC];
+              *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(hr + pl * m.W + n);
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) hf[k] = pl == 0 ? to_f<T>(hv[k]) : hf[k] + to_f<T>(hv[k]);
+            }
 #pragma unroll
             for (int k = 0; k < VEC; k += 4) *reinterpret_cast<float4*>(kk + k) = *reinterpret_cast<const float4*>(kos + n + k);
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) dot[u] = fmaf(to_f<T>(hv[k]), kk[k], dot[u]);
+            for (int k = 0; k < VEC; ++k) dot[u] = fmaf(hf[k], kk[k], dot[u]);
           }
         }
       }
@@ -830,17 +864,30 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
 #pragma unroll 4
     for (int b = b0 + threadIdx.x / G; b < b1; b += rstep) {
       const size_t o = ((size_t)net * B + b) * m.W + (size_t)cg * VEC;
-      alignas(16) T zv[VEC];
-      alignas(16) T hv[VEC];
-      alignas(16) T out[VEC];
-      *reinterpret_cast<uint4*>(zv) = *reinterpret_cast<const uint4*>(z + o);
-      *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(h + o);
+      const size_t o3 = ((size_t)net * B + b) * NP * m.W + (size_t)cg * VEC;    // X3: plane 0 of the row
+      float zr[VEC], hr[VEC], du_r[VEC];
+      if constexpr (X3) {
+#pragma unroll
+        for (int k = 0; k < VEC; k += 4) *reinterpret_cast<float4*>(zr + k) = *reinterpret_cast<const float4*>(zf + o + k);
+      } else {
+        alignas(16) T zv[VEC];
+        *reinterpret_cast<uint4*>(zv) = *reinterpret_cast<const uint4*>(z + o);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) zr[k] = to_f<T>(zv[k]);
+      }
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) {
+        alignas(16) T hv[VEC];
+        *reinterpret_cast<uint4*>(hv) = *reinterpret_cast<const uint4*>(h + o3 + pl * m.W);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) hr[k] = pl == 0 ? to_f<T>(hv[k]) : hr[k] + to_f<T>(hv[k]);
+      }
       const float rb = rs[b - b0];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float zz = to_f<T>(zv[k]);
+        const float zz = zr[k];
         const float dh = rb * head_c[k];
-        g_ko[k] += rb * to_f<T>(hv[k]);
+        g_ko[k] += rb * hr[k];
         float diff;
         const float da = act_grad_sel<FAST>(zz, w, &diff);
         const float dz = dh * da;
@@ -848,9 +895,21 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
         g_s += dz * zz;
         const float du = dz * s_l;
         g_b[k] += du;
-        out[k] = from_f<T>(du);
+        du_r[k] = du;
       }
-      *reinterpret_cast<uint4*>(dU + o) = *reinterpret_cast<const uint4*>(out);
+      if constexpr (X3) {
+        alignas(16) uint32_t pk[3][VEC / 2];
+#pragma unroll
+        for (int k = 0; k < VEC; k += 2) split3_pair(du_r[k], du_r[k + 1], &pk[0][k / 2], &pk[1][k / 2], &pk[2][k / 2]);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+          *reinterpret_cast<uint4*>(dU + o3 + pl * m.W) = *reinterpret_cast<const uint4*>(pk[pl]);
+      } else {
+        alignas(16) T out[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) out[k] = from_f<T>(du_r[k]);
+        *reinterpret_cast<uint4*>(dU + o) = *reinterpret_cast<const uint4*>(out);
+      }
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
@@ -965,7 +1024,7 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
                   float* __restrict__ av, float* __restrict__ grad, int32_t* step_count, float c_ll,
                   float prior_weight, float lr, float* prior, float* ll, float* const* loss_slot,
                   int32_t* slot, unsigned int* counter, float* __restrict__ derived,
-                  __nv_bfloat16* __restrict__ wn, size_t w_per_net, int n_net) {
+                  __nv_bfloat16* __restrict__ wn, size_t w_per_net, int wn_planes, int n_net) {
   __shared__ float pred[8];
   __shared__ int s_last;
   pdl_enter(params, am, av, grad, step_count, prior, ll, loss_slot, slot, counter, derived, wn);
@@ -1035,7 +1094,14 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
           const int cnt = (l == 0 ? m.F : m.W) * m.W;
           if (rel >= 0 && rel < cnt) {
             const size_t lo = l == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(l - 1) * m.W * m.W;
-            wn[(size_t)net * w_per_net + lo + rel] = __float2bfloat16_rn(th_new);
+            if (wn_planes == 3) {
+              // bf16x3 staging: [Kp][3*W], plane p of (k, n) at k*3W + p*W + n
+              const int k = rel / m.W, n = rel - k * m.W;
+              __nv_bfloat16* d = wn + 3 * ((size_t)net * w_per_net + lo) + (size_t)k * 3 * m.W + n;
+              split3_one(th_new, d, d + m.W, d + 2 * m.W);
+            } else {
+              wn[(size_t)net * w_per_net + lo + rel] = __float2bfloat16_rn(th_new);
+            }
             break;
           }
         }
@@ -1459,6 +1525,13 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
   BNF_PROF("encode", st);
   launch_k(encode_kernel<T>, grid, dim3(256), smem, st, m, derived, x, idx, idx_stride, B, feat);
 }
+void launch_encode_x3(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
+                      int64_t idx_stride, int B, __nv_bfloat16* feat3, int n_net, cudaStream_t st) {
+  dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
+  size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
+  BNF_PROF("encode", st);
+  launch_k(encode_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, st, m, derived, x, idx, idx_stride, B, feat3);
+}
 template void launch_encode<float>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, float*, int, cudaStream_t);
 template void launch_encode<__nv_bfloat16>(const DevModel&, const float*, const float*, const int32_t*, int64_t, int, __nv_bfloat16*, int, cudaStream_t);
 
@@ -1492,6 +1565,13 @@ void launch_head(const DevModel& m, const float* params, const float* derived, c
   BNF_PROF("head", st);
   launch_k(head_kernel<T>, grid, dim3(256), 0, st, m, params, derived, h, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
 }
+void launch_head_x3(const DevModel& m, const float* params, const float* derived, const __nv_bfloat16* h3,
+                    const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
+                    float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st) {
+  dim3 grid((B + kHeadRows - 1) / kHeadRows, n_net);
+  BNF_PROF("head", st);
+  launch_k(head_kernel<__nv_bfloat16, 3>, grid, dim3(256), 0, st, m, params, derived, h3, y, idx, idx_stride, B, out_loc, opre, r, ll, grad);
+}
 template void launch_head<float>(const DevModel&, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 template void launch_head<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 
@@ -1522,7 +1602,34 @@ bool launch_head_fused(const DevModel& m, const float* params, const float* deri
   const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("head_fused", st);
-  launch_k(head_fused_kernel<T>, grid, dim3(256), smem, st, m, params, derived, h, z, y, idx, idx_stride, B, R, dU, ll, grad);
+  launch_k(head_fused_kernel<T>, grid, dim3(256), smem, st, m, params, derived, h, (const void*)z, y, idx, idx_stride, B, R, dU, ll, grad);
+  return true;
+}
+bool head_fused_x3_supported(const DevModel& m) {
+  const int G = m.W / 8;
+  return m.W % 8 == 0 && G <= 256 && 256 % G == 0;
+}
+bool launch_head_fused_x3(const DevModel& m, const float* params, const float* derived, const __nv_bfloat16* h3,
+                          const float* z, const float* y, const int32_t* idx, int64_t idx_stride, int B,
+                          __nv_bfloat16* dU3, float* ll, float* grad, int n_net, cudaStream_t st) {
+  if (!head_fused_x3_supported(m)) return false;
+  const size_t smem = (size_t)(kHeadFusedMaxRows + 3 * m.W) * sizeof(float);
+  static int occ = 0, w_of = 0, dev_of = -1;
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  if (!occ || w_of != m.W || dev_of != dev_now) {
+    w_of = m.W;
+    dev_of = dev_now;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(head_fused_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel<__nv_bfloat16, true>, 256, smem);
+    if (occ < 1) occ = 1;
+  }
+  const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
+  dim3 grid((B + R - 1) / R, n_net);
+  BNF_PROF("head_fused", st);
+  launch_k(head_fused_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, st, m, params, derived, h3, (const void*)z, y, idx,
+           idx_stride, B, R, dU3, ll, grad);
   return true;
 }
 template bool launch_head_fused<float>(const DevModel&, const float*, const float*, const float*, const float*, const float*, const int32_t*, int64_t, int, float*, float*, float*, int, cudaStream_t);
@@ -1603,7 +1710,7 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
 void launch_map_update(const DevModel& m, float* params, float* am, float* av, float* grad,
                        int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
                        float* ll, float* const* loss_slot, int32_t* slot, unsigned int* counter, float* derived,
-                       __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st) {
+                       __nv_bfloat16* wn, size_t w_per_net, int wn_planes, int n_net, cudaStream_t st) {
   // about one wave of resident blocks in total: every block pays one fence + one ticket atomic
   const int sms = sm_count_cached();
   int bx = (sms * 8 + n_net - 1) / n_net;
@@ -1611,12 +1718,13 @@ void launch_map_update(const DevModel& m, float* params, float* am, float* av, f
   if (bx > bmax) bx = bmax;
   if (bx < 1) bx = 1;
   BNF_PROF("map_update", st);
-  if (wn)
+  // fast (MUFU) update math only in the single-pass bf16 mode; fp32 and bf16x3 keep optax's exact sequence
+  if (wn && wn_planes == 1)
     launch_k(map_update_kernel<true>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
-             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, n_net);
+             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, wn_planes, n_net);
   else
     launch_k(map_update_kernel<false>, dim3(bx, n_net), dim3(256), 0, st, m, params, am, av, grad, step_count, c_ll,
-             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, n_net);
+             prior_weight, lr, prior, ll, loss_slot, slot, counter, derived, wn, w_per_net, wn_planes, n_net);
 }
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st) {

@@ -51,7 +51,17 @@ void launch_map_adam(int P, float* params, float* am, float* av, const float* g_
 void launch_map_update(const DevModel& m, float* params, float* am, float* av, float* grad,
                        int32_t* step_count, float c_ll, float prior_weight, float lr, float* prior,
                        float* ll, float* const* loss_slot, int32_t* slot, unsigned int* counter, float* derived,
-                       __nv_bfloat16* wn, size_t w_per_net, int n_net, cudaStream_t st);
+                       __nv_bfloat16* wn, size_t w_per_net, int wn_planes, int n_net, cudaStream_t st);
+// ---- bf16x3 (split-operand) mode: activations fed to a GEMM are rows of three bf16 planes
+void launch_encode_x3(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
+                      int64_t idx_stride, int B, __nv_bfloat16* feat3, int n_net, cudaStream_t st);
+void launch_head_x3(const DevModel& m, const float* params, const float* derived, const __nv_bfloat16* h3,
+                    const float* y, const int32_t* idx, int64_t idx_stride, int B, float* out_loc,
+                    float* opre, float* r, float* ll, float* grad, int n_net, cudaStream_t st);
+bool head_fused_x3_supported(const DevModel& m);
+bool launch_head_fused_x3(const DevModel& m, const float* params, const float* derived, const __nv_bfloat16* h3,
+                          const float* z, const float* y, const int32_t* idx, int64_t idx_stride, int B,
+                          __nv_bfloat16* dU3, float* ll, float* grad, int n_net, cudaStream_t st);
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st);
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,

@@ -80,6 +80,35 @@ cast_weights_kernel(const __grid_constant__ DevModel m, const float* __restrict_
   }
 }
 
+// bf16x3 staging: wn3 = [layer][Kp][3*W] per network, plane p of element (k, n) at k*3W + p*W + n
+// (natural (in,out) order inside a plane, so both the forward (MN-major) and the dgrad (K-major)
+// B operand read it); rows >= fan_in are zero.
+__global__ void __launch_bounds__(256)
+cast_weights_x3_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                       bf16* __restrict__ wn3, size_t per_net) {
+  pdl_enter(params, wn3);
+  const int net = blockIdx.z;
+  for (int layer = 0; layer < m.L; ++layer) {
+    const int Kin = layer == 0 ? m.F : m.W, Kp = layer == 0 ? m.Fp : m.W;
+    const float* src = params + (size_t)net * m.P + m.off_kernel[layer];
+    bf16* dst = wn3 + 3 * ((size_t)net * per_net + (layer == 0 ? 0 : (size_t)m.Fp * m.W + (size_t)(layer - 1) * m.W * m.W));
+    const int total = Kp * m.W;
+    for (int e = (blockIdx.x * 256 + threadIdx.x); e < total; e += gridDim.x * 256) {
+      const int k = e / m.W, n = e - k * m.W;
+      const float v = k < Kin ? src[e] : 0.f;
+      bf16* d = dst + (size_t)k * 3 * m.W + n;
+      split3_one(v, d, d + m.W, d + 2 * m.W);
+    }
+  }
+}
+void tc_cast_weights_x3(const DevModel& m, const float* params, bf16* wn3, int n_net, cudaStream_t st) {
+  const int kmax = m.Fp > m.W ? m.Fp : m.W;
+  int bx = (kmax * m.W + 255) / 256;
+  if (bx > 64) bx = 64;
+  BNF_PROF("cast_weights", st);
+  launch_k(cast_weights_x3_kernel, dim3(bx, 1, n_net), dim3(256), 0, st, m, params, wn3, tc_weight_elems(m));
+}
+
 // wt may be NULL (only the natural-layout copy is needed)
 void tc_cast_weights(const DevModel& m, const float* params, bf16* wt, bf16* wn, int n_net, cudaStream_t st) {
   int kmax = m.Fp > m.W ? m.Fp : m.W;
@@ -259,6 +288,10 @@ struct TcArgs {
   const bf16* zin; float* gradp; int off_bias_prev, off_ls_prev, off_actw, layer_prev;
   int out_cm; // TC_DGRAD_F32: write outf column-major [net][col][row]
   const float* y; float* ll;   // TC_FWD_HEAD: observations, per-network log-likelihood accumulators
+  // split-operand (bf16x3) mode: every operand tensor holds three bf16 planes side by side along
+  // its contiguous dimension (plane p at columns [p*pstride, (p+1)*pstride)); the reduction runs over
+  // six segments of kseg k-blocks, one per plane pair (see kX3PlaneA / kX3PlaneB)
+  int x3, kseg, a_pstride, b_pstride;
   int dbg;   // BNF_TC_DBG ablation mask (only read when compiled with -DBNF_TC_EXPERIMENT)
   long long* tl;   // BNF_TC_TL timeline buffer [cta][16 tiles][16 events] of clock64 (experiment builds)
 };
@@ -299,6 +332,14 @@ __host__ __device__ constexpr int epi_warps_of(int mode, int a_mode) {
 constexpr bool kEpi16 = false;
 __host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { return mode == 5 /*TC_DGRAD_ACT*/ ? 12 : 8; }
 #endif
+// bf16x3 (split-operand, f32-parity) mode.  An f32 value a is carried as a0 + a1 + a2 with
+// a0 = bf16(a), a1 = bf16(a - a0), a2 = bf16(a - a0 - a1) (residual <= 2^-27 |a|); the f32 product
+// sum is the sum of the six bf16 GEMMs a_i.b_j with i + j <= 2 (dropped terms <= 2^-27).  They run
+// as ONE reduction of six segments into one TMEM accumulator, smallest products first: tcgen05
+// accumulates with round-toward-zero (measured, profiles/experiments/README.md r2a-2), so the
+// accumulator should be small while the many small addends arrive.  Segment s multiplies plane
+// kX3PlaneA[s] of A with plane kX3PlaneB[s] of B: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0).
+constexpr uint32_t kX3PlaneA = 0x001102u, kX3PlaneB = 0x010120u;   // nibble s = plane of segment s
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
 
 constexpr int kXTileBytes = 128 * kMaxD * 4;
@@ -312,7 +353,9 @@ constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer
 // CTA2: a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
 // from L2 drops by a third and the ring gets deeper (32 KB stages).
-template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct TcCfg {
+template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 = false> struct TcCfg {
+  static_assert(!X3 || MODE == TC_FWD || MODE == TC_DGRAD_ACT || MODE == TC_DGRAD_ENC, "x3 epilogues: fwd, dgrad+act, dgrad0+encode");
+  static_assert(!X3 || !kEpi16, "the x3 epilogues have no sixteen-warp variant");
   // TC_DGRAD_ENC: the dfeat tile stays on chip -- a 128 x (BLOCK_N+1) f32 tile in shared memory.
   // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
   // SM at Fp = 64: two ring stages, no TMA-store staging tiles (~100 KB, 128 TMEM columns each).
@@ -324,9 +367,11 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadScratch : 0;
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
-  static constexpr int kStgWarp = MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096;
-  static constexpr int kEpiW = epi_warps_of(MODE, A_MODE);
-  static constexpr int kStages = MODE == TC_DGRAD_ENC ? 2 :
+  // X3: TC_FWD [z f32 4 KB | h planes 3 x 2 KB]; TC_DGRAD_ACT [z ring kZRing x 4 KB | dU planes 3 x 2 KB]
+  static constexpr int kStgWarp = X3 ? (MODE == TC_DGRAD_ACT ? 4096 * kZRing + 3 * 2048 : 4096 + 3 * 2048)
+                                     : (MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096);
+  static constexpr int kEpiW = X3 ? 8 : epi_warps_of(MODE, A_MODE);
+  static constexpr int kStagesBf16 = MODE == TC_DGRAD_ENC ? 2 :
       MODE == TC_FWD_HEAD ? (kEpiW > 12 ? (CTA2 ? 2 : (BLOCK_N == 256 ? 1 : (BLOCK_N == 128 ? 3 : 4)))
                                         : (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : 4))) :
       MODE == TC_DGRAD_ACT ? (kEpiW > 12 ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 5))) :
@@ -336,12 +381,17 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
       (kEpiW > 12 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 6))) :
        kEpiW > 8 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))
                  : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
-  static constexpr int kEpi = epi_warps_of(MODE, A_MODE);
-  static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
-  static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
+  static constexpr int kEpi = kEpiW;
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // X3 (bigger staging tiles): as many ring stages as fit beside them, at most 6
+  static constexpr int kX3Fixed = kEpi * kStgWarp + kBarBytes + 2 * 256 * 4 + (MODE == TC_DGRAD_ACT ? (kAccCols + 32) * 4 : 0);
+  static constexpr int kStagesX3 = (232448 - kX3Fixed) / kStageBytes > 6 ? 6 : (232448 - kX3Fixed) / kStageBytes;
+  static constexpr int kStages = (X3 && MODE != TC_DGRAD_ENC) ? kStagesX3 : kStagesBf16;
+  static_assert(kStages >= 2, "at least two ring stages");
+  static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
+  static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
   static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpi * kStgWarp;
   // CTA-wide partial sums of the epilogue's column / scalar gradients (flushed to HBM when the
   // network changes): TC_DGRAD_ACT [kAccCols] bias columns + scalars
@@ -352,12 +402,12 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0> struct T
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, int A_MODE, int MODE, bool CTA2>
-__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE, CTA2, MODE>::kThreads), (TcCfg<BLOCK_N, A_MODE, CTA2, MODE>::kMinBlocks))
+template <int BLOCK_N, int A_MODE, int MODE, bool CTA2, bool X3 = false>
+__global__ void __launch_bounds__((TcCfg<BLOCK_N, A_MODE, CTA2, MODE, X3>::kThreads), (TcCfg<BLOCK_N, A_MODE, CTA2, MODE, X3>::kMinBlocks))
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_o0, const __grid_constant__ CUtensorMap map_o1,
                const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
-  using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2, MODE>;
+  using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2, MODE, X3>;
   constexpr bool A_MN = A_MODE == 1;                  // A operand MN-major
   constexpr bool B_MN = A_MODE == 1 || A_MODE == 3;   // B operand MN-major
   constexpr bool ENCODE = A_MODE == 2;
@@ -465,6 +515,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&empty[stage], phase ^ 1);
           if (lane == 0 && kb == kb0) TL((t - tile0) / tile_step, 0);
           if (lane == 0 && kb == kb1 - 1) TL((t - tile0) / tile_step, 1);
+          // x3: k-block kb of the six-segment reduction = k-block kk of plane pair (pa, pb)
+          int kk = kb, ca = 0, cb = 0;
+          if (a.x3) {
+            const int seg = kb / a.kseg;
+            kk = kb - seg * a.kseg;
+            ca = (int)((kX3PlaneA >> (4 * seg)) & 3u) * a.a_pstride;
+            cb = (int)((kX3PlaneB >> (4 * seg)) & 3u) * a.b_pstride;
+          }
           if (elect_one()) {
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
@@ -486,30 +544,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               else mbar_arrive_remote(&full[stage], 0);
               const int nb = n_t * BLOCK_N + (int)cta_rank * (BLOCK_N / 2);   // this CTA's half of B
               if (!A_MN) {
-                tma_load_3d_2sm(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+                tma_load_3d_2sm(sa, &map_a, &full[stage], kk * 64 + ca, m_t * 128, net);
               } else {
                 for (int j = 0; j < 2; ++j)
-                  tma_load_3d_2sm(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+                  tma_load_3d_2sm(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64 + ca, kk * 64, net);
               }
               if (!B_MN) {
-                tma_load_3d_2sm(sb, &map_b, &full[stage], kb * 64, nb, net);
+                tma_load_3d_2sm(sb, &map_b, &full[stage], kk * 64 + cb, nb, net);
               } else {
                 for (int j = 0; j < BLOCK_N / 128; ++j)
-                  tma_load_3d_2sm(sb + j * 8192, &map_b, &full[stage], nb + j * 64, kb * 64, net);
+                  tma_load_3d_2sm(sb + j * 8192, &map_b, &full[stage], nb + j * 64 + cb, kk * 64, net);
               }
             } else {
               mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
               if (!A_MN) {
-                tma_load_3d(sa, &map_a, &full[stage], kb * 64, m_t * 128, net);
+                tma_load_3d(sa, &map_a, &full[stage], kk * 64 + ca, m_t * 128, net);
               } else {   // MN-major: boxes of [64 reduction rows][64 MN elements]
                 for (int j = 0; j < 2; ++j)
-                  tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64, kb * 64, net);
+                  tma_load_3d(sa + j * 8192, &map_a, &full[stage], m_t * 128 + j * 64 + ca, kk * 64, net);
               }
               if (!B_MN) {
-                tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
+                tma_load_3d(sb, &map_b, &full[stage], kk * 64 + cb, n_t * BLOCK_N, net);
               } else {
                 for (int j = 0; j < BLOCK_N / 64; ++j)
-                  tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
+                  tma_load_3d(sb + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64 + cb, kk * 64, net);
               }
             }
           }
@@ -585,10 +643,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float h_sl = 0.f, h_w = 0.f, h_sout = 0.f, h_bo = 0.f, h_fls = 0.f, h_flik = 0.f, h_fpi = 0.f, h_fos = 0.f;
     float p_wact = 0.f, p_sprev = 0.f, p_fls = 0.f;   // TC_DGRAD_ACT: per-network constants
     f32x2 gw2 = 0ull, gs2 = 0ull;    // TC_DGRAD_ACT: per-lane packed partial sums of the current network
+    float xg_w = 0.f, xg_s = 0.f;    // the same sums in the x3 epilogue (scalar math)
     // this warp's share of the two scalar gradients -> the CTA's shared-memory sums (before a flush)
     auto dact_scalars = [&]() {
-      const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2)) * a.isf;     // sum dh*diff,  dh = acc*isf
-      const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2)) * a.isf;     // sum dz*z,     dz = dh*act'(z)
+      const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2) + xg_w) * a.isf;     // sum dh*diff,  dh = acc*isf
+      const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2) + xg_s) * a.isf;     // sum dz*z,     dz = dh*act'(z)
+      xg_w = 0.f; xg_s = 0.f;
       if (lane == 0) {
         atomicAdd(&colacc[kAccCols], g_w * p_wact * (1.f - p_wact));
         atomicAdd(&colacc[kAccCols + 1], g_s * p_fls);
@@ -917,7 +977,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // DRAM round trip (measured: 15.1 -> 10.1 ms on the wind shard with both removed).
       float s_prev = 0.f;
       f32x2 cdu2 = 0ull;
-      uint8_t* zring = staging + warp * Cfg::kStgWarp + 2048;
+      constexpr int kZSlot = X3 ? 4096 : 2048;      // x3: z is f32 (32x32 f32 tile, 128B swizzle)
+      uint8_t* zring = staging + warp * Cfg::kStgWarp + (X3 ? 0 : 2048);
       uint64_t* zb = zbar + warp * kZRing;
       if (MODE == TC_DGRAD_ACT) {
         if (net != acc_net) {
@@ -949,8 +1010,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int i = 0; i < kZRing; ++i) {
             if (half * 32 + 32 * kParts * i >= BLOCK_N) break;
             const uint32_t sl = (zc + i) % kZRing;
-            mbar_arrive_expect_tx(&zb[sl], 2048);
-            tma_load_3d(zring + sl * 2048, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 32 * kParts * i, m_t * 128 + q * 32, net);
+            mbar_arrive_expect_tx(&zb[sl], kZSlot);
+            tma_load_3d(zring + sl * kZSlot, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 32 * kParts * i, m_t * 128 + q * 32, net);
           }
         }
       }
@@ -1074,6 +1135,97 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
+        if constexpr (X3 && MODE == TC_FWD) {
+          // ---- bf16x3 forward: z = acc*c1 + s_l*b stays f32 (the backward pass needs it), h = act(z)
+          // leaves as its three bf16 planes (the next GEMM's split A operand).  Staging per warp:
+          // [z 32x32 f32, 128B swizzle | h planes 3 x (32x32 bf16, 64B swizzle)]
+          uint8_t* stg = staging + warp * Cfg::kStgWarp;
+          uint32_t hp[3][16];
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * k);
+            const float z0 = fmaf(__uint_as_float(v[4 * k]), c1, b4.x), z1 = fmaf(__uint_as_float(v[4 * k + 1]), c1, b4.y);
+            const float z2 = fmaf(__uint_as_float(v[4 * k + 2]), c1, b4.z), z3 = fmaf(__uint_as_float(v[4 * k + 3]), c1, b4.w);
+            if (a.out0) *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(z0, z1, z2, z3);
+            float d, h0, h1, h2, h3;
+            act_grad_x3(z0, w_act, &d, &h0);
+            act_grad_x3(z1, w_act, &d, &h1);
+            act_grad_x3(z2, w_act, &d, &h2);
+            act_grad_x3(z3, w_act, &d, &h3);
+            split3_pair(h0, h1, &hp[0][2 * k], &hp[1][2 * k], &hp[2][2 * k]);
+            split3_pair(h2, h3, &hp[0][2 * k + 1], &hp[1][2 * k + 1], &hp[2][2 * k + 1]);
+          }
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(stg + 4096 + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(hp[p][4 * k], hp[p][4 * k + 1], hp[p][4 * k + 2], hp[p][4 * k + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) tma_store_3d(&map_o1, stg + 4096 + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
+            if (a.out0) tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          continue;
+        }
+        if constexpr (X3 && MODE == TC_DGRAD_ACT) {
+          // ---- bf16x3 dgrad + activation backward: the f32 z tile of the chunk arrives by TMA
+          // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as three bf16 planes.
+          // Staging per warp: [z ring | dU planes 3 x 2 KB]
+          uint8_t* so = staging + warp * Cfg::kStgWarp + kZRing * 4096;
+          const uint32_t zsl = zc % kZRing;
+          mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
+          const uint8_t* zt = zring + zsl * 4096 + lane * 128;
+          uint32_t pk[3][16];
+          float du[32];
+          const float cdu = a.isf * s_prev;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 z4 = *reinterpret_cast<const float4*>(zt + ((k ^ (lane & 7)) << 4));
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float vv = __uint_as_float(v[4 * k + e]);
+              float diff, hh;
+              const float da = act_grad_x3(zz[e], w_act, &diff, &hh);
+              const float x = vv * da;
+              xg_w = fmaf(vv, diff, xg_w);
+              xg_s = fmaf(x, zz[e], xg_s);
+              du[4 * k + e] = x * cdu;
+            }
+            split3_pair(du[4 * k], du[4 * k + 1], &pk[0][2 * k], &pk[1][2 * k], &pk[2][2 * k]);
+            split3_pair(du[4 * k + 2], du[4 * k + 3], &pk[0][2 * k + 1], &pk[1][2 * k + 1], &pk[2][2 * k + 1]);
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          // every lane has read its z row: refill the slot with the tile kZRing chunks ahead
+          if (lane == 0 && c + 32 * kParts * kZRing < BLOCK_N) {
+            mbar_arrive_expect_tx(&zb[zsl], 4096);
+            tma_load_3d(zring + zsl * 4096, &map_o1, &zb[zsl], col0 + 32 * kParts * kZRing, m_t * 128 + q * 32, net);
+          }
+          ++zc;
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(so + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(pk[p][4 * k], pk[p][4 * k + 1], pk[p][4 * k + 2], pk[p][4 * k + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          warp_transpose_sum(du, lane);
+          atomicAdd(&colacc[col0 + lane], du[0]);
+          continue;
+        }
         if (MODE == TC_FWD) {
           uint32_t zp[16], hp[16];
           const ActConst2 ak(w_act);
@@ -1291,7 +1443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const int r = lane + 32 * j;
               const float sx = sx_cur[r * (kMaxD + 1) + i];
               float sn, cs;
-              sincos_reduced(cc * sx, &sn, &cs);
+              if constexpr (X3) sincosf(cc * sx, &sn, &cs); else sincos_reduced(cc * sx, &sn, &cs);
               const float Gc = gtile[r * (BLOCK_N + 1) + cc0], Gs = gtile[r * (BLOCK_N + 1) + cs0];
               gs += (Gc * cs + Gs * sn) * rden;
               gl_a = fmaf(kf * (cs * Gs - sn * Gc), -sx, gl_a);
@@ -1304,7 +1456,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               const int r = lane + 32 * j;
               float sn, cs;
-              sincos_reduced(wk * sx_cur[r * (kMaxD + 1) + dm.D], &sn, &cs);
+              if constexpr (X3) sincosf(wk * sx_cur[r * (kMaxD + 1) + dm.D], &sn, &cs);
+              else sincos_reduced(wk * sx_cur[r * (kMaxD + 1) + dm.D], &sn, &cs);
               gs += (gtile[r * (BLOCK_N + 1) + c0] * cs + gtile[r * (BLOCK_N + 1) + c1i] * sn) * rh;
             }
           } else {
@@ -1504,19 +1657,34 @@ static int make_out_map(CUtensorMap* map, const bf16* base, uint64_t cols, uint6
   return 0;
 }
 
+// f32 tensor [net][rows][cols]: 32x32 boxes (128-byte rows), 128-byte swizzle (x3: z tiles)
+static int make_f32_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t nets) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return tc_fail(BNF_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {cols, rows, nets};
+  cuuint64_t strides[2] = {cols * 4, rows * cols * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return tc_fail(BNF_ERR_CUDA, "cuTensorMapEncodeTiled (f32 map) failed");
+  return 0;
+}
+
 struct OutMaps { CUtensorMap o0, o1; };
 
-template <int BLOCK_N, int MN, int MODE, bool CTA2>
+template <int BLOCK_N, int MN, int MODE, bool CTA2, bool X3 = false>
 static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
                        const DevModel* dm) {
-  using Cfg = TcCfg<BLOCK_N, MN, CTA2, MODE>;
+  using Cfg = TcCfg<BLOCK_N, MN, CTA2, MODE, X3>;
   static DevModel dm_zero;   // zero-initialised placeholder for the non-encode instantiations
   // the attribute is per DEVICE: a process that moves to another GPU must set it there too
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem) != cudaSuccess)
       return tc_fail(BNF_ERR_CUDA, "cudaFuncSetAttribute(smem) failed");
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
@@ -1526,7 +1694,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
   int grid = (int)(total < slots ? total : slots);
   if (grid < 1) grid = 1;
   if (CTA2) grid *= 2;
-  BNF_PROF(MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD_HEAD ? "tc_fwd_head" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  BNF_PROF(X3 && MODE == TC_FWD ? "tc_gemm_fwd_x3" : X3 && MODE == TC_DGRAD_ACT ? "tc_gemm_dgrad_x3" : MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD_HEAD ? "tc_fwd_head" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1557,7 +1725,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
     cudaMemsetAsync(d_tl, 0, 512 * 256 * sizeof(long long), st);
     ax.tl = d_tl;
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, ma, mb, om.o0, om.o1, ax, dmr);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2, X3>, ma, mb, om.o0, om.o1, ax, dmr);
   if (trace) {
     static int n_traced = 0;
     cudaStreamSynchronize(st);
@@ -1578,7 +1746,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
     }
   }
 #else
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2>, ma, mb, om.o0, om.o1, a, dmr);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BLOCK_N, MN, MODE, CTA2, X3>, ma, mb, om.o0, om.o1, a, dmr);
 #endif
   if (e != cudaSuccess) {
     snprintf(g_tc_err, sizeof(g_tc_err), "tc_gemm_kernel launch failed: %s", cudaGetErrorString(e));
@@ -1595,13 +1763,13 @@ static bool want_cta2(const TcArgs& a, int block_n) {
   return block_n == 256 && a.m_tiles >= 2;
 }
 
-template <int BLOCK_N, int MN, int MODE>
+template <int BLOCK_N, int MN, int MODE, bool X3 = false>
 static int launch_tc_m(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps& om, const TcArgs& a, int sm_count, cudaStream_t st,
                        const DevModel* dm = nullptr) {
   if constexpr (BLOCK_N == 256 && MN != 2 && (MODE == TC_FWD || MODE == TC_FWD_HEAD || MODE == TC_DGRAD_ACT || MODE == TC_WGRAD || MODE == TC_PLAIN_F32)) {
-    if (want_cta2(a, BLOCK_N)) return launch_tc_k<BLOCK_N, MN, MODE, true>(ma, mb, om, a, sm_count, st, dm);
+    if (want_cta2(a, BLOCK_N)) return launch_tc_k<BLOCK_N, MN, MODE, true, X3>(ma, mb, om, a, sm_count, st, dm);
   }
-  return launch_tc_k<BLOCK_N, MN, MODE, false>(ma, mb, om, a, sm_count, st, dm);
+  return launch_tc_k<BLOCK_N, MN, MODE, false, X3>(ma, mb, om, a, sm_count, st, dm);
 }
 
 // one kernel instantiation per (tile width, operand mode, epilogue): each carries only its own
@@ -1616,17 +1784,22 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
     return launch_tc_m<BLOCK_N, 1, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else if constexpr (MN == 3) {
     if (a.mode == TC_FWD_HEAD) return launch_tc_m<BLOCK_N, 3, TC_FWD_HEAD>(ma, mb, om, a, sm, st, dm);
+    if (a.mode == TC_FWD && a.x3) return launch_tc_m<BLOCK_N, 3, TC_FWD, true>(ma, mb, om, a, sm, st, dm);
     if (a.mode == TC_FWD) return launch_tc_m<BLOCK_N, 3, TC_FWD>(ma, mb, om, a, sm, st, dm);
     return launch_tc_m<BLOCK_N, 3, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else {
     switch (a.mode) {
       case TC_FWD: return launch_tc_m<BLOCK_N, 0, TC_FWD>(ma, mb, om, a, sm, st, dm);
-      case TC_DGRAD_ACT: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ACT>(ma, mb, om, a, sm, st, dm);
+      case TC_DGRAD_ACT:
+        if (a.x3) return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ACT, true>(ma, mb, om, a, sm, st, dm);
+        return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ACT>(ma, mb, om, a, sm, st, dm);
       case TC_DGRAD_BF16: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_BF16>(ma, mb, om, a, sm, st, dm);
       case TC_DGRAD_F32: return launch_tc_m<BLOCK_N, 0, TC_DGRAD_F32>(ma, mb, om, a, sm, st, dm);
       case TC_DGRAD_ENC:
-        if constexpr (BLOCK_N <= 128) return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ENC>(ma, mb, om, a, sm, st, dm);
-        else return tc_fail(BNF_ERR_INVALID, "TC_DGRAD_ENC needs one n-tile of <= 128 columns");
+        if constexpr (BLOCK_N <= 128) {
+          if (a.x3) return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ENC, true>(ma, mb, om, a, sm, st, dm);
+          return launch_tc_m<BLOCK_N, 0, TC_DGRAD_ENC>(ma, mb, om, a, sm, st, dm);
+        } else return tc_fail(BNF_ERR_INVALID, "TC_DGRAD_ENC needs one n-tile of <= 128 columns");
       default: return launch_tc_m<BLOCK_N, 0, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
     }
   }
@@ -1660,9 +1833,32 @@ bool tc_fwd_uses_wt() {
 }
 
 int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived, const bf16* a_in,
-                 const bf16* wt, const bf16* wn, bf16* z, bf16* h, int n_net, int B, cudaStream_t st) {
+                 const bf16* wt, const bf16* wn, bf16* z, bf16* h, int n_net, int B, cudaStream_t st,
+                 bool x3, float* zf) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
+  if (x3) {
+    // split operands: a_in [n_net,B,3*Kp], wn [layer][Kp][3*W]; outputs zf [n_net,B,W] f32 (may be
+    // NULL: forward only) and h [n_net,B,3*W]
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, a_in, 3 * (uint64_t)Kp, B, n_net, 3 * (uint64_t)Kp, (uint64_t)B * 3 * Kp, 128);
+    if (rc) return rc;
+    if ((rc = make_map(&mb, wn + 3 * layer_off(m, layer), 3 * (uint64_t)m.W, Kp, n_net, 3 * (uint64_t)m.W, 3 * tc_weight_elems(m), 64))) return rc;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mode = TC_FWD; a.n_net = n_net;
+    a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1;
+    a.x3 = 1; a.kseg = Kp / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W;
+    a.m_valid = B; a.n_valid = m.W;
+    a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
+    a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
+    a.out0 = (bf16*)zf; a.out1 = h; a.out_batch = (long long)B * m.W; a.ld_out = m.W;
+    OutMaps om;
+    memset(&om, 0, sizeof(om));
+    if ((rc = make_out_map(&om.o1, h, 3 * (uint64_t)m.W, B, n_net))) return rc;
+    if (zf && (rc = make_f32_map(&om.o0, zf, m.W, B, n_net))) return rc;
+    return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st);
+  }
   const bool use_wt = tc_fwd_uses_wt() || wn == nullptr;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
@@ -1757,6 +1953,36 @@ int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* der
   return launch_tc_n<2>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
+// bf16x3 variant of the fused dgrad + activation backward: dU [n_net,B,3*W] and wn [layer][Kp][3*W]
+// are split operands, z_prev [n_net,B,Kp] is f32, out [n_net,B,3*Kp] receives dU of layer-1 split.
+int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* dU, bf16* out, const float* z_prev,
+                    const float* params, const float* derived, float* grad, int n_net, int B, cudaStream_t st) {
+  const DevModel& m = p->m;
+  const int Kp = kp_of(m, layer), bn = pick_block_n(Kp);
+  if (layer < 1 || Kp > kAccCols) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad + activation backward needs W <= 1024");
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, dU, 3 * (uint64_t)m.W, B, n_net, 3 * (uint64_t)m.W, (uint64_t)B * 3 * m.W, 128);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = TC_DGRAD_ACT; a.n_net = n_net;
+  a.m_tiles = (B + 127) / 128; a.n_tiles = Kp / bn; a.k_splits = 1;
+  if ((rc = make_map(&mb, wn3 + 3 * layer_off(m, layer), 3 * (uint64_t)m.W, Kp, n_net, 3 * (uint64_t)m.W, 3 * tc_weight_elems(m),
+                     want_cta2(a, bn) ? bn / 2 : bn))) return rc;
+  a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W;
+  a.m_valid = B; a.n_valid = Kp;
+  a.isf = m.inv_sqrt_W;
+  a.zin = (const bf16*)z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
+  a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
+  a.off_ls_prev = m.off_layer_scale[layer - 1]; a.off_actw = m.off_actw;
+  a.out0 = out; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if ((rc = make_out_map(&om.o0, out, 3 * (uint64_t)Kp, B, n_net))) return rc;
+  if ((rc = make_f32_map(&om.o1, z_prev, Kp, B, n_net))) return rc;
+  return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
+}
+
 int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16* out_bf, float* out_f32,
              int n_net, int B, cudaStream_t st, const bf16* z_prev, const float* params,
              const float* derived, float* grad) {
@@ -1806,18 +2032,20 @@ bool tc_dgrad0_enc_supported(const DevModel& m) {
 
 int tc_dgrad0_enc(const bnf_plan* p, const bf16* wn, const bf16* dU, const float* x, const int32_t* idx,
                   int64_t idx_stride, const float* params, const float* derived, float* grad, int n_net,
-                  int B, cudaStream_t st) {
+                  int B, cudaStream_t st, bool x3) {
   const DevModel& m = p->m;
   const int Kp = m.Fp, bn = pick_block_n(Kp);
   if (!tc_dgrad0_enc_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad0 + encode backward needs Fp <= 128");
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 128);
+  const uint64_t pl = x3 ? 3 : 1;     // planes side by side in every operand row
+  int rc = make_map(&ma, dU, pl * m.W, B, n_net, pl * m.W, (uint64_t)B * pl * m.W, 128);
   if (rc) return rc;
-  if ((rc = make_map(&mb, wn, m.W, Kp, n_net, m.W, tc_weight_elems(m), bn))) return rc;
+  if ((rc = make_map(&mb, wn, pl * m.W, Kp, n_net, pl * m.W, pl * tc_weight_elems(m), bn))) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_DGRAD_ENC; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = m.W / 64;
+  if (x3) { a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W; }
   a.m_valid = B; a.n_valid = Kp;
   a.isf = m.inv_sqrt_F;
   a.x = x; a.idx = idx; a.idx_stride = idx_stride;
@@ -1828,19 +2056,21 @@ int tc_dgrad0_enc(const bnf_plan* p, const bf16* wn, const bf16* dU, const float
 }
 
 int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,
-             cudaStream_t st) {
+             cudaStream_t st, bool x3) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer), Kin = layer == 0 ? m.F : m.W, bn = pick_block_n(m.W);
   CUtensorMap ma, mb;
+  const uint64_t pl = x3 ? 3 : 1;     // planes side by side in every operand row
   // MN-major operands: boxes of [64 batch rows][64 contiguous features]
-  int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 64);
+  int rc = make_map(&ma, a_in, pl * Kp, B, n_net, pl * Kp, (uint64_t)B * pl * Kp, 64);
   if (rc) return rc;
-  rc = make_map(&mb, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 64);
+  rc = make_map(&mb, dU, pl * m.W, B, n_net, pl * m.W, (uint64_t)B * pl * m.W, 64);
   if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_WGRAD; a.n_net = n_net;
   a.m_tiles = (Kp + 127) / 128; a.n_tiles = m.W / bn; a.k_blocks = (B + 63) / 64;
+  if (x3) { a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; }
   const int sm = sm_count_of(p);
   const bool pair = want_cta2(a, bn);
   const int slots = pair ? sm / 2 : sm;
@@ -1849,6 +2079,13 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   if (base_tiles < slots) splits = (int)(slots / base_tiles);   // fill one wave, never a ragged second one
   if (splits > a.k_blocks / 4) splits = a.k_blocks / 4;   // >= 4 k-blocks per split
   if (splits < 1) splits = 1;
+  if (x3) {
+    // tcgen05 accumulates with round-toward-zero, one truncation per UMMA_K step: keep every TMEM
+    // accumulation short (<= 64 k-blocks = 4096 batch rows, ~4e-6 of the partial sum; measured in
+    // profiles/experiments/README.md r2a-2) and let the f32 atomics (round-to-nearest) add the splits
+    const int min_splits = (a.k_blocks + 63) / 64;
+    if (splits < min_splits) splits = min_splits;
+  }
   // every split must own at least one k-block
   while (splits > 1 && (a.k_blocks + splits - 1) / splits * (splits - 1) >= a.k_blocks) --splits;
   a.k_splits = splits;
@@ -1864,7 +2101,7 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
 int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_net, int M, int N, int K,
                   int sm_count, cudaStream_t st) {
   const int bn = pick_block_n(N);
-  if (N % 64 != 0 || (K % 64 != 0 && mn_major != 1)) return tc_fail(BNF_ERR_INVALID, "N, K must be multiples of 64");
+  if (N % 64 != 0 || (K % 64 != 0 && mn_major != 1 && mn_major != 4)) return tc_fail(BNF_ERR_INVALID, "N, K must be multiples of 64");
   CUtensorMap ma, mb;
   int rc;
   TcArgs a;
@@ -1874,6 +2111,31 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
   a.m_valid = M; a.n_valid = N; a.outf = C; a.out_batch = (long long)M * N; a.ld_out = N;
   OutMaps om;
   memset(&om, 0, sizeof(om));
+  if (mn_major >= 3 && mn_major <= 5) {
+    // split-operand (bf16x3) GEMMs: every operand row holds three bf16 planes side by side
+    //   3: A [net][M][3K] K-major,  B [net][K][3N] MN-major   (forward)
+    //   4: A [net][K][3M] MN-major, B [net][K][3N] MN-major   (wgrad)
+    //   5: A [net][M][3K] K-major,  B [net][N][3K] K-major    (dgrad)
+    if (K % 64 != 0 && mn_major != 4) return tc_fail(BNF_ERR_INVALID, "K must be a multiple of 64");
+    a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = 6 * a.kseg;
+    const uint64_t M3 = 3 * (uint64_t)M, N3 = 3 * (uint64_t)N, K3 = 3 * (uint64_t)K;
+    if (mn_major == 3) {
+      a.a_pstride = K; a.b_pstride = N;
+      if ((rc = make_map(&ma, A, K3, M, n_net, K3, (uint64_t)M * K3, 128))) return rc;
+      if ((rc = make_map(&mb, Bm, N3, K, n_net, N3, (uint64_t)K * N3, 64))) return rc;
+      return launch_tc_n<3>(bn, ma, mb, om, a, sm_count, st);
+    }
+    if (mn_major == 4) {
+      a.a_pstride = M; a.b_pstride = N;
+      if ((rc = make_map(&ma, A, M3, K, n_net, M3, (uint64_t)K * M3, 64))) return rc;
+      if ((rc = make_map(&mb, Bm, N3, K, n_net, N3, (uint64_t)K * N3, 64))) return rc;
+      return launch_tc_n<1>(bn, ma, mb, om, a, sm_count, st);
+    }
+    a.a_pstride = K; a.b_pstride = K;
+    if ((rc = make_map(&ma, A, K3, M, n_net, K3, (uint64_t)M * K3, 128))) return rc;
+    if ((rc = make_map(&mb, Bm, K3, N, n_net, K3, (uint64_t)N * K3, want_cta2(a, bn) ? bn / 2 : bn))) return rc;
+    return launch_tc_n<0>(bn, ma, mb, om, a, sm_count, st);
+  }
   if (mn_major == 2) {   // A [net][M][K] (K-major), B [net][K][N] (MN-major)
     if ((rc = make_map(&ma, A, K, M, n_net, K, (uint64_t)M * K, 128))) return rc;
     if ((rc = make_map(&mb, Bm, N, K, n_net, N, (uint64_t)N * K, 64))) return rc;

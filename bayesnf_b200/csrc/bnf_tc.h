@@ -19,8 +19,15 @@ void tc_cast_weights(const DevModel& m, const float* params, __nv_bfloat16* wt, 
 // B operand: `wn` read MN-major (default) or `wt` read K-major (BNF_FWD_WT=1 / wn == NULL)
 int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float* derived,
                  const __nv_bfloat16* a_in, const __nv_bfloat16* wt, const __nv_bfloat16* wn,
-                 __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B, cudaStream_t st);
+                 __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B, cudaStream_t st,
+                 bool x3 = false, float* zf = nullptr);
 bool tc_fwd_uses_wt();
+// ---- bf16x3 (split-operand, f32-parity) mode: every activation / weight tensor fed to a GEMM
+// holds three bf16 planes side by side (a = a0 + a1 + a2); z stays f32.  wn3 = [layer][Kp][3*W].
+void tc_cast_weights_x3(const DevModel& m, const float* params, __nv_bfloat16* wn3, int n_net, cudaStream_t st);
+int tc_dgrad_act_x3(const bnf_plan* p, int layer, const __nv_bfloat16* wn3, const __nv_bfloat16* dU,
+                    __nv_bfloat16* out, const float* z_prev, const float* params, const float* derived,
+                    float* grad, int n_net, int B, cudaStream_t st);
 // training step, last hidden layer: fwd GEMM + head + log-likelihood + activation backward
 bool tc_fwd_head_supported(const DevModel& m);
 int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const __nv_bfloat16* a_in,
@@ -43,9 +50,9 @@ bool tc_dgrad_act_supported(const DevModel& m);
 bool tc_dgrad0_enc_supported(const DevModel& m);
 int tc_dgrad0_enc(const bnf_plan* p, const __nv_bfloat16* wn, const __nv_bfloat16* dU, const float* x,
                   const int32_t* idx, int64_t idx_stride, const float* params, const float* derived,
-                  float* grad, int n_net, int B, cudaStream_t st);
+                  float* grad, int n_net, int B, cudaStream_t st, bool x3 = false);
 int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
-             float* grad, int n_net, int B, cudaStream_t st);
+             float* grad, int n_net, int B, cudaStream_t st, bool x3 = false);
 
 int tc_debug_gemm(int mn_major, const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, int n_net,
                   int M, int N, int K, int sm_count, cudaStream_t st);

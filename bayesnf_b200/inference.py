@@ -36,13 +36,19 @@ from . import parallel
 
 ArrayT = np.ndarray
 
+# 'bf16x3': tcgen05 tensor cores at f32-class accuracy (operands as bf16 triples, six products per
+#           GEMM, f32 pre-activations) -- meets the 1e-5 parity bar; the default.
+# 'bf16'  : single-pass bf16 tensor cores (throughput mode, ~1e-2 of scale).
+# 'fp32'  : SIMT f32 FMA (no tensor cores; any width).  'bf16_simt': debug.
+# 'tf32x3' is accepted as an alias of 'bf16x3' (the split-operand mode under its generic name).
 _PRECISIONS = {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16,
-               'bf16_simt': _lib.PREC_BF16_SIMT}
-_default_precision = os.environ.get('BAYESNF_B200_PRECISION', 'fp32')
+               'bf16_simt': _lib.PREC_BF16_SIMT, 'bf16x3': _lib.PREC_BF16X3,
+               'tf32x3': _lib.PREC_BF16X3}
+_default_precision = os.environ.get('BAYESNF_B200_PRECISION', 'bf16x3')
 
 
 def set_default_precision(name: str) -> None:
-  """'fp32' (SIMT, <=1e-5 parity mode) or 'bf16' (tcgen05 tensor cores)."""
+  """'bf16x3' (tensor cores, <=1e-5 parity), 'bf16' (tensor cores, throughput) or 'fp32' (SIMT)."""
   global _default_precision
   if name not in _PRECISIONS:
     raise ValueError(f'unknown precision {name!r}')
@@ -97,26 +103,55 @@ class Engine:
     if self.precision_name not in _PRECISIONS:
       raise ValueError(f'unknown precision {self.precision_name!r}')
     self.prec = _PRECISIONS[self.precision_name]
+    if precision is None and _lib.lib.bnf_precision_supported(spec.plan, self.prec) != 0:
+      # the DEFAULT tensor-core mode does not cover this shape (width not in {64..1024 powers of
+      # two} or > 128 features): the f32 SIMT CUDA kernels do.  An explicitly requested mode
+      # fails loudly instead.
+      self.precision_name, self.prec = 'fp32', _lib.PREC_FP32
     self.device = _device()
     self._ws: dict[tuple, torch.Tensor] = {}
 
+  # Workspaces are cached per (mode, networks, rows).  fit() / predict() alternate between a few
+  # shapes (training step, forecast slab, ragged last slab), so a handful stays alive; the oldest
+  # go when the cache holds more than `_WS_MAX_ENTRIES` buffers or `_WS_MAX_FRACTION` of the
+  # device memory.
+  _WS_MAX_ENTRIES = 4
+  _WS_MAX_FRACTION = 0.5
+
   def workspace(self, mode: int, n_net: int, rows: int) -> torch.Tensor:
     key = (mode, n_net, rows)
-    ws = self._ws.get(key)
+    ws = self._ws.pop(key, None)
     if ws is None:
       nbytes = _lib.lib.bnf_workspace_bytes(self.spec.plan, self.prec, n_net, rows, mode)
       if nbytes == 0:
         raise ValueError('invalid workspace request')
-      self._ws.clear()  # one live workspace: shapes change rarely
+      cap = self._WS_MAX_FRACTION * torch.cuda.get_device_properties(self.device).total_memory
+      while self._ws and (len(self._ws) >= self._WS_MAX_ENTRIES or
+                          nbytes + sum(t.numel() for t in self._ws.values()) > cap):
+        self._ws.pop(next(iter(self._ws)))          # least recently used first
       ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-      self._ws[key] = ws
+    self._ws[key] = ws                               # (re)insert as most recently used
     return ws
 
+  def forward_slab_rows(self, n_net: int, budget_bytes: int | None = None) -> int:
+    """Rows per forecast slab so that the forward workspace of `n_net` networks stays within a
+    memory budget (the reference forecasts in 1024-row batches for the same reason,
+    inference.py:129-181): clamp(budget // bytes_per_row, 128, 16384)."""
+    if budget_bytes is None:
+      free, _ = torch.cuda.mem_get_info(self.device)
+      budget_bytes = min(8 << 30, free // 4)
+    probe = 1024
+    per_row = _lib.lib.bnf_workspace_bytes(self.spec.plan, self.prec, n_net, probe, _lib.WS_FORWARD) / probe
+    rows = int(budget_bytes // max(per_row, 1.0))
+    return max(128, min(16384, rows // 128 * 128))
+
   # ---- mlp.apply over networks (forecast_inner, inference.py:103-126) ----
-  def forward(self, params: torch.Tensor, x: torch.Tensor, slab: int = 16384) -> torch.Tensor:
+  def forward(self, params: torch.Tensor, x: torch.Tensor, slab: int | None = None) -> torch.Tensor:
     """params [M,P] f32, x [N,D] f32 -> loc [M,N] f32 (row slabs like :129-181)."""
     M, N = params.shape[0], x.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+    if slab is None:
+      slab = self.forward_slab_rows(M)
     slab = max(1, min(slab, N))
     tmp = torch.empty((M, slab), dtype=torch.float32, device=self.device)
     for s in range(0, N, slab):

@@ -23,6 +23,7 @@ JAX path cannot be installed here), clocks, gpu_launches.
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import sys
 import threading
@@ -261,11 +262,16 @@ def main():
   ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--workload', default='chickenpox_map_e8', choices=sorted(WORKLOADS))
-  ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32', 'bf16_simt'])
+  ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'tf32x3', 'fp32', 'bf16_simt'],
+                  help="bf16: single-pass tcgen05 (BASELINE configs name bf16); bf16x3 (alias tf32x3): tcgen05 at "
+                       "the 1e-5 parity tolerance (split operands); fp32: SIMT")
+  ap.add_argument('--repeats', type=int, default=0, help='timed K-step blocks (0: >= 10 and >= 100 ms in total)')
   ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-baseline work')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-profile', action='store_true')
   args = ap.parse_args()
+  if args.precision == 'tf32x3':
+    args.precision = 'bf16x3'
   wl = WORKLOADS[args.workload]
   x, y, margs = synth(wl)
   if args.impl == 'reference':
@@ -302,7 +308,6 @@ def main():
   idx = None
   gen = torch.Generator(device=dev).manual_seed(rank)
   if is_vi:
-    import math
     rho = torch.full_like(p, math.log(math.expm1(0.3)))
     m = torch.zeros((E, 2, spec.num_params), dtype=torch.float32, device=dev)
     v = torch.zeros_like(m)
@@ -336,23 +341,44 @@ def main():
     torch.cuda.synchronize()
 
   # ---- device-resident timing -------------------------------------------------
+  # Warm up with W steps AND one block of exactly the timed shape (K steps: graph capture,
+  # workspace and loss-buffer allocation all happen here), then time R blocks of EXACTLY K steps,
+  # each bracketed by barrier + synchronize on both sides and by CUDA events on the launching
+  # stream; per block the MAX over ranks, over blocks the MEDIAN.  R >= 10 and R*K steps >= 100 ms,
+  # so one host hiccup on one rank cannot set the number.
   run(max(3, args.warmup))
-  sampler = ClockSampler(local)
-  barrier()
-  sampler.start()
-  l0 = _lib.lib.bnf_debug_launch_count()
+  run(args.steps)
+  torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  losses = run(args.steps)
+  run(args.steps)
   e1.record()
-  barrier()
-  launches = _lib.lib.bnf_debug_launch_count() - l0
-  sampler.stop_flag = True
-  ms = e0.elapsed_time(e1)
-  t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+  torch.cuda.synchronize()
+  est_ms = max(e0.elapsed_time(e1), 1e-3)
+  repeats = args.repeats or int(min(200, max(10, math.ceil(100.0 / est_ms))))
+  rep = torch.tensor([repeats], dtype=torch.int64, device=dev)
   if world > 1:
-    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-  ms = float(t_ms[0])
+    dist.all_reduce(rep, op=dist.ReduceOp.MAX)
+  repeats = int(rep[0])
+  sampler = ClockSampler(local)
+  sampler.start()
+  block_ms, launches = [], 0
+  for _ in range(repeats):
+    barrier()
+    l0 = _lib.lib.bnf_debug_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    losses = run(args.steps)
+    e1.record()
+    barrier()
+    launches = _lib.lib.bnf_debug_launch_count() - l0
+    block_ms.append(e0.elapsed_time(e1))
+  sampler.stop_flag = True
+  t_ms = torch.tensor(block_ms, dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)      # per block: the slowest rank
+  ms = float(t_ms.median())
+  ms_min, ms_max = float(t_ms.min()), float(t_ms.max())
   assert torch.isfinite(losses).all(), 'non-finite loss in the timed region'
   value = world * E * S * B * args.steps / (ms * 1e-3)   # network-rows per second (VI: x S draws)
 
@@ -396,9 +422,9 @@ def main():
 
   for i in range(3):
     e2e_enqueue(i)
-  e2e_pipe_s = timed(pipelined)
+  e2e_pipe_s = float(np.median([timed(pipelined) for _ in range(5)]))     # median of 5 blocks of k_e2e steps
   assert torch.isfinite(loss_host).all(), 'non-finite loss in the end-to-end region'
-  e2e_sync_s = timed(blocking)
+  e2e_sync_s = float(np.median([timed(blocking) for _ in range(3)]))
   e2e_val = world * E * S * B * k_e2e / e2e_pipe_s
   e2e_sync_val = world * E * S * B * k_e2e / e2e_sync_s
 
@@ -461,7 +487,10 @@ def main():
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'bf16_simt': 'bf16-storage/f32-fma'}[args.precision],
+        'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'bf16_simt': 'bf16-storage/f32-fma',
+                  'bf16x3': 'f32 via bf16x3 split operands (tcgen05 kind::f16, f32 accumulate)'}[args.precision],
+        'timing': {'blocks': repeats, 'steps_per_block': args.steps, 'block_ms_median': ms, 'block_ms_min': ms_min,
+                   'block_ms_max': ms_max, 'rule': 'median over blocks of the max over ranks (CUDA events)'},
         'data': 'synthetic',
         'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
                    'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,

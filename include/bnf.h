@@ -52,11 +52,18 @@ enum { BNF_NORMAL = 0, BNF_NB = 1, BNF_ZINB = 2 };
 /* Arithmetic mode of the dense stack.
  *   BNF_PREC_FP32 : f32 SIMT FMA, f32 activations.  The <=1e-5 parity mode.
  *   BNF_PREC_BF16 : tcgen05 kind::f16 (bf16 operands, f32 TMEM accumulators),
- *                   bf16 activations in HBM, f32 master weights/grads/Adam.   */
+ *                   bf16 activations in HBM, f32 master weights/grads/Adam.
+ *   BNF_PREC_BF16X3 : see below -- the tensor-core mode at the parity tolerance. */
 enum {
   BNF_PREC_FP32 = 0,
   BNF_PREC_BF16 = 1,
-  BNF_PREC_BF16_SIMT = 2 /* debug: bf16 storage, SIMT f32 FMA GEMMs (no tensor cores) */
+  BNF_PREC_BF16_SIMT = 2, /* debug: bf16 storage, SIMT f32 FMA GEMMs (no tensor cores) */
+  /* f32-class arithmetic ON the tensor cores: every GEMM operand a is carried as three bf16
+   * planes a0 + a1 + a2 (|a - a0 - a1 - a2| <= 2^-27 |a|) and every f32 GEMM runs as the six
+   * tcgen05 kind::f16 products a_i.b_j, i + j <= 2, into one f32 TMEM accumulator; pre-activations
+   * stay f32 in HBM; activation math with <= 3e-7 absolute error.  Meets the 1e-5 parity bar
+   * (tests/test_gpu_parity.py) -- the default precision of the Python layer.                   */
+  BNF_PREC_BF16X3 = 3
 };
 
 enum {
@@ -107,6 +114,11 @@ int bnf_plan_info(const bnf_plan_t* plan, bnf_plan_info_t* out);
 /* leaf 0.. in reference order (after the three scalars at offsets 0,1,2).     */
 int bnf_plan_leaf(const bnf_plan_t* plan, int32_t leaf, char* name, int32_t name_len,
                   int64_t* offset, int32_t* rows, int32_t* cols);
+
+/* 0 when `precision` can run this plan (tensor-core modes need width % 64 == 0; BNF_PREC_BF16X3
+ * also width in {64,128,256,512,1024} and <= 128 encoded features), else the error code the
+ * compute entry points would return (message in bnf_last_error()).  Host-only.          */
+int bnf_precision_supported(const bnf_plan_t* plan, int32_t precision);
 
 /* Bytes of scratch a call needs for `n_networks` x `batch_rows`.  `mode` says
  * which entry point will use it (for BNF_WS_VI n_networks = S * members).     */
@@ -209,6 +221,9 @@ int bnf_nb_mixture_quantiles(const float* loc, const float* shape_raw, const flo
  * bnf_debug_gemm: run the tcgen05 GEMM kernel alone, C[net][M][N] (f32) =
  *   mn_major == 0: A[net][M][K] x B[net][N][K]^T   (both K-major, as fwd/dgrad use it)
  *   mn_major == 1: A[net][K][M]^T x B[net][K][N]   (both MN-major, as wgrad uses it)
+ *   mn_major == 2: A[net][M][K] x B[net][K][N]     (A K-major, B MN-major: forward)
+ *   mn_major == 3, 4, 5: the bf16x3 (split-operand) versions of 2, 1, 0 -- every operand row
+ *     holds three bf16 planes side by side (A[net][M][3K] ...), C = the f32-accurate product.
  * A, B are bf16.  Used by tests/test_gpu_tc.py against a plain f32 matmul.      */
 int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c,
                    int32_t n_networks, int32_t m, int32_t n, int32_t k, void* stream);

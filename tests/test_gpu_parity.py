@@ -1,10 +1,11 @@
 """GPU parity: CUDA path (through the C ABI) vs the CPU oracle on the same inputs.
 
 Tolerances (stated per test):
-* fp32 mode: the north-star bar, 1e-5 relative to the tensor's scale for
-  forward values / log-likelihoods; gradients are compared against the
-  float64 twin of the oracle with 1e-4 of the leaf's max-abs (the f32 oracle's
-  own autograd noise is of that order on 80k-parameter sums).
+* fp32 (SIMT) and bf16x3 (tcgen05 tensor cores, split operands) modes: the north-star bar,
+  1e-5 relative to the tensor's scale for forward values / log-likelihoods; gradients are
+  compared against the float64 twin of the oracle with 1e-4 of the leaf's max-abs (the f32
+  oracle's own autograd noise is of that order on 80k-parameter sums).  Every parity test of
+  the f32 path is parametrised over BOTH modes with the SAME tolerance.
 * bf16 modes: bf16 operand rounding (2^-9) -> 3e-2 of scale.
 """
 import json
@@ -79,16 +80,26 @@ def _engine(cfg, dist='NORMAL', prec='fp32'):
   return inference.Engine(spec, prec), spec
 
 
+PARITY_MODES = ['fp32', 'bf16x3']   # SIMT f32 and the tensor-core f32-parity mode: same tolerances
+
+
+def _skip_unsupported(name, prec):
+  if prec == 'bf16x3' and name == 'odd':
+    pytest.skip('width 40 is not a tensor-core shape (bf16x3 needs width in {64..1024}); fp32 covers it')
+
+
+@pytest.mark.parametrize('prec', PARITY_MODES)
 @pytest.mark.parametrize('name', ['small', 'chickenpox', 'deep', 'odd'])
-def test_forward_fp32(cuda, name):
+def test_forward_fp32(cuda, name, prec):
   """mlp.apply: <= 1e-5 of output scale vs the f32 oracle (and its f64 twin)."""
   from bayesnf_b200 import inference
+  _skip_unsupported(name, prec)
   cfg = _cfgs()[name]
   n = cfg['init_x'][0]
   x, y = _data(cfg, n)
   om, om64 = O.OracleModel(**cfg), O.OracleModel(**cfg, dtype=torch.float64)
   P = _random_params(om, 3, y)
-  eng, spec = _engine(cfg)
+  eng, spec = _engine(cfg, prec=prec)
   xd, _ = inference._to_device_data(x, y)
   loc = eng.forward(P.to(cuda), xd, slab=64).cpu()
   for j in range(3):
@@ -99,17 +110,19 @@ def test_forward_fp32(cuda, name):
     assert float((loc[j].double() - want64).abs().max()) <= 1e-5 * scale + 1e-6
 
 
+@pytest.mark.parametrize('prec', PARITY_MODES)
 @pytest.mark.parametrize('dist', ['NORMAL', 'NB', 'ZINB'])
 @pytest.mark.parametrize('name', ['small', 'chickenpox', 'odd'])
-def test_loglik_and_grad_fp32(cuda, name, dist):
+def test_loglik_and_grad_fp32(cuda, name, dist, prec):
   from bayesnf_b200 import inference
+  _skip_unsupported(name, prec)
   cfg = _cfgs()[name]
   n = cfg['init_x'][0]
   x, y = _data(cfg, n, counts=dist != 'NORMAL')
   om64 = O.OracleModel(**cfg, dtype=torch.float64)
   om = O.OracleModel(**cfg)
   P = _random_params(om, 2, y, seed=3)
-  eng, spec = _engine(cfg, dist)
+  eng, spec = _engine(cfg, dist, prec)
   xd, yd = inference._to_device_data(x, y)
   ll, grad = eng.loglik_grad(P.to(cuda), xd, yd)
   ll, grad = ll.cpu(), grad.cpu()
@@ -124,10 +137,11 @@ def test_loglik_and_grad_fp32(cuda, name, dist):
       want = -g64[a:b]
       got = grad[j, a:b].double()
       tol = 1e-4 * float(want.abs().max()) + 1e-5 * float(g64.abs().max()) * 1e-2 + 1e-7
-      assert float((got - want).abs().max()) <= tol, (name, dist, a, b, float((got - want).abs().max()), tol)
+      assert float((got - want).abs().max()) <= tol, (name, dist, prec, a, b, float((got - want).abs().max()), tol)
 
 
-def test_minibatch_index_gather(cuda):
+@pytest.mark.parametrize('prec', PARITY_MODES)
+def test_minibatch_index_gather(cuda, prec):
   """Per-member index rows (inference.py:593-595) and the shared VI sub-batch."""
   from bayesnf_b200 import inference
   cfg = _cfgs()['small']
@@ -135,7 +149,7 @@ def test_minibatch_index_gather(cuda):
   x, y = _data(cfg, n)
   om = O.OracleModel(**cfg)
   P = _random_params(om, 2, y)
-  eng, _ = _engine(cfg)
+  eng, _ = _engine(cfg, prec=prec)
   xd, yd = inference._to_device_data(x, y)
   rng = np.random.default_rng(5)
   idx = np.stack([rng.permutation(n)[:64], rng.permutation(n)[:64]]).astype(np.int32)
@@ -150,8 +164,9 @@ def test_minibatch_index_gather(cuda):
     assert abs(float(ll1[j]) - float(want)) <= 2e-5 * abs(float(want))
 
 
+@pytest.mark.parametrize('prec', PARITY_MODES)
 @pytest.mark.parametrize('pw', [1.0, 0.0])
-def test_map_steps_fp32(cuda, pw):
+def test_map_steps_fp32(cuda, pw, prec):
   """k Adam steps from injected init / batch order == oracle fit (inference.py:577-619)."""
   from bayesnf_b200 import inference
   cfg = _cfgs()['small']
@@ -163,7 +178,7 @@ def test_map_steps_fp32(cuda, pw):
   perms = np.stack([[rng.permutation(n) for _ in range(2)] for _ in range(epochs)]).astype(np.int32)
   params, losses = inference.fit_map(x, y, 0, 'NORMAL', cfg, num_particles=2, learning_rate=0.01,
                                      num_epochs=epochs, prior_weight=pw, batch_size=B,
-                                     precision='fp32', init_params=P0.numpy(), batch_indices=perms)
+                                     precision=prec, init_params=P0.numpy(), batch_indices=perms)
   from bayesnf_b200 import models
   spec = models.ModelSpec(**cfg)
   flat = spec.flatten(params)[0]
@@ -178,14 +193,15 @@ def test_map_steps_fp32(cuda, pw):
     np.testing.assert_allclose(losses[0, j], lj.numpy(), rtol=2e-5)
 
 
-def test_full_batch_multi_epoch(cuda):
+@pytest.mark.parametrize('prec', PARITY_MODES)
+def test_full_batch_multi_epoch(cuda, prec):
   from bayesnf_b200 import inference, models
   cfg = _cfgs()['small']
   n = 200
   x, y = _data(cfg, n)
   om = O.OracleModel(**cfg)
   P0 = _random_params(om, 1, y, seed=2)
-  params, losses = inference.fit_map(x, y, 0, 'NORMAL', cfg, 1, 0.005, 4, precision='fp32',
+  params, losses = inference.fit_map(x, y, 0, 'NORMAL', cfg, 1, 0.005, 4, precision=prec,
                                      init_params=P0.numpy())
   xd, yd = inference._to_device_data(x, y)
   pj, lj = O.fit_map_member(om, P0[0], xd.cpu(), yd.cpu(), lambda ep: torch.arange(n), 4, n,
@@ -195,7 +211,8 @@ def test_full_batch_multi_epoch(cuda):
   np.testing.assert_allclose(losses[0, 0], lj.numpy(), rtol=2e-5)
 
 
-def test_vi_step_fp32(cuda):
+@pytest.mark.parametrize('prec', PARITY_MODES)
+def test_vi_step_fp32(cuda, prec):
   """One VI step with injected eps == oracle autograd through the reparameterised ELBO."""
   from bayesnf_b200 import inference, models
   cfg = _cfgs()['small']
@@ -213,7 +230,7 @@ def test_vi_step_fp32(cuda):
   kl, lr = 0.1, 0.01
   sur, losses, samples = inference.fit_vi(
       x, y, 0, 'NORMAL', cfg, ensemble_size=E, learning_rate=lr, num_epochs=1,
-      sample_size_divergence=S, sample_size_posterior=4, kl_weight=kl, precision='fp32',
+      sample_size_divergence=S, sample_size_posterior=4, kl_weight=kl, precision=prec,
       init_params=(mu.numpy(), rho.numpy()), eps=eps.numpy(),
       posterior_eps=np.zeros((4, E, P), np.float32))
   xd, yd = inference._to_device_data(x, y)
@@ -448,3 +465,65 @@ def test_full_size_additivity_and_permutation_invariance(cuda, prec, tol):
   assert float(((g_p - g).abs() / scale).max()) <= tol
   assert float(((g_a + g_b - g).abs() / scale).max()) <= tol
 
+
+
+def _chickenpox_full(n=10440):
+  """BASELINE configs[1] at full size: 8 members x 10 440 rows (20 sites x 522 weeks), W256 L2."""
+  cfg = dict(_cfgs()['chickenpox'])
+  cfg['init_x'] = (n, 3)
+  cfg['input_scales'] = [521.0, 1, 1]
+  rng = np.random.default_rng(0)
+  t = np.repeat(np.arange(522.0), 20)
+  x = np.stack([t, np.tile(rng.normal(size=20), 522), np.tile(rng.normal(size=20), 522)], 1)
+  y = 10 * np.sin(2 * np.pi * t / 52.1775) + 3 * x[:, 1] + rng.normal(size=n)
+  return cfg, x, y
+
+
+# mode -> (rel. tol. on the loss, gradient leaf tol. as a fraction of the leaf's max-abs,
+#          abs. tol. on the 99.9 % quantile of |param - oracle param| after 5 Adam steps of lr 0.005)
+FULL_SIZE_TOL = {'fp32': (2e-5, 1e-4, 1e-4), 'bf16x3': (2e-5, 1e-4, 1e-4), 'bf16': (2e-2, 5e-2, 5e-3)}
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16x3', 'bf16'])
+def test_full_size_configs1_against_oracle(cuda, prec):
+  """BASELINE configs[1] AT FULL SIZE (8 members x 10 440 rows, width 256, depth 2) directly against
+  the CPU oracle: the log-likelihood, every gradient leaf (vs the oracle's float64 twin) and the
+  parameters + loss curve after 5 full-batch MAP Adam steps (vs the f32 oracle's own
+  value_and_grad + optax.adam restatement, inference.py:599-608), for the SIMT f32 mode, the
+  tensor-core f32-parity mode (same tolerances) and the single-pass bf16 mode (its own, looser,
+  stated tolerances: bf16 has 8 significand bits)."""
+  from bayesnf_b200 import inference, models
+  ll_tol, g_tol, p_tol = FULL_SIZE_TOL[prec]
+  cfg, x, y = _chickenpox_full()
+  n, E, steps, lr = len(y), 8, 5, 0.005
+  om, om64 = O.OracleModel(**cfg), O.OracleModel(**cfg, dtype=torch.float64)
+  P0 = _random_params(om, E, y, seed=17)
+  eng, spec = _engine(cfg, 'NORMAL', prec)
+  xd, yd = inference._to_device_data(x, y)
+  ll, grad = eng.loglik_grad(P0.to(cuda), xd, yd)
+  ll, grad = ll.cpu(), grad.cpu()
+  parts = [(0, 1)] + [(o, o + (int(np.prod(s)) if s else 1)) for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+  xc, yc = xd.cpu(), yd.cpu()
+  for j in range(E):
+    loss64, g64 = O.map_loss_and_grad(om64, P0[j].double(), xc.double(), yc.double(), n, 0.0, 'NORMAL')
+    assert abs(float(ll[j]) + float(loss64)) <= ll_tol * abs(float(loss64)), (prec, j, float(ll[j]), float(loss64))
+    for (a, b) in parts:
+      want, got = -g64[a:b], grad[j, a:b].double()
+      # bf16: scalar leaves that are cancellation-prone sums get the usual floor of 1e-3 of the
+      # network's largest gradient (as in tests/test_gpu_tc.py); the f32-class modes get none
+      floor = 1e-3 * g_tol if prec == 'bf16' else 1e-7
+      tol = g_tol * float(want.abs().max()) + floor * float(g64.abs().max()) + 1e-7
+      err = float((got - want).abs().max())
+      assert err <= tol, (prec, j, a, b, err, tol)
+  # ---- 5 Adam steps (prior + optax.adam + restaged weights) from the same initial parameters
+  params, losses = inference.fit_map(x, y, 0, 'NORMAL', cfg, num_particles=E, learning_rate=lr,
+                                     num_epochs=steps, precision=prec, init_params=P0.numpy())
+  flat = models.ModelSpec(**cfg).flatten(params)[0]
+  for j in range(E):
+    pj, lj = O.fit_map_member(om, P0[j], xc, yc, lambda ep: torch.arange(n), steps, n, lr, 1.0, 'NORMAL')
+    np.testing.assert_allclose(losses[0, j], lj.numpy(), rtol=max(ll_tol, 2e-5))
+    d = np.abs(flat[j] - pj.numpy())
+    # Adam normalises the step: an entry whose gradient is pure summation noise may walk the
+    # other way (|delta| up to 2*lr per step), hence a quantile for the bulk and a hard cap
+    assert float(np.quantile(d, 0.999)) <= p_tol, (prec, j, float(np.quantile(d, 0.999)))
+    assert float(d.max()) <= 2 * lr * steps + 1e-6

@@ -346,3 +346,44 @@ def test_single_step_calls_replay_cached_graph(cuda):
     tol = 1e-5 if prec == 'fp32' else 2e-3
     np.testing.assert_allclose(outs[0][1].numpy(), outs[1][1].numpy(), rtol=tol)
     assert float((outs[0][0] - outs[1][0]).abs().max()) <= (1e-5 if prec == 'fp32' else 2e-2)
+
+
+def _split3(x):
+  """f32 -> three bf16 planes concatenated along the last axis (the bf16x3 operand layout)."""
+  x0 = x.to(torch.bfloat16)
+  r1 = x - x0.float()
+  x1 = r1.to(torch.bfloat16)
+  x2 = (r1 - x1.float()).to(torch.bfloat16)
+  return torch.cat([x0, x1, x2], dim=-1).contiguous()
+
+
+@pytest.mark.parametrize('cta2', ['0', '1'])
+@pytest.mark.parametrize('layout,nets,m,n,k', [
+    (3, 1, 128, 64, 64), (3, 2, 300, 256, 256), (3, 2, 1000, 512, 1024), (3, 8, 10440, 256, 64),
+    (4, 1, 64, 64, 200), (4, 2, 256, 256, 1000), (4, 8, 256, 256, 10440),
+    (5, 1, 128, 64, 64), (5, 3, 200, 128, 192), (5, 2, 1000, 256, 256)])
+def test_gemm_split_operands(cuda, monkeypatch, cta2, layout, nets, m, n, k):
+  """bf16x3 GEMMs (six bf16 products of the operands' three planes, one TMEM accumulator) in the
+  three operand layouts of the dense stack, against the f64 product of the f32 inputs:
+  <= 2e-6 of the output scale per 1024 reduction elements (f32 rounding class; cuBLAS f32 measures
+  5e-7 .. 1.2e-6 on the same shapes, profiles/experiments/README.md r2a-3).  The TMEM accumulation
+  rounds toward zero once per 16 reduction elements, so the error of ONE accumulation grows with
+  K; the real wgrad therefore splits the batch into <= 4096-row accumulations (tc_wgrad) whose
+  partial sums are added by f32 atomics -- the whole-path tests check that."""
+  monkeypatch.setenv('BNF_CTA2', cta2)
+  g = torch.Generator(device='cuda').manual_seed(m + 3 * n + k + layout)
+  if layout == 3:     # A [M,K] . B [K,N]
+    a = torch.randn(nets, m, k, generator=g, device=cuda)
+    b = torch.randn(nets, k, n, generator=g, device=cuda)
+    want = torch.bmm(a.double(), b.double())
+  elif layout == 4:   # A [K,M]^T . B [K,N]
+    a = torch.randn(nets, k, m, generator=g, device=cuda)
+    b = torch.randn(nets, k, n, generator=g, device=cuda)
+    want = torch.bmm(a.double().transpose(1, 2), b.double())
+  else:               # A [M,K] . B [N,K]^T
+    a = torch.randn(nets, m, k, generator=g, device=cuda)
+    b = torch.randn(nets, n, k, generator=g, device=cuda)
+    want = torch.bmm(a.double(), b.double().transpose(1, 2))
+  c = _gemm(layout, _split3(a), _split3(b), nets, m, n, k)
+  err = float((c.double() - want).abs().max())
+  assert err <= 2e-6 * max(1.0, k / 1024) * float(want.abs().max()), err
