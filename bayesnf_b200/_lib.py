@@ -57,6 +57,11 @@ SIGNATURES = {
     'bnf_loglik_grad': (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),
     'bnf_map_steps': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, _I32, _I32,
                                 _I32, _F, _F, _P, _P, _SZ, _P]),
+    'bnf_map_epochs': (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _F, _F, _U64, _I64,
+                                 _P, _P, _SZ, _P]),
+    'bnf_vi_steps': (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I32, _I32, _U64, _I64, _P, _P, _I32, _I32, _I32,
+                               _F, _F, _P, _P, _SZ, _P]),
+    'bnf_debug_permutation': (C.c_int, [_U64, _I64, _I32, _I32, C.POINTER(_I32)]),
     'bnf_vi_step': (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I32, _I32, _P, _U64, _P, _P, _P,
                               _I32, _I32, _F, _F, _P, _P, _SZ, _P]),
     'bnf_vi_sample': (C.c_int, [_P, _P, _P, _I32, _I32, _P, _U64, _P, _P]),

@@ -163,17 +163,13 @@ extern "C" int bnf_plan_create(const bnf_config_t* c, bnf_plan_t** out) {
   return BNF_OK;
 }
 
-struct MapGraphKey;
-static void free_map_graph_keys(bnf_plan* p);
+static void free_graph_cache(bnf_plan* p);
 
 extern "C" void bnf_plan_destroy(bnf_plan_t* p) {
   if (!p) return;
-  if (p->graph_stream) {
-    cudaDeviceSynchronize();
-    if (p->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
-    cudaStreamDestroy((cudaStream_t)p->graph_stream);
-  }
-  free_map_graph_keys(p);
+  if (p->graph_stream) cudaDeviceSynchronize();
+  free_graph_cache(p);
+  if (p->graph_stream) cudaStreamDestroy((cudaStream_t)p->graph_stream);
   delete p;
 }
 
@@ -224,6 +220,7 @@ struct Ws {
   float* ll; float* prior;
   float* grad;             // MAP / VI internal gradient [n_net, P]
   float* vz; float* veps; float* vloss;  // VI
+  int32_t* idxwin;         // device-drawn batch windows [n_net (MAP) or 1 (VI), B]
   bf16* wt; bf16* wn;      // bf16 weight staging for the tcgen05 path
   float* mm;               // small scratch
   size_t bytes;
@@ -262,6 +259,8 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
     w.dfeat = x3 ? nullptr : (float*)c.take(rows * m.Fp * 4);   // bf16x3: dfeat never leaves the SM
   }
   if (mode == BNF_WS_MAP || mode == BNF_WS_VI) w.grad = (float*)c.take((size_t)n_net * m.P * 4);
+  if (mode == BNF_WS_MAP) w.idxwin = (int32_t*)c.take((size_t)n_net * B * 4);
+  if (mode == BNF_WS_VI) w.idxwin = (int32_t*)c.take((size_t)B * 4);
   if (mode == BNF_WS_VI) {
     w.vz = (float*)c.take((size_t)n_net * m.P * 4);
     w.veps = (float*)c.take((size_t)n_net * m.P * 4);
@@ -503,31 +502,102 @@ extern "C" int bnf_loglik_grad(const bnf_plan_t* p, int32_t prec, const float* p
   return run_net_any(p, prec, params, n_net, x, y, idx, idx_stride, B, w, nullptr, out_ll, grad, st);
 }
 
-// Signature of a captured MAP step: every pointer / scalar baked into the graph's kernel nodes.
-// (The loss buffer is NOT baked: map_update_kernel reads its address from the workspace, where the
-// prologue of every call stores it -- callers may pass a fresh buffer per call and still replay.)
-struct MapGraphKey {
-  const void* params; const void* am; const void* av; const void* step_count; const void* x;
-  const void* y; const void* ws;
-  int prec, n_net, B, n_total; float lr, pw; int flags, pad;
-  bool operator==(const MapGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+// ---- CUDA-graph replay of one training step -------------------------------------------------
+// Signature of a captured step: every pointer / scalar baked into the graph's kernel nodes.
+// (The loss buffer is NOT baked: the kernels that write a step's loss read its address from the
+// workspace, where the prologue of every call stores it -- callers may pass a fresh buffer per
+// call and still replay.)
+struct StepGraphKey {
+  const void* p0; const void* p1; const void* p2; const void* p3; const void* step_count; const void* x;
+  const void* y; const void* idx; const void* ws;
+  long long idx_stride, first_member; unsigned long long seed;
+  int kind, prec, n_net, aux, B, n_total; float lr, w; int flags, shuffle;
+  bool operator==(const StepGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
 };
 
-static void free_map_graph_keys(bnf_plan* p) {
-  delete (MapGraphKey*)p->graph_key;
-  delete (MapGraphKey*)p->last_key;
-  p->graph_key = p->last_key = nullptr;
+static void free_graph_cache(bnf_plan* p) {
+  for (int k = 0; k < 2; ++k) {
+    if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+    delete (StepGraphKey*)p->graph_key[k];
+    delete (StepGraphKey*)p->last_key[k];
+    p->graph_exec[k] = p->graph_key[k] = p->last_key[k] = nullptr;
+  }
 }
 static bool pdl_scope_would_enable() {
   const char* e = getenv("BNF_PDL");
   return !(e && e[0] == '0');
 }
 
-extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
-                             int32_t* step_count, int32_t n_net, const float* x, const float* y,
-                             const int32_t* idx, int64_t idx_stride, int32_t B, int32_t n_total,
-                             int32_t n_steps, float lr, float prior_weight, float* out_loss, void* ws,
-                             size_t ws_bytes, void* stream) {
+// Replays `one_step` n_steps times on `st`: as a cached CUDA graph (slot `kind`: 0 MAP, 1 VI) when
+// its arguments are those of the cached capture or the call is long enough to pay for a capture,
+// else as direct launches.  one_step(stream) must enqueue a step whose launch arguments do not
+// depend on the step number.
+template <typename F>
+static int replay_steps(const bnf_plan* p, int kind, const StepGraphKey& key, int n_steps, cudaStream_t st, F one_step) {
+  bool use_graph = !prof_enabled() && !getenv("BNF_NO_GRAPH");
+  if (use_graph) {
+    StepGraphKey* cached = (StepGraphKey*)p->graph_key[kind];
+    StepGraphKey* last = (StepGraphKey*)p->last_key[kind];
+    const bool hit = p->graph_exec[kind] && cached && *cached == key;
+    const bool seen = last && *last == key;
+    if (!last) { last = new StepGraphKey(); p->last_key[kind] = last; }
+    *last = key;
+    if (!hit && n_steps < 4 && !seen) use_graph = false;     // not worth a capture yet
+    if (use_graph && !hit) {
+      if (!p->graph_stream) {
+        cudaStream_t gs;
+        CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        p->graph_stream = gs;
+      }
+      cudaStream_t gs = (cudaStream_t)p->graph_stream;
+      if (p->graph_exec[kind]) {
+        // the old graph may still be running on the caller's stream
+        CU(cudaStreamSynchronize(st));
+        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[kind]);
+        p->graph_exec[kind] = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+      const unsigned long long before = bnf_debug_launch_count();
+      const int rc = one_step(gs);
+      p->graph_launches[kind] = (long long)(bnf_debug_launch_count() - before);
+      cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+      prof_add_launches(-p->graph_launches[kind]);                 // captured, not launched
+      if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (rc) return rc;
+        return fail(BNF_ERR_CUDA, "CUDA graph capture of the training step failed (%s)", cudaGetErrorString(ce));
+      }
+      cudaGraphExec_t exec = nullptr;
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      p->graph_exec[kind] = exec;
+      if (!cached) { cached = new StepGraphKey(); p->graph_key[kind] = cached; }
+      *cached = key;
+    }
+  }
+  if (use_graph) {
+    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[kind], st));
+    prof_add_launches(p->graph_launches[kind] * n_steps);
+    return BNF_OK;
+  }
+  for (int s = 0; s < n_steps; ++s) {
+    int rc = one_step(st);
+    if (rc) return rc;
+  }
+  CUK();
+  return BNF_OK;
+}
+
+// shuffle: the batch windows are drawn on the device (idx must be NULL); else idx / idx == NULL as
+// documented for bnf_map_steps
+static int map_steps_impl(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
+                          int32_t* step_count, int32_t n_net, const float* x, const float* y,
+                          const int32_t* idx, int64_t idx_stride, int32_t B, int32_t n_total,
+                          int32_t n_steps, float lr, float prior_weight, bool shuffle, uint64_t seed,
+                          int64_t first_member, float* out_loss, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_common(p, prec, n_net, B);
   if (rc) return rc;
   if (!params || !am || !av || !step_count || !x || !y || !out_loss || !ws)
@@ -543,6 +613,8 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   float** loss_slot = (float**)(w.mm + 10);                  // device copy of `out_loss` (8-byte aligned)
   const bool x3 = prec == BNF_PREC_BF16X3;
   const bool tc = prec == BNF_PREC_BF16;
+  const int spe = n_total / B;                               // steps per epoch (ragged tail dropped)
+  if (shuffle) { idx = w.idxwin; idx_stride = B; }
   // Paths that read the transposed weight copy (fused-encode experiment, BNF_FWD_WT=1) keep the
   // round-1 step (prep + cast every step): the fused update only maintains the natural copy.
   const bool legacy = (tc && need_wt()) || getenv("BNF_LEGACY_STEP");
@@ -550,10 +622,11 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   if (legacy) {
     CU(cudaMemsetAsync(slot, 0, 4, st));
     for (int s = 0; s < n_steps; ++s) {
-      const int32_t* idx_s = idx ? idx + (size_t)s * B : nullptr;
+      const int32_t* idx_s = (idx && !shuffle) ? idx + (size_t)s * B : idx;
       CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
       CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
       CU(cudaMemsetAsync(w.prior, 0, (size_t)n_net * 4, st));
+      if (shuffle) launch_batch_window(n_total, B, spe, n_net, seed, first_member, step_count, w.idxwin, st);
       launch_tick(step_count, slot, st);
       rc = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, st);
       if (rc) return rc;
@@ -571,11 +644,13 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
   if (x3) tc_cast_weights_x3(m, params, w.wn, n_net, st);
   CUK();
 
-  // One training step: encode -> fwd GEMMs -> head -> bwd GEMMs -> encode_bwd -> fused update.
-  // Launch arguments do not depend on the step (device-side cursors), so the sequence replays
-  // as one CUDA graph; consecutive kernels are chained by programmatic dependent launch.
+  // One training step: [batch window] -> encode -> fwd GEMMs -> head -> bwd GEMMs -> encode_bwd ->
+  // fused update.  With idx == NULL (full batch) or device-drawn windows the launch arguments do
+  // not depend on the step (device-side cursors), so the sequence replays as one CUDA graph;
+  // consecutive kernels are chained by programmatic dependent launch.
   auto one_step = [&](cudaStream_t s, const int32_t* idx_s) -> int {
     PdlScope pdl(true);
+    if (shuffle) launch_batch_window(n_total, B, spe, n_net, seed, first_member, step_count, w.idxwin, s);
     int r = run_net_any(p, prec, params, n_net, x, y, idx_s, idx_stride, B, w, nullptr, w.ll, w.grad, s, /*prepped=*/true);
     if (r) return r;
     launch_map_update(m, params, am, av, w.grad, step_count, c_ll, prior_weight, lr, w.prior, w.ll, loss_slot,
@@ -584,66 +659,102 @@ extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, f
     return BNF_OK;
   };
 
-  // Full-batch steps (idx == NULL) replay a cached graph; it is re-captured when any baked
-  // argument changes.  A single short call with new arguments runs direct launches instead.
-  bool use_graph = idx == nullptr && !prof_enabled() && !getenv("BNF_NO_GRAPH");
-  MapGraphKey key;
-  memset(&key, 0, sizeof(key));
-  key.params = params; key.am = am; key.av = av; key.step_count = step_count; key.x = x; key.y = y;
-  key.ws = ws; key.prec = prec; key.n_net = n_net; key.B = B; key.n_total = n_total;
-  key.lr = lr; key.pw = prior_weight; key.flags = (pdl_scope_would_enable() ? 1 : 0) | (need_wt() ? 2 : 0);
-  if (use_graph) {
-    MapGraphKey* cached = (MapGraphKey*)p->graph_key;
-    MapGraphKey* last = (MapGraphKey*)p->last_key;
-    const bool hit = p->graph_exec && cached && *cached == key;
-    const bool seen = last && *last == key;
-    if (!last) { last = new MapGraphKey(); p->last_key = last; }
-    *last = key;
-    if (!hit && n_steps < 4 && !seen) use_graph = false;     // not worth a capture yet
-    if (use_graph && !hit) {
-      if (!p->graph_stream) {
-        cudaStream_t gs;
-        CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
-        p->graph_stream = gs;
-      }
-      cudaStream_t gs = (cudaStream_t)p->graph_stream;
-      if (p->graph_exec) {
-        // the old graph may still be running on the caller's stream
-        CU(cudaStreamSynchronize(st));
-        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec);
-        p->graph_exec = nullptr;
-      }
-      cudaGraph_t graph = nullptr;
-      CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
-      const unsigned long long before = bnf_debug_launch_count();
-      rc = one_step(gs, nullptr);
-      p->graph_launches = (long long)(bnf_debug_launch_count() - before);
-      cudaError_t ce = cudaStreamEndCapture(gs, &graph);
-      prof_add_launches(-p->graph_launches);                 // captured, not launched
-      if (rc || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        return fail(BNF_ERR_CUDA, "CUDA graph capture of the MAP step failed (%s)", cudaGetErrorString(ce));
-      }
-      cudaGraphExec_t exec = nullptr;
-      ce = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-      p->graph_exec = exec;
-      if (!cached) { cached = new MapGraphKey(); p->graph_key = cached; }
-      *cached = key;
-    }
-  }
-  if (use_graph) {
-    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec, st));
-    prof_add_launches(p->graph_launches * n_steps);
-    return BNF_OK;
+  if (idx == nullptr || shuffle) {
+    StepGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p0 = params; key.p1 = am; key.p2 = av; key.step_count = step_count; key.x = x; key.y = y;
+    key.idx = idx; key.idx_stride = idx_stride; key.ws = ws; key.kind = 0; key.prec = prec; key.n_net = n_net;
+    key.B = B; key.n_total = n_total; key.lr = lr; key.w = prior_weight;
+    key.flags = (pdl_scope_would_enable() ? 1 : 0) | (need_wt() ? 2 : 0);
+    key.shuffle = shuffle ? 1 : 0; key.seed = shuffle ? seed : 0; key.first_member = shuffle ? first_member : 0;
+    return replay_steps(p, 0, key, n_steps, st, [&](cudaStream_t s) { return one_step(s, idx); });
   }
   for (int s = 0; s < n_steps; ++s) {
-    // idx == NULL: every step is a full pass over rows [0, B) (full-batch epochs)
-    rc = one_step(st, idx ? idx + (size_t)s * B : nullptr);
+    // injected index rows: step s uses rows [s*B, (s+1)*B) of every network's index row
+    rc = one_step(st, idx + (size_t)s * B);
     if (rc) return rc;
   }
+  CUK();
+  return BNF_OK;
+}
+
+extern "C" int bnf_map_steps(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
+                             int32_t* step_count, int32_t n_net, const float* x, const float* y,
+                             const int32_t* idx, int64_t idx_stride, int32_t B, int32_t n_total,
+                             int32_t n_steps, float lr, float prior_weight, float* out_loss, void* ws,
+                             size_t ws_bytes, void* stream) {
+  return map_steps_impl(p, prec, params, am, av, step_count, n_net, x, y, idx, idx_stride, B, n_total, n_steps, lr,
+                        prior_weight, false, 0, 0, out_loss, ws, ws_bytes, stream);
+}
+
+extern "C" int bnf_map_epochs(const bnf_plan_t* p, int32_t prec, float* params, float* am, float* av,
+                              int32_t* step_count, int32_t n_net, const float* x, const float* y, int32_t B,
+                              int32_t n_total, int32_t n_epochs, float lr, float prior_weight, uint64_t seed,
+                              int64_t first_member, float* out_loss, void* ws, size_t ws_bytes, void* stream) {
+  if (B < 1 || n_total < B || n_epochs < 1) return fail(BNF_ERR_INVALID, "bad batch_rows / n_rows_total / n_epochs");
+  const long long steps = (long long)n_epochs * (n_total / B);
+  if (steps > 0x7fffffffLL) return fail(BNF_ERR_INVALID, "too many steps");
+  return map_steps_impl(p, prec, params, am, av, step_count, n_net, x, y, nullptr, 0, B, n_total, (int)steps, lr,
+                        prior_weight, true, seed, first_member, out_loss, ws, ws_bytes, stream);
+}
+
+// One or more steps of the VI optimiser.  eps / idx injected (tests) only for single steps.
+static int vi_steps_impl(const bnf_plan_t* p, int32_t prec, float* mu, float* rho, float* am, float* av,
+                         int32_t* step_count, int32_t E, int32_t S, const float* eps, uint64_t seed,
+                         const float* x, const float* y, const int32_t* idx, bool shuffle, int64_t device_id,
+                         int32_t B, int32_t n_total, int32_t n_steps, float lr, float kl_weight,
+                         float* out_loss, void* ws, size_t ws_bytes, void* stream) {
+  if (E < 1 || S < 1) return fail(BNF_ERR_INVALID, "members and samples must be positive");
+  if ((long long)E * S > 65535) return fail(BNF_ERR_INVALID, "members x samples must be <= 65535");
+  const int n_net = E * S;
+  int rc = check_common(p, prec, n_net, B);
+  if (rc) return rc;
+  if (!mu || !rho || !am || !av || !step_count || !x || !y || !out_loss || !ws)
+    return fail(BNF_ERR_INVALID, "null pointer");
+  if (!(kl_weight > 0.f)) return fail(BNF_ERR_INVALID, "kl_weight must be positive");
+  if (n_steps < 1 || n_total < B) return fail(BNF_ERR_INVALID, "bad n_steps / n_rows_total");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ws w = carve(p, prec, n_net, B, BNF_WS_VI, ws);
+  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
+  const DevModel& m = p->m;
+  const float c = (float)((double)n_total / (double)B) / kl_weight;
+  int32_t* slot = (int32_t*)(w.mm + 8);                      // loss-row cursor
+  float** loss_slot = (float**)(w.mm + 10);                  // device copy of `out_loss`
+  if (shuffle) idx = w.idxwin;
+  // prologue: loss cursor = 0, loss buffer address -> workspace
+  launch_arm_loss(loss_slot, out_loss, slot, st);
+  auto one_step = [&](cudaStream_t s) -> int {
+    // one shared random sub-batch per device per step (inference.py:704-709): the first B entries of
+    // a fresh permutation keyed by (seed; device, number of completed steps)
+    if (shuffle) launch_batch_window(n_total, B, 1, 1, seed ^ 0x5649424154434855ULL, device_id, step_count, w.idxwin, s);
+    launch_tick(step_count, slot, s);
+    // device draws are keyed by (seed, step count): every step has its own Philox stream
+    launch_vi_sample(m.P, E, S, mu, rho, eps, w.veps, seed, 0x5649ULL, step_count, w.vz, s);
+    CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, s));
+    CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, s));
+    CU(cudaMemsetAsync(w.vloss, 0, (size_t)n_net * 4, s));
+    int r;
+    {
+      PdlScope pdl(true);
+      r = run_net_any(p, prec, w.vz, n_net, x, y, idx, 0, B, w, nullptr, w.ll, w.grad, s);
+    }
+    if (r) return r;
+    launch_vi_adam(m.P, E, S, mu, rho, am, av, w.vz, w.veps, w.grad, step_count, c, lr, w.vloss, s);
+    launch_vi_loss(E, S, w.vloss, w.ll, c, nullptr, loss_slot, slot, s);
+    return BNF_OK;
+  };
+  if (eps == nullptr && (idx == nullptr || shuffle)) {
+    StepGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.p0 = mu; key.p1 = rho; key.p2 = am; key.p3 = av; key.step_count = step_count; key.x = x; key.y = y;
+    key.idx = idx; key.ws = ws; key.kind = 1; key.prec = prec; key.n_net = E; key.aux = S; key.B = B;
+    key.n_total = n_total; key.lr = lr; key.w = kl_weight; key.flags = pdl_scope_would_enable() ? 1 : 0;
+    key.shuffle = shuffle ? 1 : 0; key.seed = seed; key.first_member = device_id;
+    return replay_steps(p, 1, key, n_steps, st, one_step);
+  }
+  if (n_steps != 1) return fail(BNF_ERR_INVALID, "injected eps / index rows are single-step hooks");
+  rc = one_step(st);
+  if (rc) return rc;
   CUK();
   return BNF_OK;
 }
@@ -653,32 +764,26 @@ extern "C" int bnf_vi_step(const bnf_plan_t* p, int32_t prec, float* mu, float* 
                            uint64_t seed, const float* x, const float* y, const int32_t* idx, int32_t B,
                            int32_t n_total, float lr, float kl_weight, float* out_loss, void* ws,
                            size_t ws_bytes, void* stream) {
-  if (E < 1 || S < 1) return fail(BNF_ERR_INVALID, "members and samples must be positive");
-  const int n_net = E * S;
-  int rc = check_common(p, prec, n_net, B);
-  if (rc) return rc;
-  if (!mu || !rho || !am || !av || !step_count || !x || !y || !out_loss || !ws)
-    return fail(BNF_ERR_INVALID, "null pointer");
-  if (!(kl_weight > 0.f)) return fail(BNF_ERR_INVALID, "kl_weight must be positive");
-  cudaStream_t st = (cudaStream_t)stream;
-  Ws w = carve(p, prec, n_net, B, BNF_WS_VI, ws);
-  if (w.bytes > ws_bytes) return fail(BNF_ERR_WORKSPACE, "workspace too small: need %zu, have %zu", w.bytes, ws_bytes);
-  const DevModel& m = p->m;
-  const float c = (float)((double)n_total / (double)B) / kl_weight;
-  launch_tick(step_count, nullptr, st);
-  // device draws are keyed by `seed`; the caller passes a fresh seed every step
-  launch_vi_sample(m.P, E, S, mu, rho, eps, w.veps, seed, 0x5649ULL, w.vz, st);
-  CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
-  CU(cudaMemsetAsync(w.ll, 0, (size_t)n_net * 4, st));
-  CU(cudaMemsetAsync(w.vloss, 0, (size_t)n_net * 4, st));
-  {
-    PdlScope pdl(true);
-    rc = run_net_any(p, prec, w.vz, n_net, x, y, idx, 0, B, w, nullptr, w.ll, w.grad, st);
-  }
-  if (rc) return rc;
-  launch_vi_adam(m.P, E, S, mu, rho, am, av, w.vz, w.veps, w.grad, step_count, c, lr, w.vloss, st);
-  launch_vi_loss(E, S, w.vloss, w.ll, c, out_loss, st);
-  CUK();
+  return vi_steps_impl(p, prec, mu, rho, am, av, step_count, E, S, eps, seed, x, y, idx, false, 0, B, n_total, 1, lr,
+                       kl_weight, out_loss, ws, ws_bytes, stream);
+}
+
+extern "C" int bnf_vi_steps(const bnf_plan_t* p, int32_t prec, float* mu, float* rho, float* am,
+                            float* av, int32_t* step_count, int32_t E, int32_t S, uint64_t seed,
+                            int64_t device_id, const float* x, const float* y, int32_t B, int32_t n_total,
+                            int32_t n_steps, float lr, float kl_weight, float* out_loss, void* ws,
+                            size_t ws_bytes, void* stream) {
+  return vi_steps_impl(p, prec, mu, rho, am, av, step_count, E, S, nullptr, seed, x, y, nullptr, B < n_total, device_id,
+                       B, n_total, n_steps, lr, kl_weight, out_loss, ws, ws_bytes, stream);
+}
+
+// permute_dataset (inference.py:35-39) as the device draws it: out[i] = row at position i of the
+// order of (seed; member, epoch).  Evaluated on the HOST (tests, replaying a device run).
+extern "C" int bnf_debug_permutation(uint64_t seed, int64_t member, int32_t epoch, int32_t n, int32_t* out) {
+  if (!out || n < 1 || epoch < 0) return fail(BNF_ERR_INVALID, "bad argument");
+  const bnf::PermKeys pk = bnf::perm_keys(seed, (uint64_t)member, (uint32_t)epoch);
+  const uint32_t hb = bnf::perm_half_bits((uint32_t)n);
+  for (int32_t i = 0; i < n; ++i) out[i] = (int32_t)bnf::perm_index((uint32_t)i, (uint32_t)n, hb, pk);
   return BNF_OK;
 }
 
@@ -686,7 +791,7 @@ extern "C" int bnf_vi_sample(const bnf_plan_t* p, const float* mu, const float* 
                              int32_t n_samples, const float* eps, uint64_t seed, float* out,
                              void* stream) {
   if (!p || !mu || !rho || !out || E < 1 || n_samples < 1) return fail(BNF_ERR_INVALID, "bad argument");
-  launch_vi_sample(p->m.P, E, n_samples, mu, rho, eps, nullptr, seed, 0x504fULL, out, (cudaStream_t)stream);
+  launch_vi_sample(p->m.P, E, n_samples, mu, rho, eps, nullptr, seed, 0x504fULL, nullptr, out, (cudaStream_t)stream);
   CUK();
   return BNF_OK;
 }

@@ -354,6 +354,50 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+// ---- keyed permutation of [0, n) without a sort (permute_dataset, inference.py:35-39) ---------
+// A balanced Feistel network on 2*half_bits bits (2^(2*half_bits) >= n) is a bijection of
+// [0, 2^(2*half_bits)); walking its cycle until the value falls below n restricts it to a bijection
+// of [0, n) (format-preserving encryption by cycle walking; cf. Mitchell et al., "Bandwidth-optimal
+// random shuffling for GPUs", 2021).  Every output index is computed independently in O(1): a
+// training step only evaluates the B entries of its batch window, no index array is materialised
+// for the epoch.  Round keys: two Philox blocks keyed by (seed; member, epoch).
+constexpr int kPermRounds = 8;
+struct PermKeys { uint32_t k[kPermRounds]; };
+__host__ __device__ __forceinline__ PermKeys perm_keys(uint64_t seed, uint64_t member, uint32_t epoch) {
+  PermKeys pk;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint4 a = philox4x32_10(make_uint4(epoch, 0x50524d30u, (uint32_t)member, (uint32_t)(member >> 32)), key);
+  const uint4 b = philox4x32_10(make_uint4(epoch, 0x50524d31u, (uint32_t)member, (uint32_t)(member >> 32)), key);
+  pk.k[0] = a.x; pk.k[1] = a.y; pk.k[2] = a.z; pk.k[3] = a.w;
+  pk.k[4] = b.x; pk.k[5] = b.y; pk.k[6] = b.z; pk.k[7] = b.w;
+  return pk;
+}
+__host__ __device__ __forceinline__ uint32_t perm_half_bits(uint32_t n) {
+  uint32_t bits = 1;
+  while (bits < 16 && (1ull << (2 * bits)) < (unsigned long long)n) ++bits;
+  return bits;                       // n <= 2^31 (row counts are int32)
+}
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {      // murmur3 finaliser
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t perm_index(uint32_t i, uint32_t n, uint32_t half_bits, const PermKeys& pk) {
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t v = i;
+  do {
+    uint32_t l = v >> half_bits, r = v & mask;
+#pragma unroll
+    for (int q = 0; q < kPermRounds; ++q) {
+      const uint32_t f = mix32(r ^ pk.k[q]) & mask;
+      const uint32_t nr = l ^ f;
+      l = r;
+      r = nr;
+    }
+    v = (l << half_bits) | r;
+  } while (v >= n);
+  return v;
+}
+
 __device__ __forceinline__ float u32_to_unit(uint32_t x) {   // (0, 1]
   return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }

@@ -948,9 +948,44 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
 }
 
 // =============================================================================
+// minibatch row windows drawn on the device
+//   MAP/MLE (inference.py:583-597): every member draws a fresh permutation of the n_total rows per
+//   epoch and walks it in windows of B rows (the ragged tail is dropped); VI (:704-709): one
+//   shared window per step = the first B entries of a fresh permutation.
+// The kernel reads the number of COMPLETED steps g from device memory (so its launch arguments
+// never change and the whole step replays as a CUDA graph): epoch = g / steps_per_epoch, window
+// = g % steps_per_epoch, and evaluates the keyed permutation (perm_index) for the B slots of each
+// index row: idx_win[row*B + i] = perm_{member(row), epoch}(window*B + i).
+// =============================================================================
+__global__ void __launch_bounds__(256)
+batch_window_kernel(int n_total, int B, int steps_per_epoch, uint64_t seed, int64_t first_member,
+                    const int32_t* step_count, int32_t* __restrict__ idx_win) {
+  __shared__ PermKeys pk;
+  pdl_enter(step_count, idx_win);
+  const int g = __ldcg(step_count);
+  const uint32_t epoch = (uint32_t)(g / steps_per_epoch), window = (uint32_t)(g % steps_per_epoch);
+  if (threadIdx.x == 0) pk = perm_keys(seed, (uint64_t)(first_member + blockIdx.y), epoch);
+  __syncthreads();
+  const uint32_t hb = perm_half_bits((uint32_t)n_total);
+  int32_t* out = idx_win + (size_t)blockIdx.y * B;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x)
+    out[i] = (int32_t)perm_index(window * (uint32_t)B + (uint32_t)i, (uint32_t)n_total, hb, pk);
+}
+
+// =============================================================================
 // prior + Adam (models.py:94-103; inference.py:558-569,580,605-606)
 // g_loss = -(c_ll*g_ll + pw*dlogprior); optax.adam; also sum of log-prior.
 // =============================================================================
+// prologue of a multi-step call: loss-row cursor = 0, address of the caller's loss buffer -> workspace
+__global__ void arm_loss_kernel(float** loss_slot, float* out_loss, int32_t* cursor) {
+  *loss_slot = out_loss;
+  *cursor = 0;
+}
+void launch_arm_loss(float** loss_slot, float* out_loss, int32_t* cursor, cudaStream_t st) {
+  BNF_PROF("arm_loss", st);
+  arm_loss_kernel<<<1, 1, 0, st>>>(loss_slot, out_loss, cursor);
+}
+
 __global__ void tick_kernel(int32_t* step_count, int32_t* slot) {
   *step_count += 1;
   if (slot) *slot += 1;
@@ -1157,7 +1192,10 @@ map_update_kernel(const __grid_constant__ DevModel m, float* params, float* __re
 __global__ void __launch_bounds__(256)
 vi_sample_kernel(int P, int E, int S, const float* __restrict__ mu, const float* __restrict__ rho,
                  const float* __restrict__ eps_in, float* __restrict__ eps_out, uint64_t seed,
-                 uint64_t stream_id, float* __restrict__ z) {
+                 uint64_t stream_id, const int32_t* __restrict__ step_ptr, float* __restrict__ z) {
+  // step_ptr (optional): the device-side step counter -- every optimisation step draws from its
+  // own Philox stream without the host passing a new seed (the step sequence replays as a graph)
+  if (step_ptr) stream_id ^= (uint64_t)(uint32_t)__ldcg(step_ptr) << 20;
   const size_t total = (size_t)S * E * P, EP = (size_t)E * P;
   const size_t groups = (total + 3) / 4;
   for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
@@ -1191,7 +1229,11 @@ vi_adam_kernel(int P, int E, int S, float* __restrict__ mu, float* __restrict__ 
   const int e = blockIdx.y;
   const int t = *step_count;
   const float b1 = 0.9f, b2 = 0.999f, aeps = 1e-8f;
-  const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
+  // the two powf() bias corrections cost more than an element update: once per block
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) { s_bc[0] = 1.f - powf(b1, (float)t); s_bc[1] = 1.f - powf(b2, (float)t); }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2 = s_bc[1];
   const float invS = 1.f / (float)S;
   float lacc = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
@@ -1224,8 +1266,12 @@ vi_adam_kernel(int P, int E, int S, float* __restrict__ mu, float* __restrict__ 
   if ((threadIdx.x & 31) == 0) atomicAdd(&loss_acc[e], lacc * invS);
 }
 
-__global__ void vi_loss_kernel(int E, int S, const float* loss_acc, const float* ll, float c, float* out) {
+// out row = (*slot - 1) of the buffer whose address sits in *out_slot when those are given (multi-
+// step calls: device cursors keep the launch arguments constant), else `out` directly.
+__global__ void vi_loss_kernel(int E, int S, const float* loss_acc, const float* ll, float c, float* out,
+                               float* const* out_slot, const int32_t* slot) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (out_slot) out = *out_slot + (size_t)(*slot - 1) * E;
   if (e < E) {
     float sll = 0.f;
     for (int s = 0; s < S; ++s) sll += ll[(size_t)s * E + e];
@@ -1733,11 +1779,11 @@ void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll,
 }
 
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,
-                      float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st) {
+                      float* eps_out, uint64_t seed, uint64_t stream_id, const int32_t* step_ptr, float* z, cudaStream_t st) {
   size_t total = ((size_t)S * E * P + 3) / 4;     // four elements per thread
   int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   BNF_PROF("vi_sample", st);
-  vi_sample_kernel<<<blocks, 256, 0, st>>>(P, E, S, mu, rho, eps_in, eps_out, seed, stream_id, z);
+  vi_sample_kernel<<<blocks, 256, 0, st>>>(P, E, S, mu, rho, eps_in, eps_out, seed, stream_id, step_ptr, z);
 }
 void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float* av, const float* z,
                     const float* eps, const float* g_ll, const int32_t* step_count, float c, float lr,
@@ -1747,9 +1793,18 @@ void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float
   BNF_PROF("vi_adam", st);
   vi_adam_kernel<<<dim3(bx, E), 256, 0, st>>>(P, E, S, mu, rho, am, av, z, eps, g_ll, step_count, c, lr, loss_acc);
 }
-void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out, cudaStream_t st) {
+void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out,
+                    float* const* out_slot, const int32_t* slot, cudaStream_t st) {
   BNF_PROF("vi_loss", st);
-  vi_loss_kernel<<<(E + 127) / 128, 128, 0, st>>>(E, S, loss_acc, ll, c, out);
+  vi_loss_kernel<<<(E + 127) / 128, 128, 0, st>>>(E, S, loss_acc, ll, c, out, out_slot, slot);
+}
+void launch_batch_window(int n_total, int B, int steps_per_epoch, int n_rows, uint64_t seed, int64_t first_member,
+                         const int32_t* step_count, int32_t* idx_win, cudaStream_t st) {
+  int bx = (B + 255) / 256;
+  if (bx > 64) bx = 64;
+  BNF_PROF("batch_window", st);
+  launch_k(batch_window_kernel, dim3(bx, n_rows), dim3(256), 0, st, n_total, B, steps_per_epoch, seed, first_member,
+           step_count, idx_win);
 }
 
 void launch_init_params(const DevModel& m, float lns_init, uint64_t seed, int64_t first_member,

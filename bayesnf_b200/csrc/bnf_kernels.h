@@ -44,6 +44,7 @@ void launch_wgrad_simt_t(const DevModel& m, int layer, const T* a_in, int Kin, i
                          float* grad, int n_net, int B, cudaStream_t st);
 
 void launch_tick(int32_t* step_count, int32_t* slot, cudaStream_t st);
+void launch_arm_loss(float** loss_slot, float* out_loss, int32_t* cursor, cudaStream_t st);
 void launch_map_adam(int P, float* params, float* am, float* av, const float* g_ll,
                      const int32_t* step_count, float c_ll, float prior_weight, float lr,
                      float* prior_out, int n_net, cudaStream_t st);
@@ -65,11 +66,17 @@ bool launch_head_fused_x3(const DevModel& m, const float* params, const float* d
 void launch_map_loss(int n_net, const float* ll, const float* prior, float c_ll, float prior_weight,
                      float* out, const int32_t* slot, cudaStream_t st);
 void launch_vi_sample(int P, int E, int S, const float* mu, const float* rho, const float* eps_in,
-                      float* eps_out, uint64_t seed, uint64_t stream_id, float* z, cudaStream_t st);
+                      float* eps_out, uint64_t seed, uint64_t stream_id, const int32_t* step_ptr, float* z,
+                      cudaStream_t st);
+// device-drawn minibatch windows: idx_win [n_rows, B] <- permutation of (member, epoch) at the
+// window given by the device-side count of completed steps
+void launch_batch_window(int n_total, int B, int steps_per_epoch, int n_rows, uint64_t seed, int64_t first_member,
+                         const int32_t* step_count, int32_t* idx_win, cudaStream_t st);
 void launch_vi_adam(int P, int E, int S, float* mu, float* rho, float* am, float* av, const float* z,
                     const float* eps, const float* g_ll, const int32_t* step_count, float c, float lr,
                     float* loss_acc, cudaStream_t st);
-void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out, cudaStream_t st);
+void launch_vi_loss(int E, int S, const float* loss_acc, const float* ll, float c, float* out,
+                    float* const* out_slot, const int32_t* slot, cudaStream_t st);
 void launch_init_params(const DevModel& m, float lns_init, uint64_t seed, int64_t first_member,
                         int n_net, float* params, cudaStream_t st);
 void launch_quantiles(const float* means, const float* scales, int M, int N, const double* q, int nq,

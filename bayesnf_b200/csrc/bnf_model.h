@@ -53,9 +53,10 @@ struct bnf_plan {
   int sm_count;
   // CUDA-graph replay of one full-batch MAP step (see bnf_map_steps); mutable
   // cache, so graph mode is single-threaded per plan.
+  // (slot 0: the MAP/MLE step, slot 1: the VI step)
   mutable void* graph_stream = nullptr;   // capture stream (nothing executes on it)
-  mutable void* graph_exec = nullptr;
-  mutable void* graph_key = nullptr;      // MapGraphKey of graph_exec
-  mutable void* last_key = nullptr;       // MapGraphKey of the previous full-batch call
-  mutable long long graph_launches = 0;   // kernel nodes per replay
+  mutable void* graph_exec[2] = {nullptr, nullptr};
+  mutable void* graph_key[2] = {nullptr, nullptr};    // StepGraphKey of graph_exec
+  mutable void* last_key[2] = {nullptr, nullptr};     // StepGraphKey of the previous replayable call
+  mutable long long graph_launches[2] = {0, 0};       // kernel nodes per replay
 };

@@ -194,6 +194,33 @@ class Engine:
         lr, prior_weight, _ptr(losses), _ptr(ws), ws.numel(), _stream()))
     return losses
 
+  def map_epochs(self, params, adam_m, adam_v, step_count, x, y, rows, n_total, n_epochs, lr,
+                 prior_weight, seed, first_member) -> torch.Tensor:
+    """Minibatch epochs with per-member permutations drawn on the device (bnf_map_epochs):
+    -> losses [n_epochs * (n_total // rows), M]."""
+    M = params.shape[0]
+    steps = n_epochs * (n_total // rows)
+    losses = torch.empty((steps, M), dtype=torch.float32, device=self.device)
+    ws = self.workspace(_lib.WS_MAP, M, rows)
+    _lib.check(_lib.lib.bnf_map_epochs(
+        self.spec.plan, self.prec, _ptr(params), _ptr(adam_m), _ptr(adam_v), _ptr(step_count), M,
+        _ptr(x), _ptr(y), rows, n_total, n_epochs, lr, prior_weight, C.c_uint64(seed), first_member,
+        _ptr(losses), _ptr(ws), ws.numel(), _stream()))
+    return losses
+
+  def vi_steps(self, mu, rho, adam_m, adam_v, step_count, n_mc, seed, device_id, x, y, rows, n_total,
+               n_steps, lr, kl_weight) -> torch.Tensor:
+    """n_steps VI steps, eps and the per-step shared sub-batch drawn on the device (bnf_vi_steps):
+    -> losses [n_steps, E] (not yet times kl_weight)."""
+    E = mu.shape[0]
+    losses = torch.empty((n_steps, E), dtype=torch.float32, device=self.device)
+    ws = self.workspace(_lib.WS_VI, E * n_mc, rows)
+    _lib.check(_lib.lib.bnf_vi_steps(
+        self.spec.plan, self.prec, _ptr(mu), _ptr(rho), _ptr(adam_m), _ptr(adam_v), _ptr(step_count),
+        E, n_mc, C.c_uint64(seed), device_id, _ptr(x), _ptr(y), rows, n_total, n_steps, lr, kl_weight,
+        _ptr(losses), _ptr(ws), ws.numel(), _stream()))
+    return losses
+
   def vi_step(self, mu, rho, adam_m, adam_v, step_count, n_mc, eps, seed, x, y, idx,
               rows, n_total, lr, kl_weight, out_loss):
     E = mu.shape[0]
@@ -259,11 +286,12 @@ def _to_device_data(features, target=None):
   return x, y
 
 
-def _per_member_permutations(n_members, n_rows, generator, device):
-  """Independent uniform permutation per member (permute_dataset, inference.py:35-39,
-  vmapped over members at :593-595)."""
-  keys = torch.rand((n_members, n_rows), generator=generator, device=device)
-  return keys.argsort(dim=1).to(torch.int32).contiguous()
+def device_permutation(seed: int, member: int, epoch: int, n_rows: int) -> np.ndarray:
+  """The row order the device draws for (seed; member, epoch) -- permute_dataset
+  (inference.py:35-39) as `bnf_map_epochs` evaluates it, computed on the host (tests / replay)."""
+  out = (C.c_int32 * n_rows)()
+  _lib.check(_lib.lib.bnf_debug_permutation(C.c_uint64(seed), member, epoch, n_rows, out))
+  return np.frombuffer(out, dtype=np.int32).copy()
 
 
 def fit_map(
@@ -308,7 +336,11 @@ def fit_map(
     raise ValueError('ensemble_size cannot be smaller than device_count.')
   steps_per_epoch = n_total // batch_size
   if steps_per_epoch < 1:
-    raise ValueError(f'{batch_size=} exceeds {n_total=}')
+    # the reference scans over zero steps here: initial parameters, NaN epoch losses
+    # (mean of an empty array, inference.py:583-614).  Same result, with a warning.
+    import warnings
+    warnings.warn(f'{batch_size=} exceeds the number of rows {n_total}: no training step is taken '
+                  '(as in the reference)', RuntimeWarning)
   seed = seed_to_int(seed)
   target_scale = float(np.nanstd(np.asarray(target, dtype=np.float64)))
   lns_init = math.log(target_scale / 2.0)
@@ -336,22 +368,26 @@ def fit_map(
     m = torch.zeros_like(p)
     v = torch.zeros_like(p)
     step_count = torch.zeros(1, dtype=torch.int32, device=eng.device)
-    gen = torch.Generator(device=eng.device)
-    gen.manual_seed((opt_seed + rank) & 0x7FFFFFFFFFFFFFFF)
-    if batch_size >= n_total and batch_indices is None:
+    if steps_per_epoch < 1:
+      epoch_losses = torch.full((num_epochs, members), float('nan'), device=eng.device)
+    elif batch_size >= n_total and batch_indices is None:
       losses = eng.map_steps(p, m, v, step_count, x, y, None, batch_size, n_total,
                              num_epochs, learning_rate, prior_weight)       # [epochs, M]
       epoch_losses = losses
+    elif batch_indices is None and jax_orders is None:
+      # the production path: per-member permutations, batch windows and every step on the device,
+      # one call (and one CUDA graph) for all epochs
+      ls = eng.map_epochs(p, m, v, step_count, x, y, batch_size, n_total, num_epochs, learning_rate,
+                          prior_weight, opt_seed, rank * members)
+      epoch_losses = ls.view(num_epochs, steps_per_epoch, members).mean(dim=1)   # :614
     else:
       per_epoch = []
       for ep in range(num_epochs):
         if batch_indices is not None:
           perm = torch.as_tensor(np.asarray(batch_indices[ep], dtype=np.int32)).to(eng.device)
           perm = perm.reshape(-1, n_total)[i * members:(i + 1) * members].contiguous()
-        elif jax_orders is not None:
-          perm = torch.as_tensor(jax_orders[ep]).to(eng.device).contiguous()
         else:
-          perm = _per_member_permutations(members, n_total, gen, eng.device)
+          perm = torch.as_tensor(jax_orders[ep]).to(eng.device).contiguous()
         ls = eng.map_steps(p, m, v, step_count, x, y, perm, batch_size, n_total,
                            steps_per_epoch, learning_rate, prior_weight)
         per_epoch.append(ls.mean(dim=0))                                   # :614
@@ -399,11 +435,13 @@ def fit_vi(
     init_params: tuple[np.ndarray, np.ndarray] | None = None,
     eps: np.ndarray | None = None,
     posterior_eps: np.ndarray | None = None,
+    batch_indices: np.ndarray | None = None,
 ) -> tuple[SurrogatePosterior, np.ndarray, tuple[np.ndarray, ...]]:
   """Fit an ensemble of mean-field surrogate posteriors (inference.py:336-373,
   :626-764).  ``num_epochs`` is the number of optimisation STEPS, as in the
   reference.  Test hooks: ``init_params`` = (mu, rho) [members, P]; ``eps``
-  [steps, S, members, P]; ``posterior_eps`` [num_samples, members, P].
+  [steps, S, members, P]; ``posterior_eps`` [num_samples, members, P]; ``batch_indices``
+  [steps, batch_size] shared sub-batch rows.
   Returns (surrogate, losses (1, members, steps) already times kl_weight,
   posterior samples tuple with leading (1, num_samples, members)).
   """
@@ -432,21 +470,28 @@ def fit_vi(
   am = torch.zeros((members, 2, P), dtype=torch.float32, device=eng.device)
   av = torch.zeros_like(am)
   step_count = torch.zeros(1, dtype=torch.int32, device=eng.device)
-  losses = torch.empty((num_epochs, members), dtype=torch.float32, device=eng.device)
-  gen = torch.Generator(device=eng.device)
-  gen.manual_seed((fit_seed + rank) & 0x7FFFFFFFFFFFFFFF)
-  for step in range(num_epochs):
-    idx = None
-    if batch_size is not None and batch_size < n_total:
-      # one shared random sub-batch per device per step (inference.py:704-709)
-      idx = torch.randperm(n_total, generator=gen, device=eng.device)[:batch_size]
-      idx = idx.to(torch.int32).contiguous()[None]
-    eps_t = None
-    if eps is not None:
-      eps_t = torch.as_tensor(np.asarray(eps[step], np.float32)).to(eng.device).contiguous()
-    eng.vi_step(mu, rho, am, av, step_count, sample_size_divergence, eps_t,
-                (fold_in(fit_seed, 16 + step) + rank) & 0xFFFFFFFFFFFFFFFF, x, y, idx, rows, n_total,
-                learning_rate, kl_weight, losses[step])
+  if eps is None and batch_indices is None:
+    # the production path: eps, the per-step shared sub-batch (inference.py:704-709) and every step
+    # on the device, one call (and one CUDA graph) for all steps
+    losses = eng.vi_steps(mu, rho, am, av, step_count, sample_size_divergence,
+                          (fit_seed + rank) & 0xFFFFFFFFFFFFFFFF, rank, x, y, rows, n_total, num_epochs,
+                          learning_rate, kl_weight)
+  else:
+    # test hooks: injected eps [steps, S, members, P] and / or sub-batch rows [steps, rows]
+    losses = torch.empty((num_epochs, members), dtype=torch.float32, device=eng.device)
+    for step in range(num_epochs):
+      idx = None
+      if batch_indices is not None:
+        idx = torch.as_tensor(np.asarray(batch_indices[step], np.int32)).to(eng.device).reshape(1, -1).contiguous()
+      elif rows < n_total:
+        idx = torch.as_tensor(device_permutation((fit_seed + rank) & 0xFFFFFFFFFFFFFFFF ^ 0x5649424154434855,
+                                                 rank, step, n_total)[:rows]).to(eng.device)[None].contiguous()
+      eps_t = None
+      if eps is not None:
+        eps_t = torch.as_tensor(np.asarray(eps[step], np.float32)).to(eng.device).contiguous()
+      eng.vi_step(mu, rho, am, av, step_count, sample_size_divergence, eps_t,
+                  (fit_seed + rank) & 0xFFFFFFFFFFFFFFFF, x, y, idx, rows, n_total,
+                  learning_rate, kl_weight, losses[step])
   pe = None
   if posterior_eps is not None:
     pe = torch.as_tensor(np.asarray(posterior_eps, np.float32)).to(eng.device).contiguous()

@@ -50,6 +50,11 @@ WORKLOADS = {
                             periods=[24, 168], harmonics=[4, 4], objective='vi', mc_samples=5),
     'air_quality_map_e8': dict(width=512, depth=4, members_per_gpu=8, sites=64, times=512, batch=None,
                                periods=[24, 168], harmonics=[4, 4], objective='map'),
+    # BASELINE.json configs[3] per-GPU shard: air_quality MLE (prior_weight 0), ZINB observation
+    # model, W512 L4, 32 members / 4 GPUs, batch 38 096 (scripts/evaluate.py:199-204) out of
+    # 76 224 rows (2 steps per epoch; per-member permutations drawn on the device every epoch)
+    'air_quality_mle_zinb_e8': dict(width=512, depth=4, members_per_gpu=8, sites=64, times=1191, batch=38096,
+                                    periods=[24, 168], harmonics=[4, 4], objective='mle', likelihood='ZINB'),
 }
 
 
@@ -65,6 +70,11 @@ def synth(wl, seed=20240925):
   for p in wl['periods']:
     y += rng.normal() * np.sin(2 * np.pi * t / p + rng.uniform(0, 6.28))
   y += 0.7 * la - 0.4 * lo * la + rng.normal(scale=0.5, size=T * S)
+  if wl.get('likelihood', 'NORMAL') != 'NORMAL':
+    # counts: negative-binomial draws around exp(field), ~30 % structural zeros
+    mean = np.exp(0.5 * y + 1.0)
+    y = rng.negative_binomial(2.0, 2.0 / (2.0 + mean)).astype(np.float64)
+    y[rng.random(T * S) < 0.3] = 0.0
   x = np.stack([t, la, lo], 1)
   margs = dict(width=wl['width'], depth=wl['depth'], input_scales=np.array([T - 1.0, 1.0, 1.0]),
                num_seasonal_harmonics=np.array(wl['harmonics']),
@@ -170,8 +180,10 @@ def peaks():
   return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
 
 
-def _oracle_stepper(x, y, margs):
-  """One oracle MAP step (value_and_grad + Adam) of ONE member on the full batch."""
+def _oracle_stepper(x, y, margs, wl=None):
+  """One oracle MAP/MLE step (value_and_grad + Adam) of ONE member on one batch."""
+  lik = (wl or {}).get('likelihood', 'NORMAL')
+  pw = 0.0 if (wl or {}).get('objective') == 'mle' else 1.0
   import torch
   from oracle import bnf_oracle as O
   om = O.OracleModel(**margs)
@@ -185,7 +197,7 @@ def _oracle_stepper(x, y, margs):
 
   def step():
     state['t'] += 1
-    loss, gr = O.map_loss_and_grad(om, state['p'], xt, yt, n_total, 1.0, 'NORMAL')
+    loss, gr = O.map_loss_and_grad(om, state['p'], xt, yt, n_total, pw, lik)
     state['p'], state['m'], state['v'] = O.adam_update(state['p'], gr, state['m'], state['v'], state['t'], 0.005)
   return step, B
 
@@ -208,9 +220,9 @@ def _best_thread_count(step):
   return best
 
 
-def cpu_oracle_rate(x, y, margs, budget_s):
+def cpu_oracle_rate(x, y, margs, budget_s, wl=None):
   """The CPU baseline: oracle MAP steps for ~budget_s seconds.  Returns samples/s."""
-  step, B = _oracle_stepper(x, y, margs)
+  step, B = _oracle_stepper(x, y, margs, wl)
   threads = _best_thread_count(step)
   steps, t0 = 0, time.perf_counter()
   while True:
@@ -231,7 +243,7 @@ def run_reference(args, wl, x, y, margs):
   if rank != 0:
     return
   import torch
-  step, B = _oracle_stepper(x, y, margs)
+  step, B = _oracle_stepper(x, y, margs, wl)
   _best_thread_count(step)                   # torchrun exports OMP_NUM_THREADS=1: undo it
   for _ in range(args.warmup):
     step()
@@ -294,7 +306,9 @@ def main():
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
 
-  spec = models.ModelSpec(**margs, observation_model='NORMAL')
+  lik = wl.get('likelihood', 'NORMAL')
+  pw = 0.0 if wl['objective'] == 'mle' else 1.0            # MLE = MAP without the prior (spatiotemporal.py:544-551)
+  spec = models.ModelSpec(**margs, observation_model=lik)
   eng = inference.Engine(spec, args.precision)
   E = wl['members_per_gpu']
   n_total = len(y)
@@ -305,35 +319,27 @@ def main():
   S = wl.get('mc_samples', 1)
   p = eng.init_params(0.0 if is_vi else lns, 1234, rank * E, E)
   sc = torch.zeros(1, dtype=torch.int32, device=dev)
-  idx = None
-  gen = torch.Generator(device=dev).manual_seed(rank)
   if is_vi:
     rho = torch.full_like(p, math.log(math.expm1(0.3)))
     m = torch.zeros((E, 2, spec.num_params), dtype=torch.float32, device=dev)
     v = torch.zeros_like(m)
-    if B < n_total:
-      idx = torch.randperm(n_total, generator=gen, device=dev)[:B].to(torch.int32).contiguous()[None]
   else:
     m, v = torch.zeros_like(p), torch.zeros_like(p)
-    if B < n_total:
-      idx = inference._per_member_permutations(E, n_total, gen, dev)[:, :B].contiguous()
-  vi_losses = torch.zeros((1, E), dtype=torch.float32, device=dev)
-  step_id = [0]
 
   def run(k, xx=None, yy=None):
+    """k training steps through the Engine (one C call; all draws on the device)."""
     xx = xd if xx is None else xx
     yy = yd if yy is None else yy
-    if is_vi:     # one tfp.vi step per call: S reparameterised draws per member (device Philox)
-      out = []
-      for _ in range(k):
-        step_id[0] += 1
-        eng.vi_step(p, rho, m, v, sc, S, None, 977 * step_id[0] + rank, xx, yy, idx, B, n_total, 0.01, 0.1,
-                    vi_losses[0])
-        out.append(vi_losses.clone())
-      return torch.cat(out)
-    if idx is None:
-      return eng.map_steps(p, m, v, sc, xx, yy, None, B, n_total, k, 0.005, 1.0)
-    return torch.cat([eng.map_steps(p, m, v, sc, xx, yy, idx, B, n_total, 1, 0.005, 1.0) for _ in range(k)])
+    if is_vi:     # tfp.vi steps: S reparameterised draws per member and a FRESH shared sub-batch every step
+      return eng.vi_steps(p, rho, m, v, sc, S, 977 + rank, rank, xx, yy, B, n_total, k, 0.01, 0.1)
+    if B >= n_total:
+      return eng.map_steps(p, m, v, sc, xx, yy, None, B, n_total, k, 0.005, pw)
+    # minibatches: per-member permutations and batch windows drawn on the device; k steps = k windows
+    # (bnf_map_epochs counts in epochs: ask for enough of them and keep the call at k steps when k
+    # is a multiple of the steps per epoch, else round up)
+    spe = n_total // B
+    assert k % spe == 0, f'--steps must be a multiple of the {spe} steps per epoch of this workload'
+    return eng.map_epochs(p, m, v, sc, xx, yy, B, n_total, k // spe, 0.005, pw, 4321, rank * E)
 
   def barrier():
     if world > 1:
@@ -476,7 +482,7 @@ def main():
   # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    val, timed, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget)
+    val, timed, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget, wl)
     cpu = {'value': val, 'unit': 'samples/s', 'cores': cores, 'cores_available': os.cpu_count(), 'kind': 'port',
            'sample': f'1 member x {margs["init_x"][0]} rows x {timed} MAP steps (torch-CPU oracle, f32)'}
 
@@ -495,7 +501,7 @@ def main():
         'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
                    'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
                    'mc_samples': S,
-                   'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'],
+                   'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'], 'observation_model': lik,
                    'parallelism': f'members sharded x{world}, no collective in training',
                    'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
                          if act_bytes > 126 * 2**20 else

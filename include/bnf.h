@@ -165,6 +165,21 @@ int bnf_map_steps(const bnf_plan_t* plan, int32_t precision, float* params,
                   float prior_weight, float* out_loss, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* `n_epochs` epochs of `_one_epoch` (inference.py:583-614) with the minibatch order drawn ON THE
+ * DEVICE: every epoch each member walks a fresh permutation of the n_rows_total rows
+ * (permute_dataset, :35-39, vmapped over members :593-597) in windows of batch_rows rows, the
+ * ragged tail dropped (:583-589) -- n_rows_total / batch_rows steps per epoch.  The permutation of
+ * (seed; first_member + j, epoch) is a keyed bijection evaluated per batch window (no sort, no
+ * index array; bnf_debug_permutation evaluates the same function on the host), the epoch /
+ * window follow from the device-side step_count, so the whole call replays one CUDA graph.
+ * out_loss [n_epochs * steps_per_epoch, n_networks]: loss before each update (the epoch loss of
+ * :614 is the mean over an epoch's rows).                                              */
+int bnf_map_epochs(const bnf_plan_t* plan, int32_t precision, float* params, float* adam_m,
+                   float* adam_v, int32_t* step_count, int32_t n_networks, const float* x,
+                   const float* y, int32_t batch_rows, int32_t n_rows_total, int32_t n_epochs,
+                   float learning_rate, float prior_weight, uint64_t seed, int64_t first_member,
+                   float* out_loss, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One step of tfp.vi.fit_surrogate_posterior_stateless as driven by
  * ensemble_vi (inference.py:687-739): q = prod N(mu, 1e-4 + softplus(rho)),
  * z_s = mu + sigma*eps_s, loss_e = mean_s[log q(z_s) - logprior(z_s)
@@ -179,6 +194,18 @@ int bnf_vi_step(const bnf_plan_t* plan, int32_t precision, float* mu, float* rho
                 int32_t batch_rows, int32_t n_rows_total, float learning_rate,
                 float kl_weight, float* out_loss, void* workspace,
                 size_t workspace_bytes, void* stream);
+
+/* `n_steps` such steps with everything drawn on the device (the production path; bnf_vi_step
+ * with injected eps / idx is the test hook): eps from the Philox stream of (seed, step count);
+ * when batch_rows < n_rows_total one shared random sub-batch per step = the first batch_rows
+ * entries of the permutation keyed by (seed; device_id, step count) (inference.py:704-709).
+ * The step sequence replays one CUDA graph.  out_loss [n_steps, n_members].               */
+int bnf_vi_steps(const bnf_plan_t* plan, int32_t precision, float* mu, float* rho,
+                 float* adam_m, float* adam_v, int32_t* step_count, int32_t n_members,
+                 int32_t n_mc_samples, uint64_t seed, int64_t device_id, const float* x,
+                 const float* y, int32_t batch_rows, int32_t n_rows_total, int32_t n_steps,
+                 float learning_rate, float kl_weight, float* out_loss, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* surrogate.sample(num_samples) (inference.py:741-753): out[s,e,:] = mu_e +
  * (1e-4+softplus(rho_e)) * eps[s,e,:]; eps NULL -> device Philox from seed.    */
@@ -227,6 +254,9 @@ int bnf_nb_mixture_quantiles(const float* loc, const float* shape_raw, const flo
  * A, B are bf16.  Used by tests/test_gpu_tc.py against a plain f32 matmul.      */
 int bnf_debug_gemm(int32_t mn_major, const void* a, const void* b, float* c,
                    int32_t n_networks, int32_t m, int32_t n, int32_t k, void* stream);
+/* The device's permute_dataset for (seed; member, epoch), evaluated on the HOST: out[i] = row at
+ * position i (a permutation of 0..n-1).                                                  */
+int bnf_debug_permutation(uint64_t seed, int64_t member, int32_t epoch, int32_t n, int32_t* out);
 /* Philox4x32-10 block function of the device RNG (init / VI draws / minibatch permutations),
  * evaluated on the HOST: counter4 -> out4 under key2.  Known-answer tested against the
  * Random123 vectors without a GPU.                                              */

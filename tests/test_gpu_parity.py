@@ -527,3 +527,190 @@ def test_full_size_configs1_against_oracle(cuda, prec):
     # other way (|delta| up to 2*lr per step), hence a quantile for the bulk and a hard cap
     assert float(np.quantile(d, 0.999)) <= p_tol, (prec, j, float(np.quantile(d, 0.999)))
     assert float(d.max()) <= 2 * lr * steps + 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# device-side minibatch machinery
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('prec', PARITY_MODES)
+def test_device_shuffled_epochs_match_injected_orders(cuda, prec):
+  """fit_map with batch_size < N draws the per-member permutations, the batch windows and every
+  step on the device (bnf_map_epochs, one CUDA graph); replaying the SAME orders -- computed on
+  the host by the same keyed permutation -- through the injected-index path (which
+  test_map_steps_fp32 pins to the oracle) gives the same losses and parameters."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  n, B, epochs, E = 200, 64, 3, 3
+  x, y = _data(cfg, n)
+  om = O.OracleModel(**cfg)
+  P0 = _random_params(om, E, y, seed=13).numpy()
+  seed = 1234
+  kw = dict(num_particles=E, learning_rate=0.01, num_epochs=epochs, batch_size=B, precision=prec, init_params=P0)
+  p_dev, l_dev = inference.fit_map(x, y, seed, 'NORMAL', cfg, **kw)
+  opt_seed = inference.fold_in(inference.seed_to_int(seed), 0x1002)
+  orders = np.stack([[inference.device_permutation(opt_seed, j, ep, n) for j in range(E)] for ep in range(epochs)])
+  p_inj, l_inj = inference.fit_map(x, y, seed, 'NORMAL', cfg, batch_indices=orders, **kw)
+  assert l_dev.shape == (1, E, epochs) and np.isfinite(l_dev).all()
+  np.testing.assert_allclose(l_dev, l_inj, rtol=2e-5)
+  spec = models.ModelSpec(**cfg)
+  assert float(np.abs(spec.flatten(p_dev) - spec.flatten(p_inj)).max()) <= 2e-4
+  # the orders are per member and per epoch, and the ragged tail (200 - 3*64 rows) is dropped
+  assert not np.array_equal(orders[0, 0], orders[0, 1]) and not np.array_equal(orders[0, 0], orders[1, 0])
+
+
+def test_vi_five_steps_with_subbatch_against_oracle(cuda):
+  """Five VI steps (tfp.vi.fit_surrogate_posterior_stateless as driven by ensemble_vi,
+  inference.py:687-739) with a fresh shared sub-batch per step and injected eps against the f64
+  oracle's autograd + optax.adam on (mu, rho): losses to 2e-5, variational parameters to 1e-4
+  (99.5 % quantile; they move by up to 5*lr = 0.05)."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  n, B, S, E, steps = 200, 80, 3, 2, 5
+  x, y = _data(cfg, n)
+  om64 = O.OracleModel(**cfg, dtype=torch.float64)
+  om = O.OracleModel(**cfg)
+  spec = models.ModelSpec(**cfg)
+  P = spec.num_params
+  g = torch.Generator().manual_seed(5)
+  mu = _random_params(om, E, y, seed=9)
+  mu[:, 0] = 0.0
+  rho = torch.full((E, P), O.SOFTPLUS_INV_0P3) + 0.05 * torch.randn(E, P, generator=g)
+  eps = torch.randn(steps, S, E, P, generator=g)
+  rng = np.random.default_rng(3)
+  rows = np.stack([rng.permutation(n)[:B] for _ in range(steps)]).astype(np.int32)
+  kl, lr = 0.1, 0.01
+  for prec in PARITY_MODES:
+    sur, losses, _ = inference.fit_vi(
+        x, y, 0, 'NORMAL', cfg, ensemble_size=E, learning_rate=lr, num_epochs=steps, sample_size_divergence=S,
+        sample_size_posterior=2, kl_weight=kl, batch_size=B, precision=prec, init_params=(mu.numpy(), rho.numpy()),
+        eps=eps.numpy(), posterior_eps=np.zeros((2, E, P), np.float32), batch_indices=rows)
+    xd, yd = inference._to_device_data(x, y)
+    mu1, rho1 = spec.flatten(sur.loc)[0], spec.flatten(sur.inv_softplus_scale)[0]
+    for e in range(E):
+      m_, r_ = mu[e].double(), rho[e].double()
+      am, av = torch.zeros(2 * P, dtype=torch.float64), torch.zeros(2 * P, dtype=torch.float64)
+      for t in range(steps):
+        sel = torch.tensor(rows[t].astype(np.int64))
+        loss, gmu, grho = O.vi_loss_and_grad(om64, m_, r_, eps[t, :, e].double(), xd.cpu().double()[sel],
+                                             yd.cpu().double()[sel], n, kl, 'NORMAL')
+        assert abs(losses[0, e, t] - float(loss) * kl) <= 2e-5 * abs(float(loss) * kl), (prec, e, t)
+        pq, am, av = O.adam_update(torch.cat([m_, r_]), torch.cat([gmu, grho]), am, av, t + 1, lr)
+        m_, r_ = pq[:P], pq[P:]
+      # entries whose gradient is summation noise may step the other way under Adam's normalisation
+      dm = (torch.tensor(mu1[e]).double() - m_).abs()
+      dr = (torch.tensor(rho1[e]).double() - r_).abs()
+      assert float(torch.quantile(dm, 0.995)) <= 1e-4 and float(dm.max()) <= 2 * steps * lr
+      assert float(torch.quantile(dr, 0.995)) <= 1e-4 and float(dr.max()) <= 2 * steps * lr
+
+
+def test_vi_device_steps_graph_equals_direct_launches(cuda, monkeypatch):
+  """bnf_vi_steps (eps + per-step sub-batch drawn on the device, one CUDA graph replayed) is
+  deterministic in its seed and equals the same call issued as direct launches, and -- split
+  into single-step calls -- the same sequence (device-side step counters)."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  n, B, S, E, steps = 200, 96, 4, 3, 6
+  x, y = _data(cfg, n)
+  spec = models.ModelSpec(**cfg)
+  eng = inference.Engine(spec, 'fp32')
+  xd, yd = inference._to_device_data(x, y)
+
+  def run(chunks):
+    mu = eng.init_params(0.0, 5, 0, E)
+    rho = torch.full_like(mu, O.SOFTPLUS_INV_0P3)
+    am = torch.zeros((E, 2, spec.num_params), dtype=torch.float32, device=cuda)
+    av, sc = torch.zeros_like(am), torch.zeros(1, dtype=torch.int32, device=cuda)
+    ls = torch.cat([eng.vi_steps(mu, rho, am, av, sc, S, 77, 0, xd, yd, B, n, k, 0.01, 0.1) for k in chunks])
+    torch.cuda.synchronize()
+    assert int(sc[0]) == steps
+    return ls.cpu().numpy(), mu.cpu().numpy(), rho.cpu().numpy()
+  monkeypatch.delenv('BNF_NO_GRAPH', raising=False)
+  a = run([steps])
+  b = run([steps])
+  monkeypatch.setenv('BNF_NO_GRAPH', '1')
+  c = run([steps])
+  d = run([1] * steps)
+  assert np.isfinite(a[0]).all() and a[0].shape == (steps, E)
+  for other in (b, c, d):
+    np.testing.assert_allclose(a[0], other[0], rtol=2e-5)          # f32 atomics reorder sums
+    assert float(np.abs(a[1] - other[1]).max()) <= 2e-4 and float(np.abs(a[2] - other[2]).max()) <= 2e-4
+  assert a[0][-1].mean() < a[0][0].mean()                          # the ELBO loss goes down
+
+
+def test_device_eps_are_independent_draws(cuda):
+  """The reparameterisation noise / posterior samples drawn on the device are iid N(0,1): every
+  element owns its Philox words, so neighbouring coordinates share nothing
+  (corr(eps_i^2, eps_{i+1}^2) = 0; a shared uniform would give ~ -0.12)."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['chickenpox']
+  spec = models.ModelSpec(**cfg)
+  eng = inference.Engine(spec, 'fp32')
+  E, n_s = 2, 8
+  mu = torch.zeros((E, spec.num_params), dtype=torch.float32, device=cuda)
+  rho = torch.full_like(mu, math.log(math.expm1(1.0 - 1e-4)))       # sigma = 1
+  z = eng.vi_sample(mu, rho, n_s, 123).reshape(-1).double().cpu()
+  assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+  assert abs(float((z ** 4).mean()) - 3.0) < 0.05
+  for lag in (1, 2, 3, 4):
+    a, b = z[:-lag], z[lag:]
+    assert abs(float(torch.corrcoef(torch.stack([a, b]))[0, 1])) < 5e-3, lag
+    assert abs(float(torch.corrcoef(torch.stack([a * a, b * b]))[0, 1])) < 5e-3, lag
+  z2 = eng.vi_sample(mu, rho, n_s, 124).reshape(-1).double().cpu()
+  assert abs(float(torch.corrcoef(torch.stack([z, z2]))[0, 1])) < 5e-3
+
+
+def test_num_splits_are_independent_sequential_fits(cuda):
+  """fit_map(num_splits=2) (inference.py:432-457): particles // splits members are trained per
+  split, one after the other, and concatenated on axis 1 -- equal to two separate fits of the
+  two halves of the injected initial parameters."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  n = 200
+  x, y = _data(cfg, n)
+  om = O.OracleModel(**cfg)
+  P0 = _random_params(om, 4, y, seed=31).numpy()
+  kw = dict(learning_rate=0.01, num_epochs=4, precision='fp32')
+  p_all, l_all = inference.fit_map(x, y, 3, 'NORMAL', cfg, num_particles=4, num_splits=2, init_params=P0, **kw)
+  spec = models.ModelSpec(**cfg)
+  flat = spec.flatten(p_all)
+  assert flat.shape == (1, 4, spec.num_params) and l_all.shape == (1, 4, 4)
+  for i in range(2):
+    p_i, l_i = inference.fit_map(x, y, 3, 'NORMAL', cfg, num_particles=2, init_params=P0[2 * i:2 * i + 2], **kw)
+    np.testing.assert_allclose(l_all[0, 2 * i:2 * i + 2], l_i[0], rtol=2e-5)
+    assert float(np.abs(flat[0, 2 * i:2 * i + 2] - spec.flatten(p_i)[0]).max()) <= 2e-4
+    # and each half against the oracle's own fit
+    xd, yd = inference._to_device_data(x, y)
+    for j in range(2):
+      pj, lj = O.fit_map_member(om, torch.tensor(P0[2 * i + j]), xd.cpu(), yd.cpu(), lambda ep: torch.arange(n), 4, n,
+                                0.01, 1.0, 'NORMAL')
+      np.testing.assert_allclose(l_all[0, 2 * i + j], lj.numpy(), rtol=2e-5)
+  # floor division of particles over splits (inference.py:445): 5 // 2 = 2 per split
+  p5, l5 = inference.fit_map(x, y, 3, 'NORMAL', cfg, num_particles=5, num_splits=2, **kw)
+  assert l5.shape == (1, 4, 4)
+  # different splits get different seeds (fold_in(seed, i), :436-437): the members differ
+  f5 = spec.flatten(p5)[0]
+  assert not np.allclose(f5[0], f5[2])
+
+
+def test_fit_vi_default_init_is_make_vi_init(cuda):
+  """make_vi_init (inference.py:203-231): surrogate means = 0 for every non-2-D leaf (including
+  log_noise_scale -- NOT log(std/2)), TruncatedNormal kernels; inverse-softplus scales =
+  softplus^-1(0.3) everywhere.  Checked through fit_vi with a learning rate of 0."""
+  from bayesnf_b200 import inference, models
+  cfg = _cfgs()['small']
+  x, y = _data(cfg, 200)
+  sur, losses, samples = inference.fit_vi(x, y, 11, 'NORMAL', cfg, ensemble_size=3, learning_rate=0.0, num_epochs=1,
+                                          sample_size_divergence=2, sample_size_posterior=2, kl_weight=0.1,
+                                          precision='fp32')
+  spec = models.ModelSpec(**cfg)
+  for r in sur.inv_softplus_scale:
+    np.testing.assert_allclose(r, O.SOFTPLUS_INV_0P3, rtol=1e-6)
+  for sd in sur.stddev():
+    np.testing.assert_allclose(sd, 0.3 + 1e-4, rtol=1e-5)
+  assert np.all(sur.loc[0] == 0) and np.all(sur.loc[1] == 0) and np.all(sur.loc[2] == 0)
+  for name, leaf in zip(spec.leaf_names, sur.loc[3:]):
+    if name.endswith('kernel'):
+      assert np.abs(leaf).max() <= 2.0 and leaf.std() > 0.5
+    else:
+      assert np.all(leaf == 0), name
+  assert losses.shape == (1, 3, 1) and np.isfinite(losses).all()

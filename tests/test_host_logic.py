@@ -187,3 +187,52 @@ def test_flax_variables_round_trip():
   for a, b in zip(deep.from_flax_variables(h2, v2), p2):
     np.testing.assert_array_equal(a, b)
 
+
+
+def test_philox_known_answers():
+  """The device RNG's block function against the Random123 known-answer vectors
+  (philox4x32-10), evaluated on the host through bnf_debug_philox."""
+  import ctypes as C
+
+  def ph(c, k):
+    ca, ka, o = (C.c_uint32 * 4)(*c), (C.c_uint32 * 2)(*k), (C.c_uint32 * 4)()
+    _lib.lib.bnf_debug_philox(ca, ka, o)
+    return list(o)
+  assert ph([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+  assert ph([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+  assert ph([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+      [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_device_permutation_is_a_uniform_bijection():
+  """permute_dataset as the device evaluates it (keyed Feistel bijection + cycle walking,
+  bnf_map_epochs): a permutation for every n incl. edge cases, different per member and epoch,
+  first element uniform over keys (chi-square), no excess of consecutive neighbours."""
+  for n in (1, 2, 3, 5, 100, 1023, 1024, 1025, 10440, 65536, 100003):
+    p = inference.device_permutation(5, 0, 0, n)
+    assert np.array_equal(np.sort(p), np.arange(n)), n
+  a, b, c = (inference.device_permutation(5, 0, 0, 10440), inference.device_permutation(5, 1, 0, 10440),
+             inference.device_permutation(5, 0, 1, 10440))
+  assert (a == b).mean() < 0.01 and (a == c).mean() < 0.01 and (a == np.arange(10440)).mean() < 0.01
+  np.testing.assert_array_equal(a, inference.device_permutation(5, 0, 0, 10440))     # deterministic
+  n, keys = 64, 6400
+  first, adjacent = np.zeros(n), 0
+  for e in range(keys):
+    p = inference.device_permutation(9, 3, e, n)
+    first[p[0]] += 1
+    adjacent += int((np.abs(np.diff(p)) == 1).sum())
+  chi2 = float(((first - keys / n) ** 2 / (keys / n)).sum())
+  assert chi2 < 110.0, chi2                       # df = 63: P(chi2 > 110) ~ 2e-4
+  frac = adjacent / (keys * (n - 1))
+  assert abs(frac - 2.0 / n) < 0.15 * 2.0 / n, frac
+
+
+def test_default_precision_is_the_parity_tensor_core_mode():
+  assert inference.get_default_precision() in ('bf16x3',) or 'BAYESNF_B200_PRECISION' in os.environ
+  spec = models.ModelSpec(**CONFIGS['chickenpox'])
+  assert _lib.lib.bnf_precision_supported(spec.plan, _lib.PREC_BF16X3) == 0
+  odd = dict(CONFIGS['chickenpox'])
+  odd['width'] = 40
+  spec = models.ModelSpec(**odd)
+  assert _lib.lib.bnf_precision_supported(spec.plan, _lib.PREC_BF16X3) != 0     # SIMT f32 covers it
+  assert _lib.lib.bnf_precision_supported(spec.plan, _lib.PREC_FP32) == 0
