@@ -889,7 +889,14 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
         const float dh = rb * head_c[k];
         g_ko[k] += rb * hr[k];
         float diff;
-        const float da = act_grad_sel<FAST>(zz, w, &diff);
+        float da;
+        if constexpr (X3) {
+          // the activation math of the bf16x3 tensor-core epilogues (one ex2 + one rcp, <= 3e-7 abs.)
+          float hh;
+          da = act_grad_x3(zz, w, &diff, &hh);
+        } else {
+          da = act_grad_sel<FAST>(zz, w, &diff);
+        }
         const float dz = dh * da;
         g_w += dh * diff;
         g_s += dz * zz;

@@ -137,9 +137,23 @@ NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, ', ', 0, 0, '), 'tc_gemm_dgrad': (', 0, 
                'tc_fwd_head': (', 3, 7, ',), 'tc_dgrad0_enc': (', 0, 6, ',)}
 
 
-def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head):
+def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head, precision='bf16'):
   """Algorithmic FLOPs and HBM bytes PER STEP of every kernel class:
-  bf16 activations read/written once per producer/consumer, weights ignored (L2-resident)."""
+  activations read/written once per producer/consumer, weights ignored (L2-resident).
+  bf16: 2 bytes per activation element.  bf16x3: GEMM operands (feat, h, dU) are three bf16 planes
+  = 6 bytes, pre-activations z are f32 = 4 bytes; the FLOPs are the ALGORITHMIC f32 ones (the
+  tensor cores execute six bf16 products per f32 product)."""
+  if precision == 'bf16x3':
+    a6, a4, f6 = 6 * rows * W, 4 * rows * W, 6 * rows * Fp
+    return {
+        'tc_gemm_fwd_x3': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=f6 + L * (a4 + a6) + (L - 1) * a6),
+        'head_fused': dict(flops=2.0 * rows * W, bytes=a6 + a4 + a6),                  # h, z in, dU out
+        'tc_gemm_dgrad_x3': dict(flops=2.0 * rows * (L - 1) * W * W, bytes=(L - 1) * (a6 + a4 + a6)),
+        'tc_dgrad0_enc': dict(flops=2.0 * rows * F * W, bytes=a6),
+        'tc_gemm_wgrad': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=f6 + a6 + (L - 1) * 2 * a6),
+        'map_update': dict(flops=0.0, bytes=34.0 * P_total),                           # + three bf16 planes restaged
+        'encode': dict(flops=0.0, bytes=float(f6)),
+    }
   a = 2 * rows * W            # bytes of one bf16 activation tensor [rows, W]
   nf = L - 1 if fused_head else L          # launches of the plain forward kernel
   return {
@@ -267,49 +281,20 @@ def run_reference(args, wl, x, y, margs):
   }))
 
 
-def main():
-  ap = argparse.ArgumentParser()
-  ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=200)
-  ap.add_argument('--warmup', type=int, default=20)
-  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-  ap.add_argument('--workload', default='chickenpox_map_e8', choices=sorted(WORKLOADS))
-  ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'tf32x3', 'fp32', 'bf16_simt'],
-                  help="bf16: single-pass tcgen05 (BASELINE configs name bf16); bf16x3 (alias tf32x3): tcgen05 at "
-                       "the 1e-5 parity tolerance (split operands); fp32: SIMT")
-  ap.add_argument('--repeats', type=int, default=0, help='timed K-step blocks (0: >= 10 and >= 100 ms in total)')
-  ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-baseline work')
-  ap.add_argument('--no-cpu-baseline', action='store_true')
-  ap.add_argument('--no-profile', action='store_true')
-  args = ap.parse_args()
-  if args.precision == 'tf32x3':
-    args.precision = 'bf16x3'
-  wl = WORKLOADS[args.workload]
-  x, y, margs = synth(wl)
-  if args.impl == 'reference':
-    run_reference(args, wl, x, y, margs)
-    return
-
+def run_workload(args, workload, precision, steps, warmup, env, do_e2e=True, do_profile=True, cpu_baseline=False,
+                 repeats=0, min_window_ms=100.0, keep=None):
+  """Times blocks of `steps` training steps of one workload in one arithmetic mode on this rank's
+  GPU and returns the record rank 0 prints (None on the other ranks)."""
   import torch
   import torch.distributed as dist
   from bayesnf_b200 import _lib, inference, models
-
-  rank = int(os.environ.get('RANK', '0'))
-  world = int(os.environ.get('WORLD_SIZE', '1'))
-  local = int(os.environ.get('LOCAL_RANK', '0'))
-  if world > 1:
-    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-      os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the single JSON line
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-  torch.cuda.set_device(local)
-  dev = torch.device('cuda', local)
-
+  rank, world, local, dev = env['rank'], env['world'], env['local'], env['dev']
+  wl = WORKLOADS[workload]
+  x, y, margs = synth(wl)
   lik = wl.get('likelihood', 'NORMAL')
   pw = 0.0 if wl['objective'] == 'mle' else 1.0            # MLE = MAP without the prior (spatiotemporal.py:544-551)
   spec = models.ModelSpec(**margs, observation_model=lik)
-  eng = inference.Engine(spec, args.precision)
+  eng = inference.Engine(spec, precision)
   E = wl['members_per_gpu']
   n_total = len(y)
   B = wl['batch'] or n_total
@@ -334,9 +319,7 @@ def main():
       return eng.vi_steps(p, rho, m, v, sc, S, 977 + rank, rank, xx, yy, B, n_total, k, 0.01, 0.1)
     if B >= n_total:
       return eng.map_steps(p, m, v, sc, xx, yy, None, B, n_total, k, 0.005, pw)
-    # minibatches: per-member permutations and batch windows drawn on the device; k steps = k windows
-    # (bnf_map_epochs counts in epochs: ask for enough of them and keep the call at k steps when k
-    # is a multiple of the steps per epoch, else round up)
+    # minibatches: per-member permutations and batch windows drawn on the device, k steps = k windows
     spe = n_total // B
     assert k % spe == 0, f'--steps must be a multiple of the {spe} steps per epoch of this workload'
     return eng.map_epochs(p, m, v, sc, xx, yy, B, n_total, k // spe, 0.005, pw, 4321, rank * E)
@@ -350,18 +333,19 @@ def main():
   # Warm up with W steps AND one block of exactly the timed shape (K steps: graph capture,
   # workspace and loss-buffer allocation all happen here), then time R blocks of EXACTLY K steps,
   # each bracketed by barrier + synchronize on both sides and by CUDA events on the launching
-  # stream; per block the MAX over ranks, over blocks the MEDIAN.  R >= 10 and R*K steps >= 100 ms,
-  # so one host hiccup on one rank cannot set the number.
-  run(max(3, args.warmup))
-  run(args.steps)
+  # stream; per block the MAX over ranks, over blocks the MEDIAN.  R >= 10 and R*K steps >= 100 ms
+  # for the headline, so one host hiccup on one rank cannot set the number.
+  spe_w = 1 if (is_vi or B >= n_total) else n_total // B
+  run(-(-max(3, warmup) // spe_w) * spe_w)          # warm-up steps, rounded up to whole epochs for minibatch workloads
+  run(steps)
   torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  run(args.steps)
+  run(steps)
   e1.record()
   torch.cuda.synchronize()
   est_ms = max(e0.elapsed_time(e1), 1e-3)
-  repeats = args.repeats or int(min(200, max(10, math.ceil(100.0 / est_ms))))
+  repeats = repeats or int(min(200, max(10 if min_window_ms >= 100.0 else 3, math.ceil(min_window_ms / est_ms))))
   rep = torch.tensor([repeats], dtype=torch.int64, device=dev)
   if world > 1:
     dist.all_reduce(rep, op=dist.ReduceOp.MAX)
@@ -374,7 +358,7 @@ def main():
     l0 = _lib.lib.bnf_debug_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    losses = run(args.steps)
+    losses = run(steps)
     e1.record()
     barrier()
     launches = _lib.lib.bnf_debug_launch_count() - l0
@@ -386,60 +370,69 @@ def main():
   ms = float(t_ms.median())
   ms_min, ms_max = float(t_ms.min()), float(t_ms.max())
   assert torch.isfinite(losses).all(), 'non-finite loss in the timed region'
-  value = world * E * S * B * args.steps / (ms * 1e-3)   # network-rows per second (VI: x S draws)
+  value = world * E * S * B * steps / (ms * 1e-3)   # network-rows per second (VI: x S draws)
 
   # ---- end to end through the public API, host buffers ------------------------
-  xh = torch.tensor(x.astype(np.float32)).pin_memory()
-  yh = torch.tensor(y.astype(np.float32)).pin_memory()
-  xe, ye = torch.empty_like(xd), torch.empty_like(yd)
-  k_e2e = max(5, min(args.steps, 100))
+  e2e = None
+  if do_e2e:
+    xh = torch.tensor(x.astype(np.float32)).pin_memory()
+    yh = torch.tensor(y.astype(np.float32)).pin_memory()
+    xe, ye = torch.empty_like(xd), torch.empty_like(yd)
+    k_e2e = max(5, min(steps, 100))
+    # Every step copies its inputs from pinned host memory and reads its loss back to the host.
+    # Two ways to consume the result: (a) pipelined -- the D2H read of step i is enqueued behind
+    # step i, the host goes on enqueueing step i+1 and synchronises once at the end (how a fit()
+    # call behaves: the reference's jitted scan returns the losses after the loop, inference.py:
+    # 608-614); (b) the host blocks on every step's loss before launching the next one.
+    loss_host = torch.empty((k_e2e, E), dtype=torch.float32).pin_memory()
+    if not is_vi and B < n_total:
+      spe = n_total // B          # one call = one epoch of spe steps: copy the inputs once per call
+    else:
+      spe = 1
 
-  # Every step copies its inputs from pinned host memory and reads its loss back to the host.
-  # Two ways to consume the result: (a) pipelined -- the D2H read of step i is enqueued behind
-  # step i, the host goes on enqueueing step i+1 and synchronises once at the end (how a fit()
-  # call behaves: the reference's jitted scan returns the losses after the loop, inference.py:
-  # 608-614); (b) the host blocks on every step's loss before launching the next one.
-  loss_host = torch.empty((k_e2e, E), dtype=torch.float32).pin_memory()
+    def e2e_enqueue(i):
+      xe.copy_(xh, non_blocking=True)
+      ye.copy_(yh, non_blocking=True)
+      ls = run(spe, xe, ye)
+      loss_host[i].copy_(ls.reshape(-1, E)[-1], non_blocking=True)
 
-  def e2e_enqueue(i):
-    xe.copy_(xh, non_blocking=True)
-    ye.copy_(yh, non_blocking=True)
-    ls = run(1, xe, ye)
-    loss_host[i].copy_(ls.reshape(-1, E)[-1], non_blocking=True)
+    def timed(fn):
+      barrier()
+      t0 = time.perf_counter()
+      fn()
+      barrier()
+      t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+      if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      return float(t[0])
 
-  def timed(fn):
-    barrier()
-    t0 = time.perf_counter()
-    fn()
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t[0])
+    def pipelined():
+      for i in range(k_e2e):
+        e2e_enqueue(i)
 
-  def pipelined():
-    for i in range(k_e2e):
+    def blocking():
+      for i in range(k_e2e):
+        e2e_enqueue(i)
+        torch.cuda.current_stream().synchronize()      # the loss of step i is on the host
+
+    for i in range(3):
       e2e_enqueue(i)
-
-  def blocking():
-    for i in range(k_e2e):
-      e2e_enqueue(i)
-      torch.cuda.current_stream().synchronize()      # the loss of step i is on the host
-
-  for i in range(3):
-    e2e_enqueue(i)
-  e2e_pipe_s = float(np.median([timed(pipelined) for _ in range(5)]))     # median of 5 blocks of k_e2e steps
-  assert torch.isfinite(loss_host).all(), 'non-finite loss in the end-to-end region'
-  e2e_sync_s = float(np.median([timed(blocking) for _ in range(3)]))
-  e2e_val = world * E * S * B * k_e2e / e2e_pipe_s
-  e2e_sync_val = world * E * S * B * k_e2e / e2e_sync_s
+    e2e_pipe_s = float(np.median([timed(pipelined) for _ in range(5)]))     # median of 5 blocks of k_e2e calls
+    assert torch.isfinite(loss_host).all(), 'non-finite loss in the end-to-end region'
+    e2e_sync_s = float(np.median([timed(blocking) for _ in range(3)]))
+    e2e = {'value': world * E * S * B * spe * k_e2e / e2e_pipe_s, 'unit': 'samples/s', 'steps': k_e2e * spe,
+           'h2d_bytes_per_step': int((xh.numel() * 4 + yh.numel() * 4) // spe),
+           'd2h_bytes_per_step': int(E * 4),
+           'mode': 'inputs H2D from pinned memory and the loss D2H every step; reads pipelined '
+                   'behind the steps, one host synchronisation at the end',
+           'per_step_sync_value': world * E * S * B * spe * k_e2e / e2e_sync_s}
 
   # ---- per-kernel CUDA-event timing (separate short run; not the headline) ----
   prof, roof = {}, None
   pk = peaks()
-  if not args.no_profile:
+  if do_profile:
     _lib.check(_lib.lib.bnf_debug_profile(1))
-    k_prof = 5
+    k_prof = 5 if (is_vi or B >= n_total) else (n_total // B) * max(1, 4 // (n_total // B))
     run(k_prof)
     buf = C.create_string_buffer(1 << 16)
     _lib.check(_lib.lib.bnf_debug_profile_report(buf, len(buf)))
@@ -450,7 +443,7 @@ def main():
     F, W, L = spec.num_features, wl['width'], wl['depth']
     Fp = spec.padded_features
     rows = E * S * B
-    work = algorithmic_work(rows, F, Fp, W, L, E * S * spec.num_params, 'tc_fwd_head' in prof)
+    work = algorithmic_work(rows, F, Fp, W, L, E * S * spec.num_params, 'tc_fwd_head' in prof, precision)
     for name, d in prof.items():
       if name in work and work[name]['flops'] > 0:
         d['tflops'] = work[name]['flops'] / (d['ms_per_step'] * 1e-3) / 1e12
@@ -460,13 +453,13 @@ def main():
     # algorithmic FLOPs at the measured bf16 peak take longer than its algorithmic bytes at the
     # measured HBM bandwidth, else HBM
     best = max((n for n in prof if n in work), key=lambda n: prof[n]['ms_per_step'], default=None)
-    if best and args.precision == 'bf16':
+    if best and precision in ('bf16', 'bf16x3'):
       d, wk = prof[best], work[best]
       n_l = d['launches_per_step']
       avg_ms = d['ms_per_step'] / n_l
       t_tensor = wk['flops'] / (pk['tflops_sustained'] * 1e12)
       t_hbm = wk['bytes'] / (pk['hbm_gbs'] * 1e9)
-      traffic = ncu_traffic_gb(args.workload, best)
+      traffic = ncu_traffic_gb(workload, best) if precision == 'bf16' else None
       if t_tensor >= t_hbm:
         ach, peak, unit, bound = d['tflops'], pk['tflops_sustained'], 'TFLOP/s', 'tensor'
       else:
@@ -477,52 +470,183 @@ def main():
               'algorithmic_gflop_per_launch': wk['flops'] / n_l / 1e9,
               'peak_source': pk['source'] + (', sustained bf16' if bound == 'tensor' else ', copy bandwidth'),
               'avg_launch_ms': avg_ms,
-              'note': 'CUDA-event time per launch inside bench.py (profile pass); see DESIGN.md section 9'}
+              'note': 'CUDA-event time per launch inside bench.py (profile pass); x3: executed tensor FLOPs are 6x '
+                      'the algorithmic ones; see DESIGN.md section 9'}
 
   # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------
   cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    val, timed, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget, wl)
+  if rank == 0 and world == 1 and cpu_baseline:
+    val, timed_steps, cores = cpu_oracle_rate(x, y, margs, args.cpu_budget, wl)
     cpu = {'value': val, 'unit': 'samples/s', 'cores': cores, 'cores_available': os.cpu_count(), 'kind': 'port',
-           'sample': f'1 member x {margs["init_x"][0]} rows x {timed} MAP steps (torch-CPU oracle, f32)'}
+           'sample': f'1 member x {margs["init_x"][0]} rows x {timed_steps} {wl["objective"].upper()} steps '
+                     '(torch-CPU oracle, f32)'}
+  if keep is not None:
+    keep.update(eng=eng, spec=spec, params=p, x=xd, E=E)
+  if rank != 0:
+    return None
+  fps = flops_per_sample(spec.num_features, wl['width'], wl['depth'])
+  bpe = {'fp32': 4, 'bf16x3': 6}.get(precision, 2)
+  act_bytes = E * S * B * wl['width'] * bpe * (2 * wl['depth'] + 2)
+  return {
+      'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': steps,
+      'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None,
+      'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'bf16_simt': 'bf16-storage/f32-fma',
+                'bf16x3': 'f32 via bf16x3 split operands (tcgen05 kind::f16, f32 accumulate)'}[precision],
+      'timing': {'blocks': repeats, 'steps_per_block': steps, 'block_ms_median': ms, 'block_ms_min': ms_min,
+                 'block_ms_max': ms_max, 'rule': 'median over blocks of the max over ranks (CUDA events)'},
+      'data': 'synthetic',
+      'config': {'workload': workload, 'precision': precision, 'width': wl['width'], 'depth': wl['depth'],
+                 'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
+                 'mc_samples': S,
+                 'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'], 'observation_model': lik,
+                 'parallelism': f'members sharded x{world}, no collective in training',
+                 'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
+                       if act_bytes > 126 * 2**20 else
+                       f'activation working set {act_bytes / 2**20:.0f} MiB per step (fits L2; steps '
+                       'are data-dependent so no flush is inserted)'},
+      'per_gpu_samples_per_s': value / world,
+      'algorithmic_tflops_per_gpu': value / world * fps / 1e12,
+      'samples_definition': 'members x MC draws x batch rows per second' if is_vi else 'members x batch rows per second',
+      'e2e': e2e,
+      'gpu_launches': int(launches),
+      'clocks': sampler.summary(),
+      'roofline': roof,
+      'kernels': prof,
+      'cpu_baseline': cpu,
+      'final_loss_mean': float(losses[-1].mean()),
+  }
 
+
+def predict_block(env, kept, n_rows=1 << 20):
+  """predict_bnf on N GPUs (inference.py:461-507): forward of this rank's members over n_rows test
+  rows, ONE NCCL all-gather of the predictive means over NVLink, mixture quantiles on every rank.
+  Also checks that the gathered means of another rank's members equal a local recomputation."""
+  import torch
+  import torch.distributed as dist
+  from bayesnf_b200 import inference, parallel
+  rank, world, dev = env['rank'], env['world'], env['dev']
+  eng, p, E = kept['eng'], kept['params'], kept['E']
+  g = torch.Generator(device=dev).manual_seed(7)
+  xt = torch.stack([torch.rand(n_rows, generator=g, device=dev) * 600.0,
+                    torch.randn(n_rows, generator=g, device=dev), torch.randn(n_rows, generator=g, device=dev)], 1).contiguous()
+  if world > 1:
+    dist.broadcast(xt, 0)
+  qs = [0.025, 0.5, 0.975]
+
+  def once():
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    loc = eng.forward(p, xt)
+    scales = 0.01 + torch.exp(p[:, 0])
+    ev[1].record()
+    loc_all = parallel.all_gather_leading(loc)
+    sc_all = parallel.all_gather_leading(scales)
+    ev[2].record()
+    q = inference.mixture_quantiles(loc_all.reshape(-1, n_rows), sc_all.reshape(-1), qs, False)
+    ev[3].record()
+    torch.cuda.synchronize()
+    return loc_all, q, [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+  once()
+  if world > 1:
+    dist.barrier()
+  loc_all, q, t = once()
+  tt = torch.tensor(t, dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  t = [float(v) for v in tt]
+  check = None
+  if world > 1:
+    # rank 0 recomputes the members of the LAST rank locally: the gathered block must be identical
+    p_all = parallel.all_gather_leading(p)
+    chk = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rank == 0:
+      sub = slice(0, 65536)
+      ref = eng.forward(p_all[world - 1].contiguous(), xt[sub].contiguous())
+      chk[0] = float((ref - loc_all[world - 1][:, sub]).abs().max())
+    check = float(chk[0])
+  assert torch.isfinite(q).all() and bool((q[0] <= q[1]).all()) and bool((q[1] <= q[2]).all())
+  if rank != 0:
+    return None
+  recv = (world - 1) * E * n_rows * 4
+  return {'rows': n_rows, 'members_total': E * world, 'quantiles': qs, 'precision': eng.precision_name,
+          'forward_ms': t[0], 'all_gather_ms': t[1] if world > 1 else None, 'quantile_root_ms': t[2],
+          'rows_per_s': n_rows / (sum(t) * 1e-3),
+          'member_rows_per_s': E * world * n_rows / (sum(t) * 1e-3),
+          'gathered_bytes_per_rank': E * world * n_rows * 4,
+          'all_gather_recv_gbs': (recv / (t[1] * 1e-3) / 1e9) if world > 1 else None,
+          'nvlink_peer_gbs_per_dir': 770.0,
+          'gathered_equals_local_max_abs_diff': check,
+          'collective': 'one all_gather_into_tensor (NCCL) of (members, rows) f32 means + one of the scales'}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--workload', default='chickenpox_map_e8', choices=sorted(WORKLOADS))
+  ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'tf32x3', 'fp32', 'bf16_simt'],
+                  help="bf16: single-pass tcgen05 (BASELINE configs name bf16); bf16x3 (alias tf32x3): tcgen05 at "
+                       "the 1e-5 parity tolerance (split operands); fp32: SIMT")
+  ap.add_argument('--repeats', type=int, default=0, help='timed K-step blocks (0: >= 10 and >= 100 ms in total)')
+  ap.add_argument('--cpu-budget', type=float, default=12.0, help='seconds of CPU-baseline work')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-profile', action='store_true')
+  ap.add_argument('--no-extras', action='store_true',
+                  help='skip the extra blocks of the default run (parity-mode line, wind roofline block, predict block)')
+  args = ap.parse_args()
+  if args.precision == 'tf32x3':
+    args.precision = 'bf16x3'
+  if args.impl == 'reference':
+    wl = WORKLOADS[args.workload]
+    x, y, margs = synth(wl)
+    run_reference(args, wl, x, y, margs)
+    return
+
+  import torch
+  import torch.distributed as dist
+
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if world > 1:
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+      os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the single JSON line
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+  torch.cuda.set_device(local)
+  env = {'rank': rank, 'world': world, 'local': local, 'dev': torch.device('cuda', local)}
+
+  kept = {}
+  out = run_workload(args, args.workload, args.precision, args.steps, args.warmup, env, do_e2e=True,
+                     do_profile=not args.no_profile, cpu_baseline=not args.no_cpu_baseline, repeats=args.repeats,
+                     keep=kept)
+  # ---- extra blocks of the default run: short, each a complete timed record of its own ----------
+  extras = {}
+  if not args.no_extras and args.workload == 'chickenpox_map_e8' and args.precision == 'bf16':
+    # (1) the SAME workload in the tensor-core mode that meets the 1e-5 parity tolerance
+    r = run_workload(args, args.workload, 'bf16x3', 20, 5, env, do_e2e=True, do_profile=not args.no_profile)
+    if r:
+      extras['parity_mode_bf16x3'] = {k: r[k] for k in ('value', 'unit', 'ms_per_step', 'dtype', 'timing', 'e2e',
+                                                        'gpu_launches', 'roofline', 'kernels', 'algorithmic_tflops_per_gpu')}
+    # (2) predict on all ranks: forward + one NCCL all-gather + mixture quantiles
+    pb = predict_block(env, kept)
+    if pb:
+      extras['predict'] = pb
+    kept.clear()
+    torch.cuda.empty_cache()
+    # (3) the tensor-bound regime: three steps of the wind shard (BASELINE configs[4] per GPU)
+    r = run_workload(args, 'wind_map_e16', 'bf16', 3, 3, env, do_e2e=False, do_profile=not args.no_profile,
+                     min_window_ms=0.0)
+    if r:
+      extras['roofline_wind_map_e16'] = {k: r[k] for k in ('value', 'unit', 'ms_per_step', 'config', 'timing', 'clocks',
+                                                           'gpu_launches', 'roofline', 'kernels',
+                                                           'algorithmic_tflops_per_gpu')}
   if rank == 0:
-    fps = flops_per_sample(spec.num_features, wl['width'], wl['depth'])
-    act_bytes = E * S * B * wl['width'] * (2 if args.precision != 'fp32' else 4) * (2 * wl['depth'] + 2)
-    out = {
-        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None,
-        'dtype': {'bf16': 'bf16', 'fp32': 'f32', 'bf16_simt': 'bf16-storage/f32-fma',
-                  'bf16x3': 'f32 via bf16x3 split operands (tcgen05 kind::f16, f32 accumulate)'}[args.precision],
-        'timing': {'blocks': repeats, 'steps_per_block': args.steps, 'block_ms_median': ms, 'block_ms_min': ms_min,
-                   'block_ms_max': ms_max, 'rule': 'median over blocks of the max over ranks (CUDA events)'},
-        'data': 'synthetic',
-        'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
-                   'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
-                   'mc_samples': S,
-                   'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'], 'observation_model': lik,
-                   'parallelism': f'members sharded x{world}, no collective in training',
-                   'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
-                         if act_bytes > 126 * 2**20 else
-                         f'activation working set {act_bytes / 2**20:.0f} MiB per step (fits L2; steps '
-                         'are data-dependent so no flush is inserted)'},
-        'per_gpu_samples_per_s': value / world,
-        'algorithmic_tflops_per_gpu': value / world * fps / 1e12,
-        'samples_definition': 'members x MC draws x batch rows per second' if is_vi else 'members x batch rows per second',
-        'e2e': {'value': e2e_val, 'unit': 'samples/s', 'steps': k_e2e,
-                'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4),
-                'd2h_bytes_per_step': int(E * 4),
-                'mode': 'inputs H2D from pinned memory and the loss D2H every step; reads pipelined '
-                        'behind the steps, one host synchronisation at the end',
-                'per_step_sync_value': e2e_sync_val},
-        'gpu_launches': int(launches),
-        'clocks': sampler.summary(),
-        'roofline': roof,
-        'kernels': prof,
-        'cpu_baseline': cpu,
-        'final_loss_mean': float(losses[-1].mean()),
-    }
+    out.update(extras)
     print(json.dumps(out), flush=True)
   if world > 1:
     dist.destroy_process_group()

@@ -387,3 +387,36 @@ def test_gemm_split_operands(cuda, monkeypatch, cta2, layout, nets, m, n, k):
   c = _gemm(layout, _split3(a), _split3(b), nets, m, n, k)
   err = float((c.double() - want).abs().max())
   assert err <= 2e-6 * max(1.0, k / 1024) * float(want.abs().max()), err
+
+
+@pytest.mark.parametrize('prec,ll_tol,g_tol', [('bf16', 3e-2, 5e-2), ('bf16x3', 2e-5, 1e-4)])
+def test_zinb_w512_l4_against_oracle(cuda, prec, ll_tol, g_tol):
+  """BASELINE configs[3] shape (air_quality MLE: ZINB observation model, width 512, depth 4;
+  models.py:166-191) on the tensor-core paths against the f64 oracle: at W > 256 the last layer
+  runs the plain forward kernel + head_fused_kernel (row dots, ZINB log-pmf with lgamma/digamma,
+  activation backward).  bf16: 3e-2 / 5e-2 of scale; bf16x3: the f32 parity tolerances."""
+  from bayesnf_b200 import inference, models
+  from test_gpu_parity import _data, _random_params
+  n = 600
+  cfg = dict(width=512, depth=4, input_scales=[n - 1.0, 1, 1], num_seasonal_harmonics=[4, 4],
+             seasonality_periods=[24, 168], init_x=(n, 3), fourier_degrees=[5, 5, 5], interactions=np.zeros((0, 2), int))
+  x, y = _data(cfg, n, counts=True)
+  om, om64 = O.OracleModel(**cfg), O.OracleModel(**cfg, dtype=torch.float64)
+  P = _random_params(om, 2, y, seed=23)
+  spec = models.ModelSpec(**cfg, observation_model='ZINB')
+  eng = inference.Engine(spec, prec)
+  xd, yd = inference._to_device_data(x, y)
+  ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+  ll, grad = ll.cpu(), grad.cpu()
+  parts = [(0, 1), (1, 2), (2, 3)] + [(o, o + (int(np.prod(s)) if s else 1)) for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+  for j in range(2):
+    loss64, g64 = O.map_loss_and_grad(om64, P[j].double(), xd.cpu().double(), yd.cpu().double(), n, 0.0, 'ZINB')
+    assert abs(float(ll[j]) + float(loss64)) <= ll_tol * abs(float(loss64)), (prec, float(ll[j]), float(loss64))
+    for a, b in parts:
+      if a == 0:
+        continue                                   # log_noise_scale is unused by ZINB: zero gradient
+      want, got = -g64[a:b], grad[j, a:b].double()
+      floor = 1e-3 * g_tol if prec == 'bf16' else 1e-7
+      tol = g_tol * float(want.abs().max()) + floor * float(g64.abs().max()) + 1e-7
+      assert float((got - want).abs().max()) <= tol, (prec, j, a, b, float((got - want).abs().max()), tol)
+    assert float(grad[j, 0].abs()) == 0.0
