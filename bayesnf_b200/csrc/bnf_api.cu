@@ -296,13 +296,8 @@ int check_common(const bnf_plan* p, int prec, int n_net, int B) {
   return BNF_OK;
 }
 
-bool fused_encode_enabled() {
-  // bf16 tensor-core mode, BNF_FUSED_ENCODE=1: the feature encode is fused into the Dense_0 GEMM
-  const char* fe = getenv("BNF_FUSED_ENCODE");
-  return fe && fe[0] == '1';
-}
-// the transposed bf16 kernel copy is only read by the fused-encode kernel and the BNF_FWD_WT=1 path
-bool need_wt() { return fused_encode_enabled() || tc_fwd_uses_wt(); }
+// the transposed bf16 kernel copy is only read by the BNF_FWD_WT=1 path
+bool need_wt() { return tc_fwd_uses_wt(); }
 
 // forward (+ optional backward) for n_net networks on B rows.
 template <typename T>
@@ -341,7 +336,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
         return fail(BNF_ERR_UNSUPPORTED, "bf16x3 head kernel does not support this width");
       for (int l = m.L - 1; l >= 0; --l) {
         const bf16* a_in = l == 0 ? (const bf16*)w.feat : (const bf16*)w.h[l - 1];
-        int rc = tc_wgrad(p, l, a_in, (const bf16*)w.dU[cur], grad, n_net, B, st, true);
+        int rc = tc_wgrad(p, l, a_in, (const bf16*)w.dU[cur], grad, n_net, B, st, true, l == 0 && tc_bias0_via_wgrad(m));
         if (rc) return fail(rc, "tc_wgrad (bf16x3) failed: %s", tc_last_error());
         if (l > 0) {
           rc = tc_dgrad_act_x3(p, l, w.wn, (const bf16*)w.dU[cur], (bf16*)w.dU[cur ^ 1], (const float*)w.z[l - 1],
@@ -361,10 +356,10 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
   }
   const bool tc = prec == BNF_PREC_BF16;
   if (!prepped) launch_prep(m, params, w.derived, n_net, nullptr, nullptr, nullptr, st);
-  // BNF_FUSED_ENCODE=1: encoder warps generate the A tile in shared memory (`feat` is written as a
-  // by-product only when the backward pass needs it).  Correct and tested, but with 4 encoder
-  // warps per SM it is latency-bound (profiles/README.md), so the two-kernel path is the default.
-  const bool fuse0 = tc && fused_encode_enabled();
+  // bf16 tensor-core mode: the feature encode fused into the Dense_0 GEMM (encoder warps generate the
+  // A tiles in shared memory; `feat` never reaches HBM) is the forward-only default; training steps
+  // need `feat` again for the Dense_0 wgrad and keep encode kernel + GEMM (tc_fused_encode_wanted).
+  const bool fuse0 = tc && tc_fused_encode_wanted(m, grad != nullptr);
   if (!fuse0) launch_encode<T>(m, w.derived, x, idx, idx_stride, B, (T*)w.feat, n_net, st);
   if (tc && !prepped) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
   const bool g = grad != nullptr;
@@ -379,7 +374,7 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
       continue;
     }
     if (tc && l == 0 && fuse0) {
-      int rc = tc_fwd_layer0_fused(p, params, w.derived, x, idx, idx_stride, w.wt, grad ? (bf16*)w.feat : nullptr,
+      int rc = tc_fwd_layer0_fused(p, params, w.derived, x, idx, idx_stride, w.wn, grad ? (bf16*)w.feat : nullptr,
                                    (bf16*)w.z[0], (bf16*)w.h[0], n_net, B, st);
       if (rc) return fail(rc, "tc_fwd_layer0_fused failed: %s", tc_last_error());
     } else if (tc) {
@@ -409,7 +404,11 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
     const T* a_in = l == 0 ? (const T*)w.feat : (const T*)w.h[l - 1];
     const int Kin = l == 0 ? m.F : m.W, lda = l == 0 ? m.Fp : m.W;
     if (tc) {
-      int rc = tc_wgrad(p, l, (const bf16*)a_in, (const bf16*)w.dU[cur], grad, n_net, B, st);
+      // layer 0: the constant-one feature column also yields the Dense_0 bias gradient when the
+      // fused dgrad + activation backward (which then skips its column sums) produced dU_0
+      const char* nfa = getenv("BNF_NO_FUSED_ACT_BWD");
+      const bool bias0 = l == 0 && !(nfa && nfa[0] == '1') && tc_bias0_via_wgrad(m);
+      int rc = tc_wgrad(p, l, (const bf16*)a_in, (const bf16*)w.dU[cur], grad, n_net, B, st, false, bias0);
       if (rc) return fail(rc, "tc_wgrad failed: %s", tc_last_error());
     } else {
       launch_wgrad_simt_t<T>(m, l, a_in, Kin, lda, (const T*)w.dU[cur], grad, n_net, B, st);

@@ -114,6 +114,9 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
       trow[m.col_inter + j] = (sa * sb) * dv[kDvSInter];
     }
   }
+  // constant-one feature in the first pad column (ignored by the forward GEMM: the staged kernel rows
+  // >= F are zero): row F of the Dense_0 wgrad GEMM then is the Dense_0 bias gradient (bnf_tc.cu)
+  if (m.F < m.Fp) for (int r = threadIdx.x; r < kEncRows; r += blockDim.x) tile[r * ld + m.F] = 1.f;
   __syncthreads();
   const int rows = min(kEncRows, B - row0);
   if constexpr (X3) {
@@ -201,6 +204,8 @@ encode_fast_kernel(const __grid_constant__ DevModel m, const float* __restrict__
       trow[t.c1] = __float2bfloat16_rn(sn * t.k1);
     }
   }
+  if (m.F < m.Fp) for (int r = tid; r < R; r += 256)     // constant-one feature (see encode_kernel)
+    reinterpret_cast<__nv_bfloat16*>(tile + r * ldt)[m.F] = __float2bfloat16_rn(1.f);
   __syncthreads();
   const int rows = min(R, B - row0), chunks = m.Fp / 8;
   uint4* out = reinterpret_cast<uint4*>(feat + ((size_t)net * B + row0) * m.Fp);

@@ -283,7 +283,7 @@ struct TcArgs {
   bf16* out0; bf16* out1; float* outf;
   long long out_batch; int ld_out; int grad_off;
   // A_MODE 2 (fused encode + Dense_0): raw inputs instead of a feature matrix
-  const float* x; const int32_t* idx; long long idx_stride; int x_tma; int write_feat;
+  const float* x; const int32_t* idx; long long idx_stride; int write_feat;
   // TC_DGRAD_ACT (dgrad fused with the activation backward of the previous layer)
   const bf16* zin; float* gradp; int off_bias_prev, off_ls_prev, off_actw, layer_prev;
   int out_cm; // TC_DGRAD_F32: write outf column-major [net][col][row]
@@ -292,6 +292,12 @@ struct TcArgs {
   // its contiguous dimension (plane p at columns [p*pstride, (p+1)*pstride)); the reduction runs over
   // six segments of kseg k-blocks, one per plane pair (see kX3PlaneA / kX3PlaneB)
   int x3, kseg, a_pstride, b_pstride;
+  // Dense_0 bias gradient through the wgrad GEMM: the encoders write a constant-one feature into
+  // the first pad column F (< Fp) of `feat`, so row F of the Dense_0 wgrad accumulator is
+  // isf * sum_b dU_0[b, :] = the bias gradient.  TC_WGRAD (layer 0): bias_row = F, that row goes
+  // (rescaled by 1/isf) to grad + bias_off instead of the kernel leaf.  TC_DGRAD_ACT producing
+  // dU_0: skip_bias = 1, its epilogue drops the 31-shuffle column sums.
+  int bias_row, bias_off, skip_bias; float bias_rescale;
   int dbg;   // BNF_TC_DBG ablation mask (only read when compiled with -DBNF_TC_EXPERIMENT)
   long long* tl;   // BNF_TC_TL timeline buffer [cta][16 tiles][16 events] of clock64 (experiment builds)
 };
@@ -340,9 +346,11 @@ __host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { retur
 // accumulator should be small while the many small addends arrive.  Segment s multiplies plane
 // kX3PlaneA[s] of A with plane kX3PlaneB[s] of B: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0).
 constexpr uint32_t kX3PlaneA = 0x001102u, kX3PlaneB = 0x010120u;   // nibble s = plane of segment s
-constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps
+constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps (one thread per tile row)
+constexpr int kEncMaxKb = 2;                       // A_MODE 2: Fp <= 128 = at most two 64-wide k-blocks
+constexpr int kEncMaxUnits = 128;                  // A_MODE 2: every unit owns >= 1 of the <= 128 feature columns
+struct EncUnitT { float mult, k0; int kind, dim, dim2, c0, c1, pad; };        // one feature unit (32 bytes)
 
-constexpr int kXTileBytes = 128 * kMaxD * 4;
 constexpr int kBarBytes = kEpi16 ? 1024 : 512;     // mbarriers + TMEM base slot
 constexpr int kZRing = 2;                          // TC_DGRAD_ACT: per-warp ring of 32x32 z tiles
 constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer whose bias sums stay in smem
@@ -377,21 +385,24 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
       MODE == TC_DGRAD_ACT ? (kEpiW > 12 ? (CTA2 ? 3 : (BLOCK_N == 256 ? 2 : (BLOCK_N == 128 ? 3 : 5))) :
                               kEpiW > 8 ? (CTA2 ? 4 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6)))
                                         : (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))) :
-      A_MODE == 2 ? 2 :
+      A_MODE == 2 ? (BLOCK_N == 256 ? 3 : 4) :
       (kEpiW > 12 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 6))) :
        kEpiW > 8 ? (CTA2 ? 5 : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7)))
                  : (CTA2 ? 6 : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8))));
   static constexpr int kEpi = kEpiW;
   static constexpr int kABytes = 128 * 64 * 2;
   static constexpr int kBBytes = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * 64 * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  // A_MODE 2: the ring holds only B tiles; the generated A tiles live in two resident buffers
+  static constexpr int kStageBytes = A_MODE == 2 ? kBBytes : kABytes + kBBytes;
+  static constexpr int kBOff = A_MODE == 2 ? 0 : kABytes;       // B tile inside a ring stage
   // X3 (bigger staging tiles): as many ring stages as fit beside them, at most 6
   static constexpr int kX3Fixed = kEpi * kStgWarp + kBarBytes + 2 * 256 * 4 + (MODE == TC_DGRAD_ACT ? (kAccCols + 32) * 4 : 0);
   static constexpr int kStagesX3 = (232448 - kX3Fixed) / kStageBytes > 6 ? 6 : (232448 - kX3Fixed) / kStageBytes;
   static constexpr int kStages = (X3 && MODE != TC_DGRAD_ENC) ? kStagesX3 : kStagesBf16;
   static_assert(kStages >= 2, "at least two ring stages");
   static constexpr int kThreads = 64 + 32 * kEpi + (A_MODE == 2 ? 32 * kEncWarps : 0);
-  static constexpr int kXBytes = A_MODE == 2 ? kStages * kXTileBytes : 0;
+  // A_MODE 2: [2 m-tile buffers][kEncMaxKb k-blocks][16 KB A tile] + unit table + per-row scaled inputs
+  static constexpr int kXBytes = A_MODE == 2 ? 2 * kEncMaxKb * kABytes + kEncMaxUnits * 32 + 128 * (kMaxD + 1) * 4 : 0;
   static constexpr int kStagingBytes = MODE == TC_DGRAD_ENC ? 0 : kEpi * kStgWarp;
   // CTA-wide partial sums of the epilogue's column / scalar gradients (flushed to HBM when the
   // network changes): TC_DGRAD_ACT [kAccCols] bias columns + scalars
@@ -409,7 +420,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ TcArgs a, const __grid_constant__ DevModel dm) {
   using Cfg = TcCfg<BLOCK_N, A_MODE, CTA2, MODE, X3>;
   constexpr bool A_MN = A_MODE == 1;                  // A operand MN-major
-  constexpr bool B_MN = A_MODE == 1 || A_MODE == 3;   // B operand MN-major
+  constexpr bool B_MN = A_MODE != 0;                  // B operand MN-major (natural (in,out) kernel copy / dU)
   constexpr bool ENCODE = A_MODE == 2;
   static_assert(!(CTA2 && ENCODE), "the fused encode kernel is single-CTA");
   constexpr int kEpi = Cfg::kEpi;                    // epilogue warps (ids 0..kEpi-1)
@@ -421,18 +432,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();     // 128B-swizzle tiles need 1024B alignment
-  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  // A_MODE 2: the two resident A buffers sit between the ring and the staging tiles (1024-byte aligned)
+  constexpr int kABufBytes = ENCODE ? 2 * kEncMaxKb * Cfg::kABytes : 0;
+  uint8_t* abuf = smem + Cfg::kStages * Cfg::kStageBytes;   // [2][kEncMaxKb][16 KB]
+  uint8_t* staging = abuf + kABufBytes;
   uint64_t* bars = (uint64_t*)(staging + Cfg::kStagingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
-  uint64_t* xfull = tempty + 3;                      // A_MODE 2: raw input tile landed
+  uint64_t* aready = bars + 32;                      // A_MODE 2: [2] generated A tiles of an m-tile complete
+  uint64_t* afree = bars + 34;                       // A_MODE 2: [2] the MMAs reading that buffer have retired
   uint64_t* zbar = bars + 40;                        // TC_DGRAD_ACT: [kEpi][kZRing] z tile landed
   float* sbias = (float*)(staging + Cfg::kStagingBytes + kBarBytes);  // [2][256]: s_l * bias of the tile's columns
   float* colacc = (float*)(smem + Cfg::kSmem - Cfg::kAccFloats * 4);  // TC_DGRAD_ACT / TC_FWD_HEAD partial sums
-  float* xtile = sbias + 2 * 256;                    // A_MODE 2: [kStages][128][kMaxD] f32
+  EncUnitT* etab = (EncUnitT*)(sbias + 2 * 256);     // A_MODE 2: unit table of the current network
+  float* esx = (float*)(etab + kEncMaxUnits);        // A_MODE 2: [128][kMaxD+1] scaled inputs (+ raw time) of the tile rows
   float* gtile = sbias + 2 * 256;                    // TC_DGRAD_ENC: [128][BLOCK_N+1] f32 dfeat tile
   float* eacc = sbias;                               // TC_DGRAD_ENC: [2*kMaxD+3] partial sums
   float* kos_s = sbias + 2 * 256;                    // TC_FWD_HEAD: [2][256] Dense_L kernel of the tile's network
@@ -444,10 +460,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   pdl_trigger();                       // the next kernel's CTAs may start their own prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], ENCODE ? 1 + 32 * kEncWarps : (CTA2 ? 2 : 1));
+      mbar_init(&full[s], CTA2 ? 2 : 1);
       mbar_init(&empty[s], 1);
-      if (ENCODE) mbar_init(&xfull[s], 1);
     }
+    if (ENCODE) for (int s = 0; s < 2; ++s) { mbar_init(&aready[s], 32 * kEncWarps); mbar_init(&afree[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], (CTA2 ? 2 : 1) * 32 * kEpi); }
     if (MODE == TC_DGRAD_ACT) for (int s = 0; s < kEpi * kZRing; ++s) mbar_init(&zbar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -465,12 +481,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
   if (ENCODE && warp > kMma) {
-    // zero the A slots once: pad columns [F, Fp) are never written again
+    // zero the A buffers once: pad columns [F, Fp) are never written again
     const int et = threadIdx.x - kBaseThreads;
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      uint4* pz = reinterpret_cast<uint4*>(smem + s * Cfg::kStageBytes);
-      for (int i = et; i < Cfg::kABytes / 16; i += 32 * kEncWarps) pz[i] = make_uint4(0, 0, 0, 0);
-    }
+    uint4* pz = reinterpret_cast<uint4*>(abuf);
+    for (int i = et; i < 2 * kEncMaxKb * Cfg::kABytes / 16; i += 32 * kEncWarps) pz[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -493,7 +507,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // range of tiles, i.e. mostly one network, and flushes its sums only when the network changes
   const int cta_id = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_ctas = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const bool contiguous = MODE == TC_DGRAD_ENC || MODE == TC_FWD_HEAD ||
+  const bool contiguous = MODE == TC_DGRAD_ENC || MODE == TC_FWD_HEAD || ENCODE ||
                           ((MODE == TC_DGRAD_ACT || MODE == TC_FWD) && a.n_tiles == 1);
   const int tile0 = contiguous ? (int)((long long)total_tiles * cta_id / n_ctas) : cta_id;
   const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
@@ -527,16 +541,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             if (ENCODE) {
-              // B by TMA; the raw input rows of this tile as one bulk copy for the encoder warps
+              // only the B tile travels (natural (in,out) kernel copy, MN-major); A is generated on chip
               mbar_arrive_expect_tx(&full[stage], Cfg::kBBytes);
-              tma_load_3d(sb, &map_b, &full[stage], kb * 64, n_t * BLOCK_N, net);
-              if (a.x_tma && m_t * 128 + 128 <= a.m_valid) {
-                const uint32_t xb = 128u * (uint32_t)dm.D * 4u;
-                mbar_arrive_expect_tx(&xfull[stage], xb);
-                bulk_load_1d(xtile + stage * 128 * kMaxD, a.x + (size_t)m_t * 128 * dm.D, xb, &xfull[stage]);
-              } else {
-                mbar_arrive(&xfull[stage]);
-              }
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_3d(sa + j * 8192, &map_b, &full[stage], n_t * BLOCK_N + j * 64, kb * 64, net);
             } else if (CTA2) {
               // the LEADER's full barrier collects both CTAs' bytes (count 2: its own
               // arrive.expect_tx + the peer's remote arrive)
@@ -586,8 +594,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // smem descriptors differ only in the 14-bit start address: build them once and add offsets
       const uint64_t adesc0 = A_MN ? make_smem_desc(smem_u32(smem), 8192, 1024)
                                    : make_smem_desc(smem_u32(smem), 16, 1024);
-      const uint64_t bdesc0 = B_MN ? make_smem_desc(smem_u32(smem) + Cfg::kABytes, 8192, 1024)
-                                   : make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(smem_u32(smem) + Cfg::kBOff, 8192, 1024)
+                                   : make_smem_desc(smem_u32(smem) + Cfg::kBOff, 16, 1024);
+      // A_MODE 2: A comes from the resident buffer of the tile's m-tile (two buffers, alternating)
+      const uint64_t aenc0 = make_smem_desc(smem_u32(abuf), 16, 1024);
+      int enc_buf = 1, enc_key = -1; uint32_t enc_phase[2] = {0u, 0u};
       constexpr uint32_t kStepA = (A_MN ? 2048 : 32) >> 4;      // one UMMA_K=16 slice
       constexpr uint32_t kStepB = (B_MN ? 2048 : 32) >> 4;
       int stage = 0; uint32_t phase = 0;
@@ -598,6 +609,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int split = r % a.k_splits;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
+        bool enc_last = false;
+        if constexpr (ENCODE) {
+          // tiles of one (network, m-tile) are consecutive (n fastest): the first waits for the
+          // encoder warps, the last releases the buffer once its MMAs have retired
+          const int key = t / a.n_tiles;
+          if (key != enc_key) {
+            enc_key = key;
+            enc_buf ^= 1;
+            mbar_wait(&aready[enc_buf], enc_phase[enc_buf]);
+            enc_phase[enc_buf] ^= 1u;
+            tc_fence_after();
+          }
+          enc_last = t + 1 >= tile_end || (t + 1) / a.n_tiles != key;
+        }
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (lane == 0) TL((t - tile0) / tile_step, 2);
@@ -609,10 +634,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (lane == 0 && kb == kb1 - 1) TL((t - tile0) / tile_step, 4);
           if (elect_one()) {
             const uint64_t so = (uint64_t)((stage * Cfg::kStageBytes) >> 4);
+            const uint64_t ao = ENCODE ? aenc0 + (uint64_t)(((enc_buf * kEncMaxKb + kb) * Cfg::kABytes) >> 4) : adesc0 + so;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (CTA2) umma_bf16_2sm(d_tmem, adesc0 + so + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              else umma_bf16(d_tmem, adesc0 + so + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (CTA2) umma_bf16_2sm(d_tmem, ao + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, ao + k * kStepA, bdesc0 + so + k * kStepB, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             if (CTA2) umma_commit_2sm(&empty[stage]);   // frees the slot in BOTH CTAs
             else umma_commit(&empty[stage]);            // frees the smem slot when these MMAs retire
@@ -622,6 +648,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (elect_one()) {                            // accumulator complete -> epilogue(s)
           if (CTA2) umma_commit_2sm(&tfull[acc]); else umma_commit(&tfull[acc]);
+          if (ENCODE && enc_last) umma_commit(&afree[enc_buf]);   // the encoder may refill this A buffer
         }
         __syncwarp();
         if (lane == 0) TL((t - tile0) / tile_step, 5);
@@ -1222,8 +1249,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int p = 0; p < 3; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          warp_transpose_sum(du, lane);
-          atomicAdd(&colacc[col0 + lane], du[0]);
+          if (!a.skip_bias) {                       // else the Dense_0 wgrad GEMM delivers these sums
+            warp_transpose_sum(du, lane);
+            atomicAdd(&colacc[col0 + lane], du[0]);
+          }
           continue;
         }
         if (MODE == TC_FWD) {
@@ -1319,7 +1348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          if (DBG(2)) continue;
+          if (DBG(2) || a.skip_bias) continue;      // skip_bias: the Dense_0 wgrad GEMM delivers these sums
           // bias gradient: column sums over this warp's 32 rows by a transpose-reduce (31
           // shuffles; lane L ends up with column L), added to the CTA's shared-memory partial
           // sums.  (mma.sync on the staged tile was tried for this and is far slower: the legacy
@@ -1387,15 +1416,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool col_ok = col0 + lane < a.n_valid;
           const int rows_here = min(32, a.m_valid - row_base);
           if (col_ok) {
+            // the constant-one feature row (Dense_0): its sums are the bias gradient
+            const int rb = a.bias_row - row_base;        // in [0, rows_here) only in the row group that holds it
+            const int rows_k = (rb >= 0 && rb < rows_here) ? rb : rows_here;
             if (a.k_splits == 1) {
 #pragma unroll 8
-              for (int r = 0; r < rows_here; ++r)
+              for (int r = 0; r < rows_k; ++r)
                 o[(size_t)r * a.ld_out] = st32[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
             } else {
 #pragma unroll 8
-              for (int r = 0; r < rows_here; ++r)
+              for (int r = 0; r < rows_k; ++r)
                 atomicAdd(o + (size_t)r * a.ld_out, st32[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))]);
             }
+            if (rows_k < rows_here)
+              atomicAdd(a.outf + (size_t)net * a.out_batch + a.bias_off + col0 + lane,
+                        st32[rb * 32 + ((((lane >> 2) ^ (rb & 7)) << 2) | (lane & 3))] * a.bias_rescale);
           }
         }
       }
@@ -1512,81 +1547,96 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (ENCODE) {
-    // ===================== feature encoder (warps 10..13, A_MODE 2) =====================
-    // work item = (unit, row): 128 rows of one unit per pass -> warp-uniform unit kind.
-    // Each item writes its one or two bf16 feature values straight into the 128B-swizzled
-    // K-major A tile the MMA reads; the finished tile is also TMA-stored as `feat` (wgrad
-    // of Dense_0 needs it) by one elected thread.
-    const int et = threadIdx.x - kBaseThreads;
+    // ===================== feature encoder (4 warps = one thread per tile row, A_MODE 2) =====================
+    // models.py:216-252 fused into the Dense_0 GEMM: for every (network, m-tile) the encoder warps
+    // write the 128 x Fp bf16 feature tile straight into the 128B-swizzled K-major A buffers the MMA
+    // reads (two buffers: tile i+1 is generated while the MMAs / epilogues of tile i run, and the
+    // tile is reused by every n-tile of the layer).  A thread owns one row: it scales its D inputs
+    // once, then walks the network's unit table (column indices, argument multiplier, output scale
+    // with the 1/(d+1), 1/h divisions folded in -- built when the CTA's network changes) and stores
+    // one or two bf16 values per unit.  `feat` (the Dense_0 wgrad operand) is TMA-stored from the
+    // same buffers when the backward pass needs it; forward-only calls never write it.
+    const int et = threadIdx.x - kBaseThreads;       // = tile row
     const int U = num_units(dm);
-    const float two_pi = 6.283185307179586f;
-    int stage = 0; uint32_t phase = 0;
+    int enc_buf = 1, enc_key = -1, tab_net = -1; uint32_t free_phase[2] = {0u, 0u};
     for (int t = tile0; t < tile_end; t += tile_step) {
+      const int key = t / a.n_tiles;
+      if (key == enc_key) continue;                  // another n-tile of the m-tile already generated
+      enc_key = key;
+      enc_buf ^= 1;
       const int net = t / tiles_per_net;
-      int r0 = t % tiles_per_net;
-      const int n_t = r0 % a.n_tiles; r0 /= a.n_tiles;
-      const int m_t = r0 / a.k_splits;
+      const int m_t = (t % tiles_per_net) / (a.n_tiles * a.k_splits);
       const float* dv = a.derived + (size_t)net * kDerivedStride;
-      const bool x_in_smem = a.x_tma && m_t * 128 + 128 <= a.m_valid;
-      for (int kb = 0; kb < a.k_blocks; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");
-        mbar_wait(&xfull[stage], phase);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        const float* xs = xtile + stage * 128 * kMaxD;
-        auto put = [&](int r, int c, float v) {
-          if ((c >> 6) != kb) return;
-          const int cc = c & 63;
-          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((((cc >> 3) ^ (r & 7)) & 7) << 4) + (cc & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(sa + off) = __float2bfloat16_rn(v);
-        };
-        for (int w = et; w < 128 * U; w += 32 * kEncWarps) {
-          const int u = w >> 7, r = w & 127;
-          const int row = m_t * 128 + r;
-          if (row >= a.m_valid) continue;
+      // the MMAs that read this buffer two m-tiles ago have retired (first use passes at once) ...
+      mbar_wait(&afree[enc_buf], free_phase[enc_buf] ^ 1u);
+      free_phase[enc_buf] ^= 1u;
+      // ... and so has the TMA store that read it
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (net != tab_net) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");     // nobody reads the old table any more
+        for (int u = et; u < U; u += 32 * kEncWarps) {
           const UnitInfo ui = decode_unit(dm, u);
-          const float* xr = x_in_smem ? xs + r * dm.D
-                                      : a.x + (a.idx ? (size_t)a.idx[(size_t)net * a.idx_stride + row] : (size_t)row) * dm.D;
+          EncUnitT e;
+          e.kind = ui.kind; e.dim = 0; e.dim2 = 0; e.c0 = 0; e.c1 = 0; e.mult = 0.f; e.k0 = 0.f; e.pad = 0;
           if (ui.kind == 0) {
-            put(r, dm.col_x + ui.a, (xr[ui.a] / dv[kDvDenom + ui.a]) * dv[kDvSX]);
+            e.dim = ui.a; e.c0 = dm.col_x + ui.a; e.k0 = dv[kDvSX];
           } else if (ui.kind == 1) {
-            const int i = ui.a, d = ui.b, deg = dm.fourier_deg[i];
-            const int c0 = dm.fourier_col[i] + d, c1i = c0 + deg;
-            if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
-            const float sx = xr[i] / dv[kDvDenom + i];
-            float sn, cs;
-            sincos_reduced((two_pi * (float)(1 << d)) * sx, &sn, &cs);   // MUFU: bf16 rounding dominates
-            const float den = (float)(d + 1), sc = dv[kDvSFourier + i];
-            put(r, c0, (cs / den) * sc);
-            put(r, c1i, (sn / den) * sc);
+            e.dim = ui.a; e.mult = 6.283185307179586f * (float)(1 << ui.b);
+            e.c0 = dm.fourier_col[ui.a] + ui.b; e.c1 = e.c0 + dm.fourier_deg[ui.a];
+            e.k0 = dv[kDvSFourier + ui.a] / (float)(ui.b + 1);
           } else if (ui.kind == 2) {
-            const int k = ui.a;
-            const int c0 = dm.col_seasonal + k, c1i = c0 + dm.n_seasonal;
-            if ((c0 >> 6) != kb && (c1i >> 6) != kb) continue;
-            float sn, cs;
-            sincos_reduced(dm.seasonal_w[k] * xr[0], &sn, &cs);
-            const float sc = dv[kDvSSeas], hk = dm.seasonal_h[k];
-            put(r, c0, (cs / hk) * sc);
-            put(r, c1i, (sn / hk) * sc);
+            e.dim = dm.D; e.mult = dm.seasonal_w[ui.a];
+            e.c0 = dm.col_seasonal + ui.a; e.c1 = e.c0 + dm.n_seasonal;
+            e.k0 = dv[kDvSSeas] / dm.seasonal_h[ui.a];
           } else {
-            const int j = ui.a;
-            const float sa_ = xr[dm.inter_a[j]] / dv[kDvDenom + dm.inter_a[j]];
-            const float sb_ = xr[dm.inter_b[j]] / dv[kDvDenom + dm.inter_b[j]];
-            put(r, dm.col_inter + j, (sa_ * sb_) * dv[kDvSInter]);
+            e.dim = dm.inter_a[ui.a]; e.dim2 = dm.inter_b[ui.a]; e.c0 = dm.col_inter + ui.a; e.k0 = dv[kDvSInter];
           }
+          etab[u] = e;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (a.write_feat && n_t == 0) {
-          asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");
-          if (et == 0) {
-            tma_store_3d(&map_a, sa, kb * 64, m_t * 128, net);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
-        mbar_arrive(&full[stage]);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        tab_net = net;
       }
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");       // table ready, buffer free for all rows
+      // this thread's row: scaled inputs x / (input_scale * exp(lsa)) and the raw time (slot D)
+      const int row = min(m_t * 128 + et, a.m_valid - 1);      // rows >= B: a copy of the last row (never stored)
+      const float* xr = a.x + (a.idx ? (size_t)a.idx[(size_t)net * a.idx_stride + row] : (size_t)row) * dm.D;
+      float* sx = esx + et * (kMaxD + 1);
+      for (int i = 0; i < dm.D; ++i) {
+        const float xv = xr[i];
+        sx[i] = xv / dv[kDvDenom + i];
+        if (i == 0) sx[dm.D] = xv;
+      }
+      uint8_t* ab = abuf + enc_buf * kEncMaxKb * Cfg::kABytes;
+      const int r = et;
+      const uint32_t rbase = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+      auto put = [&](int c, float v) {              // column c of this row, swizzled K-major tile of k-block c / 64
+        const int cc = c & 63;
+        const uint32_t off = (uint32_t)(c >> 6) * Cfg::kABytes + rbase + (uint32_t)((((cc >> 3) ^ (r & 7)) & 7) << 4) + (uint32_t)(cc & 7) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(ab + off) = __float2bfloat16_rn(v);
+      };
+#pragma unroll 2
+      for (int u = 0; u < U; ++u) {
+        const EncUnitT e = etab[u];                  // warp-uniform: broadcast reads
+        if (e.kind == 0) {
+          put(e.c0, sx[e.dim] * e.k0);
+        } else if (e.kind == 3) {
+          put(e.c0, (sx[e.dim] * sx[e.dim2]) * e.k0);
+        } else {
+          float sn, cs;
+          sincos_reduced(e.mult * sx[e.dim], &sn, &cs);   // MUFU: the bf16 rounding of the feature dominates
+          put(e.c0, cs * e.k0);
+          put(e.c1, sn * e.k0);
+        }
+      }
+      if (dm.F < dm.Fp) put(dm.F, 1.f);            // constant-one feature: Dense_0 bias gradient via the wgrad GEMM
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (a.write_feat) {
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEncWarps) : "memory");     // the whole tile is written
+        if (et == 0) {
+          for (int kb = 0; kb < a.k_blocks; ++kb) tma_store_3d(&map_a, ab + kb * Cfg::kABytes, kb * 64, m_t * 128, net);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      mbar_arrive(&aready[enc_buf]);
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -1923,18 +1973,41 @@ int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, co
 }
 
 // Fused feature encode + Dense_0 (models.py:216-268 for the first layer): the A operand is
-// generated on-chip from (x, idx) by encoder warps; `feat` (may be NULL) receives the tile
-// as a by-product for the Dense_0 wgrad.
+// generated on-chip from (x, idx) by encoder warps and stays resident for all n-tiles of its
+// m-tile; B is the natural (in,out) bf16 kernel copy read MN-major (the copy the fused MAP update
+// maintains).  `feat` (may be NULL) receives the tiles as a by-product for the Dense_0 wgrad.
+bool tc_fused_encode_supported(const DevModel& m) {
+  int U = m.D + m.n_seasonal + m.n_inter;
+  for (int i = 0; i < m.D; ++i) U += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+  return m.Fp <= 64 * kEncMaxKb && U <= kEncMaxUnits && !tc_fwd_uses_wt();
+}
+// Policy (measured, profiles/experiments/README.md r2f): forward-only calls (predict) use the fused
+// kernel -- `feat` then never exists in HBM.  In a TRAINING step `feat` is needed again by the
+// Dense_0 wgrad, so fusing saves only its (L2-resident) re-read, while the encoder warps share the
+// issue slots of an epilogue-bound kernel and one programmatic-launch overlap is lost: 0.184 vs
+// 0.174 ms/step at W=256, a tie at W=1024.  Training therefore keeps encode kernel + GEMM unless
+// BNF_FUSED_ENCODE=1; BNF_NO_FUSED_ENCODE=1 switches the fused kernel off everywhere.
+bool tc_fused_encode_wanted(const DevModel& m, bool training) {
+  if (!tc_fused_encode_supported(m)) return false;
+  const char* off = getenv("BNF_NO_FUSED_ENCODE");
+  if (off && off[0] == '1') return false;
+  const char* on = getenv("BNF_FUSED_ENCODE");
+  if (on && on[0] == '1') return true;
+  return !training;
+}
+
 int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
-                        const int32_t* idx, int64_t idx_stride, const bf16* wt, bf16* feat, bf16* z, bf16* h,
+                        const int32_t* idx, int64_t idx_stride, const bf16* wn, bf16* feat, bf16* z, bf16* h,
                         int n_net, int B, cudaStream_t st) {
   const DevModel& m = p->m;
   const int Kp = m.Fp, bn = pick_block_n(m.W);
+  if (!tc_fused_encode_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused encode + Dense_0 needs <= 128 padded features");
   CUtensorMap ma, mb;
   int rc;
   memset(&ma, 0, sizeof(ma));
   if (feat && (rc = make_map(&ma, feat, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128))) return rc;
-  if ((rc = make_map(&mb, wt, Kp, m.W, n_net, Kp, tc_weight_elems(m), bn))) return rc;
+  // wn [Kp][W]: boxes of [64 reduction rows][64 output columns]
+  if ((rc = make_map(&mb, wn, m.W, Kp, n_net, m.W, tc_weight_elems(m), 64))) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_FWD; a.n_net = n_net;
@@ -1944,7 +2017,6 @@ int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* der
   a.isf = m.inv_sqrt_F;
   a.out0 = z; a.out1 = h; a.out_batch = (long long)B * m.W; a.ld_out = m.W;
   a.x = x; a.idx = idx; a.idx_stride = idx_stride;
-  a.x_tma = (idx == nullptr && ((uintptr_t)x & 15) == 0) ? 1 : 0;
   a.write_feat = feat ? 1 : 0;
   OutMaps om;
   memset(&om, 0, sizeof(om));
@@ -1973,6 +2045,7 @@ int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* d
   a.m_valid = B; a.n_valid = Kp;
   a.isf = m.inv_sqrt_W;
   a.zin = (const bf16*)z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
+  a.skip_bias = (layer == 1 && tc_bias0_via_wgrad(m)) ? 1 : 0;
   a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
   a.off_ls_prev = m.off_layer_scale[layer - 1]; a.off_actw = m.off_actw;
   a.out0 = out; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
@@ -2002,6 +2075,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
   if (z_prev) {
     if (Kp > kAccCols) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad + activation backward needs W <= 1024");
     a.zin = z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
+    a.skip_bias = (layer == 1 && tc_bias0_via_wgrad(m)) ? 1 : 0;
     a.layer_prev = layer - 1; a.off_bias_prev = m.off_bias[layer - 1];
     a.off_ls_prev = m.off_layer_scale[layer - 1]; a.off_actw = m.off_actw;
   }
@@ -2019,6 +2093,13 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
 }
 
 bool tc_dgrad_act_supported(const DevModel& m) { return m.W <= kAccCols; }
+// Dense_0 bias gradient as row F of the Dense_0 wgrad GEMM (constant-one feature in the first pad
+// column of feat): needs a pad column and the fused dgrad + activation backward feeding layer 0.
+bool tc_bias0_via_wgrad(const DevModel& m) {
+  const char* e = getenv("BNF_NO_BIAS0_WGRAD");
+  if (e && e[0] == '1') return false;
+  return m.F < m.Fp && m.L >= 2 && tc_dgrad_act_supported(m);
+}
 
 // Layer-0 dgrad fused with the feature-encode backward: dfeat = isf * dU_0 @ K_0^T never leaves
 // the SM (TMEM -> shared-memory tile); the epilogue warps reduce it against the regenerated
@@ -2056,7 +2137,7 @@ int tc_dgrad0_enc(const bnf_plan* p, const bf16* wn, const bf16* dU, const float
 }
 
 int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, float* grad, int n_net, int B,
-             cudaStream_t st, bool x3) {
+             cudaStream_t st, bool x3, bool bias0) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer), Kin = layer == 0 ? m.F : m.W, bn = pick_block_n(m.W);
   CUtensorMap ma, mb;
@@ -2090,6 +2171,10 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   while (splits > 1 && (a.k_blocks + splits - 1) / splits * (splits - 1) >= a.k_blocks) --splits;
   a.k_splits = splits;
   a.m_valid = Kin; a.n_valid = m.W;
+  a.bias_row = -1;
+  if (layer == 0 && bias0) {        // row F of the accumulator = isf * sum_b dU_0 = the Dense_0 bias gradient
+    a.m_valid = Kin + 1; a.bias_row = Kin; a.bias_off = m.off_bias[0]; a.bias_rescale = 1.f / m.inv_sqrt_F;
+  }
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.outf = grad; a.out_batch = m.P; a.ld_out = m.W; a.grad_off = m.off_kernel[layer];
   OutMaps om;

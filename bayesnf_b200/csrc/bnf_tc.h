@@ -33,8 +33,11 @@ bool tc_fwd_head_supported(const DevModel& m);
 int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const __nv_bfloat16* a_in,
                 const __nv_bfloat16* wn, const float* y, const int32_t* idx, int64_t idx_stride,
                 __nv_bfloat16* dU, float* ll, float* grad, int n_net, int B, cudaStream_t st);
+// fused feature encode + Dense_0 (the default first layer of the bf16 path when Fp <= 128)
+bool tc_fused_encode_supported(const DevModel& m);
+bool tc_fused_encode_wanted(const DevModel& m, bool training);
 int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* derived, const float* x,
-                        const int32_t* idx, int64_t idx_stride, const __nv_bfloat16* wt,
+                        const int32_t* idx, int64_t idx_stride, const __nv_bfloat16* wn,
                         __nv_bfloat16* feat, __nv_bfloat16* z, __nv_bfloat16* h, int n_net, int B,
                         cudaStream_t st);
 // out_bf (hidden layers) or out_f32 (layer 0 -> dfeat [n_net,B,Fp]) receives isf * dU @ K^T
@@ -51,8 +54,10 @@ bool tc_dgrad0_enc_supported(const DevModel& m);
 int tc_dgrad0_enc(const bnf_plan* p, const __nv_bfloat16* wn, const __nv_bfloat16* dU, const float* x,
                   const int32_t* idx, int64_t idx_stride, const float* params, const float* derived,
                   float* grad, int n_net, int B, cudaStream_t st, bool x3 = false);
+// bias0: (layer 0) feat carries the constant-one column -> also emit the Dense_0 bias gradient
 int tc_wgrad(const bnf_plan* p, int layer, const __nv_bfloat16* a_in, const __nv_bfloat16* dU,
-             float* grad, int n_net, int B, cudaStream_t st, bool x3 = false);
+             float* grad, int n_net, int B, cudaStream_t st, bool x3 = false, bool bias0 = false);
+bool tc_bias0_via_wgrad(const DevModel& m);
 
 int tc_debug_gemm(int mn_major, const __nv_bfloat16* A, const __nv_bfloat16* Bm, float* C, int n_net,
                   int M, int N, int K, int sm_count, cudaStream_t st);

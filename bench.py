@@ -84,6 +84,22 @@ def synth(wl, seed=20240925):
   return x, y, margs
 
 
+def workload_config(workload, world, F):
+  """The `config` object of the JSON line -- identical for our arm and the reference arm."""
+  wl = WORKLOADS[workload]
+  E, S = wl['members_per_gpu'], wl.get('mc_samples', 1)
+  n_total = wl['times'] * wl['sites']
+  B = wl['batch'] or n_total
+  act_bytes = E * S * B * wl['width'] * 2 * (2 * wl['depth'] + 2)     # bf16 activations of one step
+  return {'workload': workload, 'width': wl['width'], 'depth': wl['depth'], 'features': int(F),
+          'members_per_gpu': E, 'members_total': E * world, 'mc_samples': S, 'batch_rows': B, 'rows_total': n_total,
+          'objective': wl['objective'], 'observation_model': wl.get('likelihood', 'NORMAL'),
+          'parallelism': f'members sharded x{world}, no collective in training',
+          'l2': (f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2' if act_bytes > 126 * 2**20 else
+                 f'activation working set {act_bytes / 2**20:.0f} MiB per step (fits L2; steps are data-dependent so '
+                 'no flush is inserted)')}
+
+
 def flops_per_sample(F, W, L):
   return 6 * (F * W + (L - 1) * W * W + W)      # SURVEY.md 8d: fwd + dgrad + wgrad
 
@@ -257,6 +273,8 @@ def run_reference(args, wl, x, y, margs):
   if rank != 0:
     return
   import torch
+  from oracle import bnf_oracle as O
+  om_features = O.OracleModel(**margs).F
   step, B = _oracle_stepper(x, y, margs, wl)
   _best_thread_count(step)                   # torchrun exports OMP_NUM_THREADS=1: undo it
   for _ in range(args.warmup):
@@ -273,8 +291,7 @@ def run_reference(args, wl, x, y, margs):
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
       'data': 'synthetic',
-      'config': {'workload': args.workload, 'width': wl['width'], 'depth': wl['depth'],
-                 'batch_rows': B, 'objective': wl['objective']},
+      'config': workload_config(args.workload, args.gpus, om_features),
       'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'cores_available': os.cpu_count(),
                        'kind': 'port', 'sample': sample},
       'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -485,8 +502,6 @@ def run_workload(args, workload, precision, steps, warmup, env, do_e2e=True, do_
   if rank != 0:
     return None
   fps = flops_per_sample(spec.num_features, wl['width'], wl['depth'])
-  bpe = {'fp32': 4, 'bf16x3': 6}.get(precision, 2)
-  act_bytes = E * S * B * wl['width'] * bpe * (2 * wl['depth'] + 2)
   return {
       'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': steps,
       'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,
@@ -496,15 +511,8 @@ def run_workload(args, workload, precision, steps, warmup, env, do_e2e=True, do_
       'timing': {'blocks': repeats, 'steps_per_block': steps, 'block_ms_median': ms, 'block_ms_min': ms_min,
                  'block_ms_max': ms_max, 'rule': 'median over blocks of the max over ranks (CUDA events)'},
       'data': 'synthetic',
-      'config': {'workload': workload, 'precision': precision, 'width': wl['width'], 'depth': wl['depth'],
-                 'features': spec.num_features, 'members_per_gpu': E, 'members_total': E * world,
-                 'mc_samples': S,
-                 'batch_rows': B, 'rows_total': n_total, 'objective': wl['objective'], 'observation_model': lik,
-                 'parallelism': f'members sharded x{world}, no collective in training',
-                 'l2': f'activation working set {act_bytes / 2**20:.0f} MiB per step > 126 MiB L2'
-                       if act_bytes > 126 * 2**20 else
-                       f'activation working set {act_bytes / 2**20:.0f} MiB per step (fits L2; steps '
-                       'are data-dependent so no flush is inserted)'},
+      'config': workload_config(workload, world, spec.num_features),
+      'precision': precision,
       'per_gpu_samples_per_s': value / world,
       'algorithmic_tflops_per_gpu': value / world * fps / 1e12,
       'samples_definition': 'members x MC draws x batch rows per second' if is_vi else 'members x batch rows per second',
