@@ -317,8 +317,16 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
         tc_cast_weights_x3(m, params, w.wn, n_net, st);
       }
       launch_encode_x3(m, w.derived, x, idx, idx_stride, B, (bf16*)w.feat, n_net, st);
+      // training with W <= 256: the last hidden layer's GEMM also runs the head, the log-likelihood and
+      // its own activation backward (TC_FWD_HEAD): z, h of that layer never reach HBM
+      const bool head_epi = g && ll && tc_fwd_head_supported(m);
       for (int l = 0; l < m.L; ++l) {
         const bf16* a_in = l == 0 ? (const bf16*)w.feat : (const bf16*)w.h[l - 1];
+        if (head_epi && l == m.L - 1) {
+          int rc = tc_fwd_head(p, params, w.derived, a_in, w.wn, y, idx, idx_stride, (bf16*)w.dU[0], ll, grad, n_net, B, st, true);
+          if (rc) return fail(rc, "tc_fwd_head (bf16x3) failed: %s", tc_last_error());
+          continue;
+        }
         int rc = tc_fwd_layer(p, l, params, w.derived, a_in, nullptr, w.wn, nullptr, (bf16*)w.h[l], n_net, B, st,
                               true, g ? (float*)w.z[l] : nullptr);
         if (rc) return fail(rc, "tc_fwd_layer (bf16x3) failed: %s", tc_last_error());
@@ -331,7 +339,8 @@ int run_net(const bnf_plan* p, int prec, const float* params, int n_net, const f
         return fail(BNF_ERR_INVALID, "gradient without log-likelihood output");
       }
       int cur = 0;
-      if (!launch_head_fused_x3(m, params, w.derived, (const bf16*)w.h[m.L - 1], (const float*)w.z[m.L - 1], y, idx,
+      if (!head_epi &&
+          !launch_head_fused_x3(m, params, w.derived, (const bf16*)w.h[m.L - 1], (const float*)w.z[m.L - 1], y, idx,
                                 idx_stride, B, (bf16*)w.dU[cur], ll, grad, n_net, st))
         return fail(BNF_ERR_UNSUPPORTED, "bf16x3 head kernel does not support this width");
       for (int l = m.L - 1; l >= 0; --l) {

@@ -145,15 +145,19 @@ __global__ void encode_kernel(const __grid_constant__ DevModel m, const float* _
 struct EncUnit { float mult, k0, k1; int kind, dim, dim2, c0, c1; };
 constexpr int kEncFastRows = 64;
 
+// X3: the bf16x3 variant -- accurate sincosf (the f32 arguments reach 1e3..1e5 rad), the tile is kept in
+// f32 and leaves as three bf16 planes [plane 0: Fp | plane 1: Fp | plane 2: Fp] per row.
+template <bool X3>
 __global__ void __launch_bounds__(256)
 encode_fast_kernel(const __grid_constant__ DevModel m, const float* __restrict__ derived,
                    const float* __restrict__ x, const int32_t* __restrict__ idx, int64_t idx_stride,
                    int B, __nv_bfloat16* __restrict__ feat, int U) {
   extern __shared__ __align__(16) uint8_t esm[];
   constexpr int R = kEncFastRows;
+  constexpr int ES = X3 ? 4 : 2;                         // bytes per tile element
   pdl_enter(derived, x, idx, feat);
-  const int ldt = m.Fp * 2 + 16;                         // bytes per tile row (16-byte aligned, 4-way banks)
-  uint8_t* tile = esm;                                   // [R][ldt] bf16 features
+  const int ldt = m.Fp * ES + 16;                        // bytes per tile row (16-byte aligned, 4-way banks)
+  uint8_t* tile = esm;                                   // [R][ldt] features
   float* sxs = reinterpret_cast<float*>(esm + R * ldt);  // [R][kMaxD+1] x/denom, slot D = raw time
   EncUnit* tab = reinterpret_cast<EncUnit*>(sxs + R * (kMaxD + 1));
   const int net = blockIdx.y, row0 = blockIdx.x * R, tid = threadIdx.x;
@@ -169,12 +173,15 @@ encode_fast_kernel(const __grid_constant__ DevModel m, const float* __restrict__
       const int i = ui.a, d = ui.b;
       t.dim = i; t.mult = 6.283185307179586f * (float)(1 << d);
       t.c0 = m.fourier_col[i] + d; t.c1 = t.c0 + m.fourier_deg[i];
-      t.k0 = t.k1 = dv[kDvSFourier + i] / (float)(d + 1);
+      // X3 keeps the reference's operation order (feature / (d+1)) * scale, models.py:87,250
+      t.k0 = X3 ? (float)(d + 1) : dv[kDvSFourier + i] / (float)(d + 1);
+      t.k1 = dv[kDvSFourier + i];
     } else if (ui.kind == 2) {
       const int k = ui.a;
       t.dim = m.D; t.mult = m.seasonal_w[k];
       t.c0 = m.col_seasonal + k; t.c1 = t.c0 + m.n_seasonal;
-      t.k0 = t.k1 = dv[kDvSSeas] / m.seasonal_h[k];
+      t.k0 = X3 ? m.seasonal_h[k] : dv[kDvSSeas] / m.seasonal_h[k];
+      t.k1 = dv[kDvSSeas];
     } else {
       t.dim = m.inter_a[ui.a]; t.dim2 = m.inter_b[ui.a]; t.c0 = m.col_inter + ui.a; t.k0 = dv[kDvSInter];
     }
@@ -188,30 +195,55 @@ encode_fast_kernel(const __grid_constant__ DevModel m, const float* __restrict__
     if (i == 0) sxs[r * (kMaxD + 1) + m.D] = xv;
   }
   __syncthreads();
+  auto put = [&](int r, int c, float v) {
+    if constexpr (X3) reinterpret_cast<float*>(tile + r * ldt)[c] = v;
+    else reinterpret_cast<__nv_bfloat16*>(tile + r * ldt)[c] = __float2bfloat16_rn(v);
+  };
   for (int w = tid; w < R * U; w += 256) {
     const int u = w / R, r = w % R;                      // a warp shares one unit: uniform table reads
     const EncUnit t = tab[u];
     const float* sr = sxs + r * (kMaxD + 1);
-    __nv_bfloat16* trow = reinterpret_cast<__nv_bfloat16*>(tile + r * ldt);
     if (t.kind == 0) {
-      trow[t.c0] = __float2bfloat16_rn(sr[t.dim] * t.k0);
+      put(r, t.c0, sr[t.dim] * t.k0);
     } else if (t.kind == 3) {
-      trow[t.c0] = __float2bfloat16_rn((sr[t.dim] * sr[t.dim2]) * t.k0);
+      put(r, t.c0, (sr[t.dim] * sr[t.dim2]) * t.k0);
     } else {
       float sn, cs;
-      sincos_reduced(t.mult * sr[t.dim], &sn, &cs);
-      trow[t.c0] = __float2bfloat16_rn(cs * t.k0);
-      trow[t.c1] = __float2bfloat16_rn(sn * t.k1);
+      if constexpr (X3) {
+        sincosf(t.mult * sr[t.dim], &sn, &cs);
+        put(r, t.c0, (cs / t.k0) * t.k1);
+        put(r, t.c1, (sn / t.k0) * t.k1);
+      } else {
+        sincos_reduced(t.mult * sr[t.dim], &sn, &cs);
+        put(r, t.c0, cs * t.k0);
+        put(r, t.c1, sn * t.k0);
+      }
     }
   }
-  if (m.F < m.Fp) for (int r = tid; r < R; r += 256)     // constant-one feature (see encode_kernel)
-    reinterpret_cast<__nv_bfloat16*>(tile + r * ldt)[m.F] = __float2bfloat16_rn(1.f);
+  if (m.F < m.Fp) for (int r = tid; r < R; r += 256) put(r, m.F, 1.f);     // constant-one feature (see encode_kernel)
   __syncthreads();
   const int rows = min(R, B - row0), chunks = m.Fp / 8;
-  uint4* out = reinterpret_cast<uint4*>(feat + ((size_t)net * B + row0) * m.Fp);
-  for (int e = tid; e < rows * chunks; e += 256) {
-    const int r = e / chunks, j = e - r * chunks;
-    out[e] = *reinterpret_cast<const uint4*>(tile + r * ldt + j * 16);
+  if constexpr (X3) {
+    // 8 features of a row -> 16 bytes in each of the three planes
+    for (int e = tid; e < rows * chunks; e += 256) {
+      const int r = e / chunks, j = e - r * chunks;
+      const float4 f0 = *reinterpret_cast<const float4*>(tile + r * ldt + j * 32);
+      const float4 f1 = *reinterpret_cast<const float4*>(tile + r * ldt + j * 32 + 16);
+      alignas(16) uint32_t pk[3][4];
+      split3_pair(f0.x, f0.y, &pk[0][0], &pk[1][0], &pk[2][0]);
+      split3_pair(f0.z, f0.w, &pk[0][1], &pk[1][1], &pk[2][1]);
+      split3_pair(f1.x, f1.y, &pk[0][2], &pk[1][2], &pk[2][2]);
+      split3_pair(f1.z, f1.w, &pk[0][3], &pk[1][3], &pk[2][3]);
+      __nv_bfloat16* o = feat + ((size_t)net * B + row0 + r) * 3 * m.Fp + j * 8;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) *reinterpret_cast<uint4*>(o + pl * m.Fp) = *reinterpret_cast<const uint4*>(pk[pl]);
+    }
+  } else {
+    uint4* out = reinterpret_cast<uint4*>(feat + ((size_t)net * B + row0) * m.Fp);
+    for (int e = tid; e < rows * chunks; e += 256) {
+      const int r = e / chunks, j = e - r * chunks;
+      out[e] = *reinterpret_cast<const uint4*>(tile + r * ldt + j * 16);
+    }
   }
 }
 
@@ -1573,7 +1605,7 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
       if (smem_f <= 48 * 1024) {
         dim3 grid_f((B + kEncFastRows - 1) / kEncFastRows, n_net);
         BNF_PROF("encode", st);
-        launch_k(encode_fast_kernel, grid_f, dim3(256), smem_f, st, m, derived, x, idx, idx_stride, B, feat, U);
+        launch_k(encode_fast_kernel<false>, grid_f, dim3(256), smem_f, st, m, derived, x, idx, idx_stride, B, feat, U);
         return;
       }
     }
@@ -1585,6 +1617,19 @@ void launch_encode(const DevModel& m, const float* derived, const float* x, cons
 }
 void launch_encode_x3(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
                       int64_t idx_stride, int B, __nv_bfloat16* feat3, int n_net, cudaStream_t st) {
+  {
+    const char* e = getenv("BNF_ENCODE_GENERIC");
+    int U = m.D + m.n_seasonal + m.n_inter;
+    for (int i = 0; i < m.D; ++i) U += m.fourier_deg[i] > 0 ? m.fourier_deg[i] : 0;
+    const size_t smem_f = (size_t)kEncFastRows * (m.Fp * 4 + 16) + (size_t)kEncFastRows * (kMaxD + 1) * 4 +
+                          (size_t)U * sizeof(EncUnit);
+    if (!(e && e[0] == '1') && smem_f <= 48 * 1024) {
+      dim3 grid_f((B + kEncFastRows - 1) / kEncFastRows, n_net);
+      BNF_PROF("encode", st);
+      launch_k(encode_fast_kernel<true>, grid_f, dim3(256), smem_f, st, m, derived, x, idx, idx_stride, B, feat3, U);
+      return;
+    }
+  }
   dim3 grid((B + kEncRows - 1) / kEncRows, n_net);
   size_t smem = (size_t)kEncRows * (m.Fp + 1) * sizeof(float);
   BNF_PROF("encode", st);

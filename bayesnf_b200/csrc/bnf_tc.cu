@@ -362,7 +362,8 @@ constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer
 // each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
 // from L2 drops by a third and the ring gets deeper (32 KB stages).
 template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 = false> struct TcCfg {
-  static_assert(!X3 || MODE == TC_FWD || MODE == TC_DGRAD_ACT || MODE == TC_DGRAD_ENC, "x3 epilogues: fwd, dgrad+act, dgrad0+encode");
+  static_assert(!X3 || MODE == TC_FWD || MODE == TC_FWD_HEAD || MODE == TC_DGRAD_ACT || MODE == TC_DGRAD_ENC,
+                "x3 epilogues: fwd, fwd+head, dgrad+act, dgrad0+encode");
   static_assert(!X3 || !kEpi16, "the x3 epilogues have no sixteen-warp variant");
   // TC_DGRAD_ENC: the dfeat tile stays on chip -- a 128 x (BLOCK_N+1) f32 tile in shared memory.
   // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
@@ -370,13 +371,13 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   static constexpr int kGBytes = MODE == TC_DGRAD_ENC ? 128 * (BLOCK_N + 1) * 4 + 2 * 128 * (kMaxD + 1) * 4 : 0;
   // TC_FWD_HEAD: Dense_L kernel [2][256] + per-row partial dots [<= 4][128] in shared memory
   // + the tile's h = act(z) as bf16 in per-warp 64B-swizzled 32x32 tiles (pass 1 -> pass 2)
-  static constexpr int kHeadScratch = MODE == TC_FWD_HEAD
+  static constexpr int kHeadScratch = (MODE == TC_FWD_HEAD && !X3)     // (x3 recomputes instead of stashing h)
       ? epi_warps_of(MODE, A_MODE) * ((BLOCK_N / 32 + epi_warps_of(MODE, A_MODE) / 4 - 1) / (epi_warps_of(MODE, A_MODE) / 4)) * 2048 : 0;
   static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadScratch : 0;
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
   // X3: TC_FWD [z f32 4 KB | h planes 3 x 2 KB]; TC_DGRAD_ACT [z ring kZRing x 4 KB | dU planes 3 x 2 KB]
-  static constexpr int kStgWarp = X3 ? (MODE == TC_DGRAD_ACT ? 4096 * kZRing + 3 * 2048 : 4096 + 3 * 2048)
+  static constexpr int kStgWarp = X3 ? (MODE == TC_DGRAD_ACT ? 4096 * kZRing + 3 * 2048 : MODE == TC_FWD_HEAD ? 3 * 2048 : 4096 + 3 * 2048)
                                      : (MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096);
   static constexpr int kEpiW = X3 ? 8 : epi_warps_of(MODE, A_MODE);
   static constexpr int kStagesBf16 = MODE == TC_DGRAD_ENC ? 2 :
@@ -396,7 +397,8 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   static constexpr int kStageBytes = A_MODE == 2 ? kBBytes : kABytes + kBBytes;
   static constexpr int kBOff = A_MODE == 2 ? 0 : kABytes;       // B tile inside a ring stage
   // X3 (bigger staging tiles): as many ring stages as fit beside them, at most 6
-  static constexpr int kX3Fixed = kEpi * kStgWarp + kBarBytes + 2 * 256 * 4 + (MODE == TC_DGRAD_ACT ? (kAccCols + 32) * 4 : 0);
+  static constexpr int kX3Fixed = kEpi * kStgWarp + kBarBytes + 2 * 256 * 4 + (MODE == TC_DGRAD_ACT ? (kAccCols + 32) * 4 : 0) +
+                                  (MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 : 0);
   static constexpr int kStagesX3 = (232448 - kX3Fixed) / kStageBytes > 6 ? 6 : (232448 - kX3Fixed) / kStageBytes;
   static constexpr int kStages = (X3 && MODE != TC_DGRAD_ENC) ? kStagesX3 : kStagesBf16;
   static_assert(kStages >= 2, "at least two ring stages");
@@ -672,13 +674,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     f32x2 gw2 = 0ull, gs2 = 0ull;    // TC_DGRAD_ACT: per-lane packed partial sums of the current network
     float xg_w = 0.f, xg_s = 0.f;    // the same sums in the x3 epilogue (scalar math)
     // this warp's share of the two scalar gradients -> the CTA's shared-memory sums (before a flush)
-    auto dact_scalars = [&]() {
+    auto dact_scalars = [&](int fnet) {
       const float g_w = warp_sum(f2_lo(gw2) + f2_hi(gw2) + xg_w) * a.isf;     // sum dh*diff,  dh = acc*isf
       const float g_s = warp_sum(f2_lo(gs2) + f2_hi(gs2) + xg_s) * a.isf;     // sum dz*z,     dz = dh*act'(z)
       xg_w = 0.f; xg_s = 0.f;
       if (lane == 0) {
-        atomicAdd(&colacc[kAccCols], g_w * p_wact * (1.f - p_wact));
-        atomicAdd(&colacc[kAccCols + 1], g_s * p_fls);
+        if (a.skip_bias) {
+          // no column sums to combine across warps: every warp adds its two scalars straight to the
+          // gradient (two atomics per warp and network change) and the CTA-wide barriers go away
+          float* g = a.gradp + (size_t)fnet * a.P;
+          atomicAdd(g + a.off_actw, g_w * p_wact * (1.f - p_wact));
+          atomicAdd(g + a.off_ls_prev, g_s * p_fls);
+        } else {
+          atomicAdd(&colacc[kAccCols], g_w * p_wact * (1.f - p_wact));
+          atomicAdd(&colacc[kAccCols + 1], g_s * p_fls);
+        }
       }
       gw2 = 0ull; gs2 = 0ull;
     };
@@ -786,6 +796,104 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         if (epi_tid == 0) TL((t - tile0) / tile_step, 7);
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);   // kd replaces the accumulator
+        if constexpr (X3) {
+          // ---- bf16x3 (f32-parity) variant: nothing is stashed -- pass 1 evaluates h = act(z) only for
+          // the row dots, pass 2 re-reads the untouched accumulator and RECOMPUTES the activation
+          // (one ex2 + one rcp per element and pass; the tile's six-segment MMAs take as long as
+          // both passes), then emits dU as three bf16 planes.  z, h of the layer never exist in HBM.
+          float dot = 0.f;
+#pragma unroll 1
+          for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(hsb + c + j);
+              const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float d, hh;
+                act_grad_x3(fmaf(__uint_as_float(v[j + e]), cz, bb[e]), w, &d, &hh);
+                dot = fmaf(hh, kk[e], dot);
+              }
+            }
+          }
+          rowdot[half * 128 + q * 32 + lane] = dot;
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kParts) : "memory");   // the warps of this lane quarter
+          float dsum = rowdot[q * 32 + lane];
+#pragma unroll
+          for (int pp = 1; pp < kParts; ++pp) dsum += rowdot[pp * 128 + q * 32 + lane];
+          const float opre = dsum * dm.inv_sqrt_W + bo;
+          float gl3[3] = {0.f, 0.f, 0.f};
+          float rr = 0.f, logp = 0.f;
+          if (row_ok) logp = head_row_loglik(dm.likelihood, dv, s_out * opre, yv, &rr, gl3);
+          if (!row_ok) rr = 0.f;
+          const float rk = rr * hc;                     // dh[col] = rk * Ko[col]
+          const float rks = rk * s_l;
+          float gw = 0.f, gs = 0.f;
+#pragma unroll
+          for (int ci = 0; ci < kHeadChunks; ++ci) {
+            const int c = half * 32 + ci * 32 * kParts;
+            if (c >= BLOCK_N) break;
+            uint32_t v[32], pk[3][16];
+            float du[32], gk[32];
+            tmem_ld32(tacc + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(hsb + c + j);
+              const float4 k4 = *reinterpret_cast<const float4*>(kos + c + j);
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float zz = fmaf(__uint_as_float(v[j + e]), cz, bb[e]);
+                float d, hh;
+                const float da = act_grad_x3(zz, w, &d, &hh);
+                const float kd = kk[e] * da;
+                gw = fmaf(kk[e], d, gw);              // sum Ko*diff   (x rk  = sum dh*diff)
+                gs = fmaf(kd, zz, gs);                // sum kd*z      (x rk  = sum dz*z)
+                du[j + e] = kd * rks;
+                gk[j + e] = hh * rr;
+              }
+              split3_pair(du[j], du[j + 1], &pk[0][j / 2], &pk[1][j / 2], &pk[2][j / 2]);
+              split3_pair(du[j + 2], du[j + 3], &pk[0][j / 2 + 1], &pk[1][j / 2 + 1], &pk[2][j / 2 + 1]);
+            }
+            uint8_t* stg = staging + warp * Cfg::kStgWarp;       // dU planes 3 x 2 KB
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(stg + pl * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pk[pl][4 * k], pk[pl][4 * k + 1], pk[pl][4 * k + 2], pk[pl][4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl) tma_store_3d(&map_o0, stg + pl * 2048, c + pl * BLOCK_N, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            warp_transpose_sum(du, lane);
+            warp_transpose_sum(gk, lane);
+            hcol_b[ci] += du[0];
+            hcol_k[ci] += gk[0];
+          }
+          tc_fence_before();
+          if (CTA2) mbar_arrive_remote(&tempty[acc], 0);
+          else mbar_arrive(&tempty[acc]);
+          if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+          hsc[0] += rk * gw;
+          hsc[1] += rk * gs;
+          if (half == 0) {
+            hsc[2] += logp;
+            hsc[3] += dm.likelihood == BNF_NORMAL ? gl3[0] : gl3[1];
+            hsc[4] += gl3[2];
+            hsc[5] += rr * opre;
+            hsc[6] += rr;
+          }
+          continue;
+        }
         constexpr int kMaxChunks = (BLOCK_N / 32 + kParts - 1) / kParts;   // chunks per warp and tile
         uint8_t* hw_scr = hscr + (size_t)warp * kMaxChunks * 2048;        // this warp's h tiles
         // ---- pass 1 (packed f32x2 math: FFMA2)
@@ -1011,18 +1119,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (net != acc_net) {
           // the network changed: flush the CTA's partial sums of the previous one
           if (acc_net >= 0) {
-            dact_scalars();
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
-            float* g = a.gradp + (size_t)acc_net * a.P;
-            for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) {
-              atomicAdd(g + a.off_bias_prev + i, colacc[i]);
-              colacc[i] = 0.f;
+            dact_scalars(acc_net);
+            if (!a.skip_bias) {
+              asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // all adds are in
+              float* g = a.gradp + (size_t)acc_net * a.P;
+              for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) {
+                atomicAdd(g + a.off_bias_prev + i, colacc[i]);
+                colacc[i] = 0.f;
+              }
+              if (epi_tid < 2) {
+                atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
+                colacc[kAccCols + epi_tid] = 0.f;
+              }
+              asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // zeroed before new adds
             }
-            if (epi_tid < 2) {
-              atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
-              colacc[kAccCols + epi_tid] = 0.f;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // zeroed before new adds
           }
           acc_net = net;
           p_wact = dv[kDvActW];
@@ -1064,6 +1174,112 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (epi_tid == 0) TL((t - tile0) / tile_step, 7);
+      if constexpr (X3 && (MODE == TC_FWD || MODE == TC_DGRAD_ACT)) {
+        // ---- bf16x3 epilogues
+        auto chunk_x3 = [&](int c, uint32_t* v) {
+          const int col0 = n_t * BLOCK_N + c;
+          if constexpr (MODE == TC_FWD) {
+            // ---- bf16x3 forward: z = acc*c1 + s_l*b stays f32 (the backward pass needs it), h = act(z)
+            // leaves as its three bf16 planes (the next GEMM's split A operand).  Staging per warp:
+            // [z 32x32 f32, 128B swizzle | h planes 3 x (32x32 bf16, 64B swizzle)]
+            uint8_t* stg = staging + warp * Cfg::kStgWarp;
+            uint32_t hp[3][16];
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+  #pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * k);
+              const float z0 = fmaf(__uint_as_float(v[4 * k]), c1, b4.x), z1 = fmaf(__uint_as_float(v[4 * k + 1]), c1, b4.y);
+              const float z2 = fmaf(__uint_as_float(v[4 * k + 2]), c1, b4.z), z3 = fmaf(__uint_as_float(v[4 * k + 3]), c1, b4.w);
+              if (a.out0) *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(z0, z1, z2, z3);
+              float d, h0, h1, h2, h3;
+              act_grad_x3(z0, w_act, &d, &h0);
+              act_grad_x3(z1, w_act, &d, &h1);
+              act_grad_x3(z2, w_act, &d, &h2);
+              act_grad_x3(z3, w_act, &d, &h3);
+              split3_pair(h0, h1, &hp[0][2 * k], &hp[1][2 * k], &hp[2][2 * k]);
+              split3_pair(h2, h3, &hp[0][2 * k + 1], &hp[1][2 * k + 1], &hp[2][2 * k + 1]);
+            }
+  #pragma unroll
+            for (int p = 0; p < 3; ++p)
+  #pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(stg + 4096 + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(hp[p][4 * k], hp[p][4 * k + 1], hp[p][4 * k + 2], hp[p][4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+  #pragma unroll
+              for (int p = 0; p < 3; ++p) tma_store_3d(&map_o1, stg + 4096 + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
+              if (a.out0) tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else {
+            // ---- bf16x3 dgrad + activation backward: the f32 z tile of the chunk arrives by TMA
+            // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as three bf16 planes.
+            // Staging per warp: [z ring | dU planes 3 x 2 KB]
+            uint8_t* so = staging + warp * Cfg::kStgWarp + kZRing * 4096;
+            const uint32_t zsl = zc % kZRing;
+            mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
+            const uint8_t* zt = zring + zsl * 4096 + lane * 128;
+            uint32_t pk[3][16];
+            float du[32];
+            const float cdu = a.isf * s_prev;
+  #pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 z4 = *reinterpret_cast<const float4*>(zt + ((k ^ (lane & 7)) << 4));
+              const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float vv = __uint_as_float(v[4 * k + e]);
+                float diff, hh;
+                const float da = act_grad_x3(zz[e], w_act, &diff, &hh);
+                const float x = vv * da;
+                xg_w = fmaf(vv, diff, xg_w);
+                xg_s = fmaf(x, zz[e], xg_s);
+                du[4 * k + e] = x * cdu;
+              }
+              split3_pair(du[4 * k], du[4 * k + 1], &pk[0][2 * k], &pk[1][2 * k], &pk[2][2 * k]);
+              split3_pair(du[4 * k + 2], du[4 * k + 3], &pk[0][2 * k + 1], &pk[1][2 * k + 1], &pk[2][2 * k + 1]);
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            // every lane has read its z row: refill the slot with the tile kZRing chunks ahead
+            if (lane == 0 && c + 32 * kParts * kZRing < BLOCK_N) {
+              mbar_arrive_expect_tx(&zb[zsl], 4096);
+              tma_load_3d(zring + zsl * 4096, &map_o1, &zb[zsl], col0 + 32 * kParts * kZRing, m_t * 128 + q * 32, net);
+            }
+            ++zc;
+  #pragma unroll
+            for (int p = 0; p < 3; ++p)
+  #pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(so + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(pk[p][4 * k], pk[p][4 * k + 1], pk[p][4 * k + 2], pk[p][4 * k + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+  #pragma unroll
+              for (int p = 0; p < 3; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (!a.skip_bias) {                       // else the Dense_0 wgrad GEMM delivers these sums
+              warp_transpose_sum(du, lane);
+              atomicAdd(&colacc[col0 + lane], du[0]);
+            }
+          }
+        };
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+        for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
+          // (prefetching the next chunk's accumulator into a second register set while this one is
+          // processed was measured -- r2i -- and gains nothing: the exposed tcgen05.ld latency just
+          // moves to the next dependent instruction, and the extra 32 registers spill)
+          uint32_t v[32];
+          tmem_ld32(tb + (uint32_t)c, v);
+          chunk_x3(c, v);
+        }
+      } else
 #pragma unroll 1
       for (int c = half * 32; c < BLOCK_N; c += 32 * kParts) {
         if constexpr (kEpi16 && A_MODE != 2 && (MODE == TC_FWD || MODE == TC_DGRAD_ACT)) {
@@ -1162,99 +1378,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
-        if constexpr (X3 && MODE == TC_FWD) {
-          // ---- bf16x3 forward: z = acc*c1 + s_l*b stays f32 (the backward pass needs it), h = act(z)
-          // leaves as its three bf16 planes (the next GEMM's split A operand).  Staging per warp:
-          // [z 32x32 f32, 128B swizzle | h planes 3 x (32x32 bf16, 64B swizzle)]
-          uint8_t* stg = staging + warp * Cfg::kStgWarp;
-          uint32_t hp[3][16];
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c + 4 * k);
-            const float z0 = fmaf(__uint_as_float(v[4 * k]), c1, b4.x), z1 = fmaf(__uint_as_float(v[4 * k + 1]), c1, b4.y);
-            const float z2 = fmaf(__uint_as_float(v[4 * k + 2]), c1, b4.z), z3 = fmaf(__uint_as_float(v[4 * k + 3]), c1, b4.w);
-            if (a.out0) *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(z0, z1, z2, z3);
-            float d, h0, h1, h2, h3;
-            act_grad_x3(z0, w_act, &d, &h0);
-            act_grad_x3(z1, w_act, &d, &h1);
-            act_grad_x3(z2, w_act, &d, &h2);
-            act_grad_x3(z3, w_act, &d, &h3);
-            split3_pair(h0, h1, &hp[0][2 * k], &hp[1][2 * k], &hp[2][2 * k]);
-            split3_pair(h2, h3, &hp[0][2 * k + 1], &hp[1][2 * k + 1], &hp[2][2 * k + 1]);
-          }
-#pragma unroll
-          for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<uint4*>(stg + 4096 + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(hp[p][4 * k], hp[p][4 * k + 1], hp[p][4 * k + 2], hp[p][4 * k + 3]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) tma_store_3d(&map_o1, stg + 4096 + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
-            if (a.out0) tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          continue;
-        }
-        if constexpr (X3 && MODE == TC_DGRAD_ACT) {
-          // ---- bf16x3 dgrad + activation backward: the f32 z tile of the chunk arrives by TMA
-          // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as three bf16 planes.
-          // Staging per warp: [z ring | dU planes 3 x 2 KB]
-          uint8_t* so = staging + warp * Cfg::kStgWarp + kZRing * 4096;
-          const uint32_t zsl = zc % kZRing;
-          mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
-          const uint8_t* zt = zring + zsl * 4096 + lane * 128;
-          uint32_t pk[3][16];
-          float du[32];
-          const float cdu = a.isf * s_prev;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float4 z4 = *reinterpret_cast<const float4*>(zt + ((k ^ (lane & 7)) << 4));
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float vv = __uint_as_float(v[4 * k + e]);
-              float diff, hh;
-              const float da = act_grad_x3(zz[e], w_act, &diff, &hh);
-              const float x = vv * da;
-              xg_w = fmaf(vv, diff, xg_w);
-              xg_s = fmaf(x, zz[e], xg_s);
-              du[4 * k + e] = x * cdu;
-            }
-            split3_pair(du[4 * k], du[4 * k + 1], &pk[0][2 * k], &pk[1][2 * k], &pk[2][2 * k]);
-            split3_pair(du[4 * k + 2], du[4 * k + 3], &pk[0][2 * k + 1], &pk[1][2 * k + 1], &pk[2][2 * k + 1]);
-          }
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-          // every lane has read its z row: refill the slot with the tile kZRing chunks ahead
-          if (lane == 0 && c + 32 * kParts * kZRing < BLOCK_N) {
-            mbar_arrive_expect_tx(&zb[zsl], 4096);
-            tma_load_3d(zring + zsl * 4096, &map_o1, &zb[zsl], col0 + 32 * kParts * kZRing, m_t * 128 + q * 32, net);
-          }
-          ++zc;
-#pragma unroll
-          for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<uint4*>(so + p * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
-                  make_uint4(pk[p][4 * k], pk[p][4 * k + 1], pk[p][4 * k + 2], pk[p][4 * k + 3]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          if (!a.skip_bias) {                       // else the Dense_0 wgrad GEMM delivers these sums
-            warp_transpose_sum(du, lane);
-            atomicAdd(&colacc[col0 + lane], du[0]);
-          }
-          continue;
-        }
         if (MODE == TC_FWD) {
           uint32_t zp[16], hp[16];
           const ActConst2 ak(w_act);
@@ -1539,11 +1662,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (MODE == TC_FWD_HEAD && acc_net >= 0) head_flush(acc_net);
     if (MODE == TC_DGRAD_ACT && acc_net >= 0) {
       // the CTA's last network: flush its partial sums
-      dact_scalars();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
-      float* g = a.gradp + (size_t)acc_net * a.P;
-      for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) atomicAdd(g + a.off_bias_prev + i, colacc[i]);
-      if (epi_tid < 2) atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
+      dact_scalars(acc_net);
+      if (!a.skip_bias) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");
+        float* g = a.gradp + (size_t)acc_net * a.P;
+        for (int i = epi_tid; i < a.n_valid; i += 32 * kEpi) atomicAdd(g + a.off_bias_prev + i, colacc[i]);
+        if (epi_tid < 2) atomicAdd(g + (epi_tid == 0 ? a.off_actw : a.off_ls_prev), colacc[kAccCols + epi_tid]);
+      }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (ENCODE) {
@@ -1744,7 +1869,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
   int grid = (int)(total < slots ? total : slots);
   if (grid < 1) grid = 1;
   if (CTA2) grid *= 2;
-  BNF_PROF(X3 && MODE == TC_FWD ? "tc_gemm_fwd_x3" : X3 && MODE == TC_DGRAD_ACT ? "tc_gemm_dgrad_x3" : MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD_HEAD ? "tc_fwd_head" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
+  BNF_PROF(X3 && MODE == TC_FWD_HEAD ? "tc_fwd_head_x3" : X3 && MODE == TC_FWD ? "tc_gemm_fwd_x3" : X3 && MODE == TC_DGRAD_ACT ? "tc_gemm_dgrad_x3" : MN == 2 ? "tc_encode_fwd0" : MODE == TC_DGRAD_ENC ? "tc_dgrad0_enc" : MODE == TC_FWD_HEAD ? "tc_fwd_head" : MODE == TC_FWD ? "tc_gemm_fwd" : (MODE == TC_WGRAD ? "tc_gemm_wgrad" : (MODE == TC_PLAIN_F32 ? "tc_gemm_plain" : "tc_gemm_dgrad")), st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -1833,6 +1958,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const OutMaps
     if (a.mode == TC_WGRAD) return launch_tc_m<BLOCK_N, 1, TC_WGRAD>(ma, mb, om, a, sm, st, dm);
     return launch_tc_m<BLOCK_N, 1, TC_PLAIN_F32>(ma, mb, om, a, sm, st, dm);
   } else if constexpr (MN == 3) {
+    if (a.mode == TC_FWD_HEAD && a.x3) return launch_tc_m<BLOCK_N, 3, TC_FWD_HEAD, true>(ma, mb, om, a, sm, st, dm);
     if (a.mode == TC_FWD_HEAD) return launch_tc_m<BLOCK_N, 3, TC_FWD_HEAD>(ma, mb, om, a, sm, st, dm);
     if (a.mode == TC_FWD && a.x3) return launch_tc_m<BLOCK_N, 3, TC_FWD, true>(ma, mb, om, a, sm, st, dm);
     if (a.mode == TC_FWD) return launch_tc_m<BLOCK_N, 3, TC_FWD>(ma, mb, om, a, sm, st, dm);
@@ -1867,6 +1993,14 @@ static int launch_tc_n(int block_n, const CUtensorMap& ma, const CUtensorMap& mb
 }
 
 static int pick_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+// experiment hook: BNF_BN_FWD / BNF_BN_DGRAD = 128 or 64 force narrower output tiles for the plain
+// forward / fused dgrad kernels (more, smaller tiles: less wave quantisation, more per-tile overhead)
+static int pick_block_n_env(int n, const char* env) {
+  const char* e = getenv(env);
+  const int want = e ? atoi(e) : 0;
+  if ((want == 128 || want == 64) && n % want == 0) return want;
+  return pick_block_n(n);
+}
 static int sm_count_of(const bnf_plan* p) {
   if (p->sm_count > 0) return p->sm_count;
   int dev = 0, n = 148;
@@ -1886,7 +2020,7 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
                  const bf16* wt, const bf16* wn, bf16* z, bf16* h, int n_net, int B, cudaStream_t st,
                  bool x3, float* zf) {
   const DevModel& m = p->m;
-  const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
+  const int Kp = kp_of(m, layer), bn = pick_block_n_env(m.W, "BNF_BN_FWD");
   if (x3) {
     // split operands: a_in [n_net,B,3*Kp], wn [layer][Kp][3*W]; outputs zf [n_net,B,W] f32 (may be
     // NULL: forward only) and h [n_net,B,3*W]
@@ -1949,26 +2083,28 @@ bool tc_fwd_head_supported(const DevModel& m) {
 
 int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const bf16* a_in, const bf16* wn,
                 const float* y, const int32_t* idx, int64_t idx_stride, bf16* dU, float* ll, float* grad,
-                int n_net, int B, cudaStream_t st) {
+                int n_net, int B, cudaStream_t st, bool x3) {
   const DevModel& m = p->m;
   const int layer = m.L - 1;
   const int Kp = kp_of(m, layer), bn = pick_block_n(m.W);
   if (!tc_fwd_head_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused head epilogue needs W in {64,128,256}");
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, a_in, Kp, B, n_net, Kp, (uint64_t)B * Kp, 128);
+  const uint64_t pl = x3 ? 3 : 1;     // planes side by side in every operand row
+  int rc = make_map(&ma, a_in, pl * Kp, B, n_net, pl * Kp, (uint64_t)B * pl * Kp, 128);
   if (rc) return rc;
-  if ((rc = make_map(&mb, wn + layer_off(m, layer), m.W, Kp, n_net, m.W, tc_weight_elems(m), 64))) return rc;
+  if ((rc = make_map(&mb, wn + pl * layer_off(m, layer), pl * m.W, Kp, n_net, pl * m.W, pl * tc_weight_elems(m), 64))) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_FWD_HEAD; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = Kp / 64;
+  if (x3) { a.x3 = 1; a.kseg = Kp / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; }
   a.m_valid = B; a.n_valid = m.W;
   a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.y = y; a.ll = ll; a.idx = idx; a.idx_stride = idx_stride; a.gradp = grad;
   OutMaps om;
   memset(&om, 0, sizeof(om));
-  if ((rc = make_out_map(&om.o0, dU, m.W, B, n_net))) return rc;
+  if ((rc = make_out_map(&om.o0, dU, pl * m.W, B, n_net))) return rc;
   return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
@@ -2030,7 +2166,7 @@ int tc_fwd_layer0_fused(const bnf_plan* p, const float* params, const float* der
 int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* dU, bf16* out, const float* z_prev,
                     const float* params, const float* derived, float* grad, int n_net, int B, cudaStream_t st) {
   const DevModel& m = p->m;
-  const int Kp = kp_of(m, layer), bn = pick_block_n(Kp);
+  const int Kp = kp_of(m, layer), bn = pick_block_n_env(Kp, "BNF_BN_DGRAD");
   if (layer < 1 || Kp > kAccCols) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad + activation backward needs W <= 1024");
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dU, 3 * (uint64_t)m.W, B, n_net, 3 * (uint64_t)m.W, (uint64_t)B * 3 * m.W, 128);
@@ -2061,7 +2197,7 @@ int tc_dgrad(const bnf_plan* p, int layer, const bf16* wn, const bf16* dU, bf16*
              const float* derived, float* grad) {
   const DevModel& m = p->m;
   const int Kp = kp_of(m, layer);          // output columns (in-features, padded)
-  const int bn = pick_block_n(Kp);
+  const int bn = z_prev ? pick_block_n_env(Kp, "BNF_BN_DGRAD") : pick_block_n(Kp);
   CUtensorMap ma, mb;
   int rc = make_map(&ma, dU, m.W, B, n_net, m.W, (uint64_t)B * m.W, 128);
   if (rc) return rc;

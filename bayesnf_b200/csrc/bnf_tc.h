@@ -32,7 +32,7 @@ int tc_dgrad_act_x3(const bnf_plan* p, int layer, const __nv_bfloat16* wn3, cons
 bool tc_fwd_head_supported(const DevModel& m);
 int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, const __nv_bfloat16* a_in,
                 const __nv_bfloat16* wn, const float* y, const int32_t* idx, int64_t idx_stride,
-                __nv_bfloat16* dU, float* ll, float* grad, int n_net, int B, cudaStream_t st);
+                __nv_bfloat16* dU, float* ll, float* grad, int n_net, int B, cudaStream_t st, bool x3 = false);
 // fused feature encode + Dense_0 (the default first layer of the bf16 path when Fp <= 128)
 bool tc_fused_encode_supported(const DevModel& m);
 bool tc_fused_encode_wanted(const DevModel& m, bool training);

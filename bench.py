@@ -161,8 +161,10 @@ def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head, precision='bf16'):
   tensor cores execute six bf16 products per f32 product)."""
   if precision == 'bf16x3':
     a6, a4, f6 = 6 * rows * W, 4 * rows * W, 6 * rows * Fp
+    nf = L - 1 if fused_head else L          # layers run by the plain forward kernel
     return {
-        'tc_gemm_fwd_x3': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=f6 + L * (a4 + a6) + (L - 1) * a6),
+        'tc_gemm_fwd_x3': dict(flops=2.0 * rows * (F * W + (nf - 1) * W * W), bytes=f6 + nf * (a4 + a6) + (nf - 1) * a6),
+        'tc_fwd_head_x3': dict(flops=2.0 * rows * (W * W + W), bytes=2 * a6),          # h in, dU out (planes)
         'head_fused': dict(flops=2.0 * rows * W, bytes=a6 + a4 + a6),                  # h, z in, dU out
         'tc_gemm_dgrad_x3': dict(flops=2.0 * rows * (L - 1) * W * W, bytes=(L - 1) * (a6 + a4 + a6)),
         'tc_dgrad0_enc': dict(flops=2.0 * rows * F * W, bytes=a6),
@@ -460,7 +462,8 @@ def run_workload(args, workload, precision, steps, warmup, env, do_e2e=True, do_
     F, W, L = spec.num_features, wl['width'], wl['depth']
     Fp = spec.padded_features
     rows = E * S * B
-    work = algorithmic_work(rows, F, Fp, W, L, E * S * spec.num_params, 'tc_fwd_head' in prof, precision)
+    work = algorithmic_work(rows, F, Fp, W, L, E * S * spec.num_params, 'tc_fwd_head' in prof or 'tc_fwd_head_x3' in prof,
+                            precision)
     for name, d in prof.items():
       if name in work and work[name]['flops'] > 0:
         d['tflops'] = work[name]['flops'] / (d['ms_per_step'] * 1e-3) / 1e12
