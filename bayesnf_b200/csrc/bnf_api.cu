@@ -254,8 +254,9 @@ Ws carve(const bnf_plan* p, int prec, int n_net, int B, int mode, void* base) {
   if (g) {
     w.opre = (float*)c.take(rows * 4);
     w.r = (float*)c.take(rows * 4);
-    w.dU[0] = c.take(rows * m.W * ts);
-    w.dU[1] = m.L > 1 ? c.take(rows * m.W * ts) : w.dU[0];
+    const size_t tdu = x3 ? 4 : ts;               // bf16x3: the backpropagated dU carries two planes
+    w.dU[0] = c.take(rows * m.W * tdu);
+    w.dU[1] = m.L > 1 ? c.take(rows * m.W * tdu) : w.dU[0];
     w.dfeat = x3 ? nullptr : (float*)c.take(rows * m.Fp * 4);   // bf16x3: dfeat never leaves the SM
   }
   if (mode == BNF_WS_MAP || mode == BNF_WS_VI) w.grad = (float*)c.take((size_t)n_net * m.P * 4);

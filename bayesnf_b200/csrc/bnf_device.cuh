@@ -138,6 +138,13 @@ __device__ __forceinline__ void split3_pair(float a, float b, uint32_t* p0, uint
   __nv_bfloat162 t2 = __floats2bfloat162_rn(sa, sb);
   *p0 = u0; *p1 = u1; *p2 = *reinterpret_cast<uint32_t*>(&t2);
 }
+// two planes only (the backpropagated dU of the bf16x3 mode): p0 = bf16(v), p1 = bf16(v - p0)
+__device__ __forceinline__ void split2_pair(float a, float b, uint32_t* p0, uint32_t* p1) {
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(a, b);
+  const uint32_t u0 = *reinterpret_cast<uint32_t*>(&t0);
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(a - __uint_as_float(u0 << 16), b - __uint_as_float(u0 & 0xffff0000u));
+  *p0 = u0; *p1 = *reinterpret_cast<uint32_t*>(&t1);
+}
 __device__ __forceinline__ void split3_one(float a, __nv_bfloat16* p0, __nv_bfloat16* p1, __nv_bfloat16* p2) {
   const __nv_bfloat16 h0 = __float2bfloat16_rn(a);
   const float r = a - __bfloat162float(h0);

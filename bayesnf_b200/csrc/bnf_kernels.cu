@@ -772,7 +772,7 @@ act_bwd_vec_kernel(const __grid_constant__ DevModel m, int layer, const float* _
 // Same math as head_kernel + act_bwd_vec_kernel<.., true>.
 // =============================================================================
 constexpr int kHeadFusedMaxRows = 512;   // rows per block are chosen at launch so the grid is whole waves
-// X3 (T = bf16, bf16x3 mode): h and dU rows hold three bf16 planes [W | W | W], z is f32
+// X3 (T = bf16, bf16x3 mode): h rows hold three bf16 planes [W | W | W], dU rows two, z is f32
 // (`z` then points to floats), accurate activation math.
 template <typename T, bool X3 = false>
 __global__ void __launch_bounds__(256)
@@ -942,12 +942,14 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
         du_r[k] = du;
       }
       if constexpr (X3) {
-        alignas(16) uint32_t pk[3][VEC / 2];
+        // dU carries two planes (bnf_tc.cu: kDuPlanes), row layout [plane 0: W | plane 1: W]
+        alignas(16) uint32_t pk[2][VEC / 2];
 #pragma unroll
-        for (int k = 0; k < VEC; k += 2) split3_pair(du_r[k], du_r[k + 1], &pk[0][k / 2], &pk[1][k / 2], &pk[2][k / 2]);
+        for (int k = 0; k < VEC; k += 2) split2_pair(du_r[k], du_r[k + 1], &pk[0][k / 2], &pk[1][k / 2]);
+        const size_t o2 = ((size_t)net * B + b) * 2 * m.W + (size_t)cg * VEC;
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
-          *reinterpret_cast<uint4*>(dU + o3 + pl * m.W) = *reinterpret_cast<const uint4*>(pk[pl]);
+        for (int pl = 0; pl < 2; ++pl)
+          *reinterpret_cast<uint4*>(dU + o2 + pl * m.W) = *reinterpret_cast<const uint4*>(pk[pl]);
       } else {
         alignas(16) T out[VEC];
 #pragma unroll
@@ -1816,7 +1818,19 @@ void launch_map_update(const DevModel& m, float* params, float* am, float* av, f
                        __nv_bfloat16* wn, size_t w_per_net, int wn_planes, int n_net, cudaStream_t st) {
   // about one wave of resident blocks in total: every block pays one fence + one ticket atomic
   const int sms = sm_count_cached();
-  int bx = (sms * 8 + n_net - 1) / n_net;
+  // blocks per SM: a thread's fixed costs (index set-up, bias-correction hand-off, ticket) are ~250
+  // instructions against ~100 per element, so small problems take fewer, longer threads (measured,
+  // chickenpox: 8 -> 18.9 us, 4 -> 17.3 us, 2 -> 19.0 us); large ones need the parallelism to keep
+  // HBM busy (wind: 8 -> 0.98 ms, 2 -> 1.45 ms).  BNF_UPDATE_BLOCKS_PER_SM overrides.
+  static int per_sm_env = -1;
+  if (per_sm_env < 0) {
+    const char* e = getenv("BNF_UPDATE_BLOCKS_PER_SM");
+    per_sm_env = e ? atoi(e) : 0;
+    if (per_sm_env < 0 || per_sm_env > 16) per_sm_env = 0;
+  }
+  const long long total_params = (long long)m.P * n_net;
+  const int per_sm = per_sm_env ? per_sm_env : (total_params < 4LL * sms * 8 * 256 ? 4 : 8);
+  int bx = (sms * per_sm + n_net - 1) / n_net;
   const int bmax = (m.P + 255) / 256;
   if (bx > bmax) bx = bmax;
   if (bx < 1) bx = 1;

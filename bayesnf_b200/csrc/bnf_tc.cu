@@ -292,6 +292,7 @@ struct TcArgs {
   // its contiguous dimension (plane p at columns [p*pstride, (p+1)*pstride)); the reduction runs over
   // six segments of kseg k-blocks, one per plane pair (see kX3PlaneA / kX3PlaneB)
   int x3, kseg, a_pstride, b_pstride;
+  uint32_t x3_pa, x3_pb;     // nibble s = plane of A / B multiplied in segment s (k_blocks = segments * kseg)
   // Dense_0 bias gradient through the wgrad GEMM: the encoders write a constant-one feature into
   // the first pad column F (< Fp) of `feat`, so row F of the Dense_0 wgrad accumulator is
   // isf * sum_b dU_0[b, :] = the bias gradient.  TC_WGRAD (layer 0): bias_row = F, that row goes
@@ -346,6 +347,13 @@ __host__ __device__ constexpr int epi_warps_of(int mode, int /*a_mode*/) { retur
 // accumulator should be small while the many small addends arrive.  Segment s multiplies plane
 // kX3PlaneA[s] of A with plane kX3PlaneB[s] of B: (2,0) (0,2) (1,1) (1,0) (0,1) (0,0).
 constexpr uint32_t kX3PlaneA = 0x001102u, kX3PlaneB = 0x010120u;   // nibble s = plane of segment s
+// The backpropagated dU tensors carry only TWO planes (d0 + d1, residual <= 2^-18 |d|: gradients are
+// judged at 1e-4 of a leaf's scale, and a leaf is a sum over the batch of independently rounded
+// terms), which drops one of the six products and a third of the dU traffic in every backward GEMM:
+//   wgrad  (A = activations, 3 planes; B = dU, 2 planes): (2,0) (1,1) (1,0) (0,1) (0,0)
+//   dgrad  (A = dU, 2 planes; B = kernels, 3 planes):     (0,2) (1,1) (1,0) (0,1) (0,0)
+constexpr int kX3BwdSegs = 5, kDuPlanes = 2;
+constexpr uint32_t kX3WgradA = 0x00112u, kX3WgradB = 0x01010u, kX3DgradA = 0x00110u, kX3DgradB = 0x01012u;
 constexpr int kEncWarps = 4;                       // A_MODE 2 only: feature-encoder warps (one thread per tile row)
 constexpr int kEncMaxKb = 2;                       // A_MODE 2: Fp <= 128 = at most two 64-wide k-blocks
 constexpr int kEncMaxUnits = 128;                  // A_MODE 2: every unit owns >= 1 of the <= 128 feature columns
@@ -377,7 +385,7 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
   // X3: TC_FWD [z f32 4 KB | h planes 3 x 2 KB]; TC_DGRAD_ACT [z ring kZRing x 4 KB | dU planes 3 x 2 KB]
-  static constexpr int kStgWarp = X3 ? (MODE == TC_DGRAD_ACT ? 4096 * kZRing + 3 * 2048 : MODE == TC_FWD_HEAD ? 3 * 2048 : 4096 + 3 * 2048)
+  static constexpr int kStgWarp = X3 ? (MODE == TC_DGRAD_ACT ? 4096 * kZRing + kDuPlanes * 2048 : MODE == TC_FWD_HEAD ? kDuPlanes * 2048 : 4096 + 3 * 2048)
                                      : (MODE == TC_DGRAD_ACT ? 2048 * (1 + kZRing) : 4096);
   static constexpr int kEpiW = X3 ? 8 : epi_warps_of(MODE, A_MODE);
   static constexpr int kStagesBf16 = MODE == TC_DGRAD_ENC ? 2 :
@@ -536,8 +544,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (a.x3) {
             const int seg = kb / a.kseg;
             kk = kb - seg * a.kseg;
-            ca = (int)((kX3PlaneA >> (4 * seg)) & 3u) * a.a_pstride;
-            cb = (int)((kX3PlaneB >> (4 * seg)) & 3u) * a.b_pstride;
+            ca = (int)((a.x3_pa >> (4 * seg)) & 3u) * a.a_pstride;
+            cb = (int)((a.x3_pb >> (4 * seg)) & 3u) * a.b_pstride;
           }
           if (elect_one()) {
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -836,7 +844,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int ci = 0; ci < kHeadChunks; ++ci) {
             const int c = half * 32 + ci * 32 * kParts;
             if (c >= BLOCK_N) break;
-            uint32_t v[32], pk[3][16];
+            uint32_t v[32], pk[kDuPlanes][16];
             float du[32], gk[32];
             tmem_ld32(tacc + (uint32_t)c, v);
 #pragma unroll
@@ -855,14 +863,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 du[j + e] = kd * rks;
                 gk[j + e] = hh * rr;
               }
-              split3_pair(du[j], du[j + 1], &pk[0][j / 2], &pk[1][j / 2], &pk[2][j / 2]);
-              split3_pair(du[j + 2], du[j + 3], &pk[0][j / 2 + 1], &pk[1][j / 2 + 1], &pk[2][j / 2 + 1]);
+              split2_pair(du[j], du[j + 1], &pk[0][j / 2], &pk[1][j / 2]);
+              split2_pair(du[j + 2], du[j + 3], &pk[0][j / 2 + 1], &pk[1][j / 2 + 1]);
             }
-            uint8_t* stg = staging + warp * Cfg::kStgWarp;       // dU planes 3 x 2 KB
+            uint8_t* stg = staging + warp * Cfg::kStgWarp;       // dU planes 2 x 2 KB
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
 #pragma unroll
-            for (int pl = 0; pl < 3; ++pl)
+            for (int pl = 0; pl < kDuPlanes; ++pl)
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 *reinterpret_cast<uint4*>(stg + pl * 2048 + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) =
@@ -871,7 +879,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
 #pragma unroll
-              for (int pl = 0; pl < 3; ++pl) tma_store_3d(&map_o0, stg + pl * 2048, c + pl * BLOCK_N, m_t * 128 + q * 32, net);
+              for (int pl = 0; pl < kDuPlanes; ++pl) tma_store_3d(&map_o0, stg + pl * 2048, c + pl * BLOCK_N, m_t * 128 + q * 32, net);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             warp_transpose_sum(du, lane);
@@ -1216,13 +1224,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           } else {
             // ---- bf16x3 dgrad + activation backward: the f32 z tile of the chunk arrives by TMA
-            // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as three bf16 planes.
-            // Staging per warp: [z ring | dU planes 3 x 2 KB]
+            // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as two bf16 planes.
+            // Staging per warp: [z ring | dU planes 2 x 2 KB]
             uint8_t* so = staging + warp * Cfg::kStgWarp + kZRing * 4096;
             const uint32_t zsl = zc % kZRing;
             mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
             const uint8_t* zt = zring + zsl * 4096 + lane * 128;
-            uint32_t pk[3][16];
+            uint32_t pk[kDuPlanes][16];
             float du[32];
             const float cdu = a.isf * s_prev;
   #pragma unroll
@@ -1239,8 +1247,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 xg_s = fmaf(x, zz[e], xg_s);
                 du[4 * k + e] = x * cdu;
               }
-              split3_pair(du[4 * k], du[4 * k + 1], &pk[0][2 * k], &pk[1][2 * k], &pk[2][2 * k]);
-              split3_pair(du[4 * k + 2], du[4 * k + 3], &pk[0][2 * k + 1], &pk[1][2 * k + 1], &pk[2][2 * k + 1]);
+              split2_pair(du[4 * k], du[4 * k + 1], &pk[0][2 * k], &pk[1][2 * k]);
+              split2_pair(du[4 * k + 2], du[4 * k + 3], &pk[0][2 * k + 1], &pk[1][2 * k + 1]);
             }
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
@@ -1260,7 +1268,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) {
   #pragma unroll
-              for (int p = 0; p < 3; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
+              for (int p = 0; p < kDuPlanes; ++p) tma_store_3d(&map_o0, so + p * 2048, col0 + p * a.n_valid, m_t * 128 + q * 32, net);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             if (!a.skip_bias) {                       // else the Dense_0 wgrad GEMM delivers these sums
@@ -2033,6 +2041,7 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
     a.mode = TC_FWD; a.n_net = n_net;
     a.m_tiles = (B + 127) / 128; a.n_tiles = m.W / bn; a.k_splits = 1;
     a.x3 = 1; a.kseg = Kp / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W;
+    a.x3_pa = kX3PlaneA; a.x3_pb = kX3PlaneB;
     a.m_valid = B; a.n_valid = m.W;
     a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
     a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
@@ -2097,14 +2106,14 @@ int tc_fwd_head(const bnf_plan* p, const float* params, const float* derived, co
   memset(&a, 0, sizeof(a));
   a.mode = TC_FWD_HEAD; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = Kp / 64;
-  if (x3) { a.x3 = 1; a.kseg = Kp / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; }
+  if (x3) { a.x3 = 1; a.kseg = Kp / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; a.x3_pa = kX3PlaneA; a.x3_pb = kX3PlaneB; }
   a.m_valid = B; a.n_valid = m.W;
   a.params = params; a.derived = derived; a.P = m.P; a.off_bias = m.off_bias[layer]; a.layer = layer;
   a.isf = layer == 0 ? m.inv_sqrt_F : m.inv_sqrt_W;
   a.y = y; a.ll = ll; a.idx = idx; a.idx_stride = idx_stride; a.gradp = grad;
   OutMaps om;
   memset(&om, 0, sizeof(om));
-  if ((rc = make_out_map(&om.o0, dU, pl * m.W, B, n_net))) return rc;
+  if ((rc = make_out_map(&om.o0, dU, (x3 ? (uint64_t)kDuPlanes : 1) * m.W, B, n_net))) return rc;
   return launch_tc_n<3>(bn, ma, mb, om, a, sm_count_of(p), st, &m);
 }
 
@@ -2169,7 +2178,7 @@ int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* d
   const int Kp = kp_of(m, layer), bn = pick_block_n_env(Kp, "BNF_BN_DGRAD");
   if (layer < 1 || Kp > kAccCols) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad + activation backward needs W <= 1024");
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, dU, 3 * (uint64_t)m.W, B, n_net, 3 * (uint64_t)m.W, (uint64_t)B * 3 * m.W, 128);
+  int rc = make_map(&ma, dU, kDuPlanes * (uint64_t)m.W, B, n_net, kDuPlanes * (uint64_t)m.W, (uint64_t)B * kDuPlanes * m.W, 128);
   if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -2177,7 +2186,8 @@ int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* d
   a.m_tiles = (B + 127) / 128; a.n_tiles = Kp / bn; a.k_splits = 1;
   if ((rc = make_map(&mb, wn3 + 3 * layer_off(m, layer), 3 * (uint64_t)m.W, Kp, n_net, 3 * (uint64_t)m.W, 3 * tc_weight_elems(m),
                      want_cta2(a, bn) ? bn / 2 : bn))) return rc;
-  a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W;
+  a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = kX3BwdSegs * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W;
+  a.x3_pa = kX3DgradA; a.x3_pb = kX3DgradB;
   a.m_valid = B; a.n_valid = Kp;
   a.isf = m.inv_sqrt_W;
   a.zin = (const bf16*)z_prev; a.gradp = grad; a.params = params; a.derived = derived; a.P = m.P;
@@ -2187,7 +2197,7 @@ int tc_dgrad_act_x3(const bnf_plan* p, int layer, const bf16* wn3, const bf16* d
   a.out0 = out; a.out_batch = (long long)B * Kp; a.ld_out = Kp;
   OutMaps om;
   memset(&om, 0, sizeof(om));
-  if ((rc = make_out_map(&om.o0, out, 3 * (uint64_t)Kp, B, n_net))) return rc;
+  if ((rc = make_out_map(&om.o0, out, kDuPlanes * (uint64_t)Kp, B, n_net))) return rc;
   if ((rc = make_f32_map(&om.o1, z_prev, Kp, B, n_net))) return rc;
   return launch_tc_n<0>(bn, ma, mb, om, a, sm_count_of(p), st);
 }
@@ -2254,15 +2264,15 @@ int tc_dgrad0_enc(const bnf_plan* p, const bf16* wn, const bf16* dU, const float
   const int Kp = m.Fp, bn = pick_block_n(Kp);
   if (!tc_dgrad0_enc_supported(m)) return tc_fail(BNF_ERR_UNSUPPORTED, "fused dgrad0 + encode backward needs Fp <= 128");
   CUtensorMap ma, mb;
-  const uint64_t pl = x3 ? 3 : 1;     // planes side by side in every operand row
-  int rc = make_map(&ma, dU, pl * m.W, B, n_net, pl * m.W, (uint64_t)B * pl * m.W, 128);
+  const uint64_t pl = x3 ? 3 : 1, pd = x3 ? kDuPlanes : 1;     // planes side by side in a kernel / dU row
+  int rc = make_map(&ma, dU, pd * m.W, B, n_net, pd * m.W, (uint64_t)B * pd * m.W, 128);
   if (rc) return rc;
   if ((rc = make_map(&mb, wn, pl * m.W, Kp, n_net, pl * m.W, pl * tc_weight_elems(m), bn))) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_DGRAD_ENC; a.n_net = n_net;
   a.m_tiles = (B + 127) / 128; a.n_tiles = 1; a.k_splits = 1; a.k_blocks = m.W / 64;
-  if (x3) { a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = 6 * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W; }
+  if (x3) { a.x3 = 1; a.kseg = m.W / 64; a.k_blocks = kX3BwdSegs * a.kseg; a.a_pstride = m.W; a.b_pstride = m.W; a.x3_pa = kX3DgradA; a.x3_pb = kX3DgradB; }
   a.m_valid = B; a.n_valid = Kp;
   a.isf = m.inv_sqrt_F;
   a.x = x; a.idx = idx; a.idx_stride = idx_stride;
@@ -2281,13 +2291,14 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   // MN-major operands: boxes of [64 batch rows][64 contiguous features]
   int rc = make_map(&ma, a_in, pl * Kp, B, n_net, pl * Kp, (uint64_t)B * pl * Kp, 64);
   if (rc) return rc;
-  rc = make_map(&mb, dU, pl * m.W, B, n_net, pl * m.W, (uint64_t)B * pl * m.W, 64);
+  const uint64_t pd = x3 ? kDuPlanes : 1;
+  rc = make_map(&mb, dU, pd * m.W, B, n_net, pd * m.W, (uint64_t)B * pd * m.W, 64);
   if (rc) return rc;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = TC_WGRAD; a.n_net = n_net;
   a.m_tiles = (Kp + 127) / 128; a.n_tiles = m.W / bn; a.k_blocks = (B + 63) / 64;
-  if (x3) { a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = 6 * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; }
+  if (x3) { a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = kX3BwdSegs * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; a.x3_pa = kX3WgradA; a.x3_pb = kX3WgradB; }
   const int sm = sm_count_of(p);
   const bool pair = want_cta2(a, bn);
   const int slots = pair ? sm / 2 : sm;
@@ -2338,7 +2349,7 @@ int tc_debug_gemm(int mn_major, const bf16* A, const bf16* Bm, float* C, int n_n
     //   4: A [net][K][3M] MN-major, B [net][K][3N] MN-major   (wgrad)
     //   5: A [net][M][3K] K-major,  B [net][N][3K] K-major    (dgrad)
     if (K % 64 != 0 && mn_major != 4) return tc_fail(BNF_ERR_INVALID, "K must be a multiple of 64");
-    a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = 6 * a.kseg;
+    a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = 6 * a.kseg; a.x3_pa = kX3PlaneA; a.x3_pb = kX3PlaneB;
     const uint64_t M3 = 3 * (uint64_t)M, N3 = 3 * (uint64_t)N, K3 = 3 * (uint64_t)K;
     if (mn_major == 3) {
       a.a_pstride = K; a.b_pstride = N;

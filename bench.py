@@ -160,15 +160,16 @@ def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head, precision='bf16'):
   = 6 bytes, pre-activations z are f32 = 4 bytes; the FLOPs are the ALGORITHMIC f32 ones (the
   tensor cores execute six bf16 products per f32 product)."""
   if precision == 'bf16x3':
+    # feat / h: three bf16 planes (6 B), z: f32 (4 B), backpropagated dU: two bf16 planes (4 B)
     a6, a4, f6 = 6 * rows * W, 4 * rows * W, 6 * rows * Fp
     nf = L - 1 if fused_head else L          # layers run by the plain forward kernel
     return {
         'tc_gemm_fwd_x3': dict(flops=2.0 * rows * (F * W + (nf - 1) * W * W), bytes=f6 + nf * (a4 + a6) + (nf - 1) * a6),
-        'tc_fwd_head_x3': dict(flops=2.0 * rows * (W * W + W), bytes=2 * a6),          # h in, dU out (planes)
-        'head_fused': dict(flops=2.0 * rows * W, bytes=a6 + a4 + a6),                  # h, z in, dU out
-        'tc_gemm_dgrad_x3': dict(flops=2.0 * rows * (L - 1) * W * W, bytes=(L - 1) * (a6 + a4 + a6)),
-        'tc_dgrad0_enc': dict(flops=2.0 * rows * F * W, bytes=a6),
-        'tc_gemm_wgrad': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=f6 + a6 + (L - 1) * 2 * a6),
+        'tc_fwd_head_x3': dict(flops=2.0 * rows * (W * W + W), bytes=a6 + a4),          # h in, dU out
+        'head_fused': dict(flops=2.0 * rows * W, bytes=a6 + a4 + a4),                   # h, z in, dU out
+        'tc_gemm_dgrad_x3': dict(flops=2.0 * rows * (L - 1) * W * W, bytes=(L - 1) * 3 * a4),   # dU in, z in, dU out
+        'tc_dgrad0_enc': dict(flops=2.0 * rows * F * W, bytes=a4),
+        'tc_gemm_wgrad': dict(flops=2.0 * rows * (F * W + (L - 1) * W * W), bytes=f6 + a4 + (L - 1) * (a6 + a4)),
         'map_update': dict(flops=0.0, bytes=34.0 * P_total),                           # + three bf16 planes restaged
         'encode': dict(flops=0.0, bytes=float(f6)),
     }
