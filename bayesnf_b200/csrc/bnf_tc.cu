@@ -293,6 +293,7 @@ struct TcArgs {
   // six segments of kseg k-blocks, one per plane pair (see kX3PlaneA / kX3PlaneB)
   int x3, kseg, a_pstride, b_pstride;
   uint32_t x3_pa, x3_pb;     // nibble s = plane of A / B multiplied in segment s (k_blocks = segments * kseg)
+  int x3_nseg;               // > 0: segments INTERLEAVED per k-block (k-block kb = segment kb % nseg of reduction block kb / nseg)
   // Dense_0 bias gradient through the wgrad GEMM: the encoders write a constant-one feature into
   // the first pad column F (< Fp) of `feat`, so row F of the Dense_0 wgrad accumulator is
   // isf * sum_b dU_0[b, :] = the bias gradient.  TC_WGRAD (layer 0): bias_row = F, that row goes
@@ -542,8 +543,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // x3: k-block kb of the six-segment reduction = k-block kk of plane pair (pa, pb)
           int kk = kb, ca = 0, cb = 0;
           if (a.x3) {
-            const int seg = kb / a.kseg;
-            kk = kb - seg * a.kseg;
+            int seg;
+            if (a.x3_nseg > 0) { kk = kb / a.x3_nseg; seg = kb - kk * a.x3_nseg; }   // wgrad: planes of one row block back to back
+            else { seg = kb / a.kseg; kk = kb - seg * a.kseg; }
             ca = (int)((a.x3_pa >> (4 * seg)) & 3u) * a.a_pstride;
             cb = (int)((a.x3_pb >> (4 * seg)) & 3u) * a.b_pstride;
           }
@@ -2298,7 +2300,19 @@ int tc_wgrad(const bnf_plan* p, int layer, const bf16* a_in, const bf16* dU, flo
   memset(&a, 0, sizeof(a));
   a.mode = TC_WGRAD; a.n_net = n_net;
   a.m_tiles = (Kp + 127) / 128; a.n_tiles = m.W / bn; a.k_blocks = (B + 63) / 64;
-  if (x3) { a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = kX3BwdSegs * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W; a.x3_pa = kX3WgradA; a.x3_pb = kX3WgradB; }
+  if (x3) {
+    a.x3 = 1; a.kseg = a.k_blocks; a.k_blocks = kX3BwdSegs * a.kseg; a.a_pstride = Kp; a.b_pstride = m.W;
+    a.x3_pa = kX3WgradA; a.x3_pb = kX3WgradB;
+    // The reduction runs over the BATCH here: segment after segment would sweep all rows of the
+    // operand planes five times, and the planes (3 + 2 per activation pair) exceed the L2 at the
+    // benchmark shapes -- ncu: 339 MB from DRAM for 256 MB of operands.  Interleaved, the five
+    // products of one 64-row block are consecutive k-blocks, so every re-read of a plane tile hits
+    // L2.  Price: the accumulator is at full magnitude for all five products of a block (the
+    // round-toward-zero bias grows ~5x); the accumulations are short (<= 64 k-blocks per split) and
+    // gradients are judged at 1e-4.
+    const char* il = getenv("BNF_X3_WGRAD_SEGMENTED");
+    a.x3_nseg = (il && il[0] == '1') ? 0 : kX3BwdSegs;
+  }
   const int sm = sm_count_of(p);
   const bool pair = want_cta2(a, bn);
   const int slots = pair ? sm / 2 : sm;
