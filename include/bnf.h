@@ -58,11 +58,13 @@ enum {
   BNF_PREC_FP32 = 0,
   BNF_PREC_BF16 = 1,
   BNF_PREC_BF16_SIMT = 2, /* debug: bf16 storage, SIMT f32 FMA GEMMs (no tensor cores) */
-  /* f32-class arithmetic ON the tensor cores: every GEMM operand a is carried as three bf16
+  /* f32-class arithmetic ON the tensor cores: every forward GEMM operand a is carried as three bf16
    * planes a0 + a1 + a2 (|a - a0 - a1 - a2| <= 2^-27 |a|) and every f32 GEMM runs as the six
-   * tcgen05 kind::f16 products a_i.b_j, i + j <= 2, into one f32 TMEM accumulator; pre-activations
-   * stay f32 in HBM; activation math with <= 3e-7 absolute error.  Meets the 1e-5 parity bar
-   * (tests/test_gpu_parity.py) -- the default precision of the Python layer.                   */
+   * tcgen05 kind::f16 products a_i.b_j, i + j <= 2, into one f32 TMEM accumulator (smallest
+   * products first: the accumulation rounds toward zero); the backpropagated dU carries two planes
+   * (five products); pre-activations stay f32 in HBM; activation math with <= 3e-7 absolute
+   * error.  Meets the 1e-5 parity bar (tests/test_gpu_parity.py) -- the default precision of the
+   * Python layer.                                                                            */
   BNF_PREC_BF16X3 = 3
 };
 
