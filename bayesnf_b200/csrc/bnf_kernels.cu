@@ -1594,6 +1594,13 @@ static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int 
   return max_rows;
 }
 
+// rows per block of head_fused_kernel: experiment hook BNF_HEAD_FUSED_MAX_ROWS (default 512)
+static int head_fused_max_rows() {
+  const char* e = getenv("BNF_HEAD_FUSED_MAX_ROWS");
+  const int v = e ? atoi(e) : 0;
+  return (v >= 32 && v <= kHeadFusedMaxRows) ? v : kHeadFusedMaxRows;
+}
+
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,
                    int64_t idx_stride, int B, T* feat, int n_net, cudaStream_t st) {
@@ -1704,7 +1711,7 @@ bool launch_head_fused(const DevModel& m, const float* params, const float* deri
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel<T>, 256, smem);
     if (occ < 1) occ = 1;
   }
-  const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
+  const int R = balanced_rows(B, n_net, occ, 32, head_fused_max_rows());
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("head_fused", st);
   launch_k(head_fused_kernel<T>, grid, dim3(256), smem, st, m, params, derived, h, (const void*)z, y, idx, idx_stride, B, R, dU, ll, grad);
@@ -1730,7 +1737,7 @@ bool launch_head_fused_x3(const DevModel& m, const float* params, const float* d
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_fused_kernel<__nv_bfloat16, true>, 256, smem);
     if (occ < 1) occ = 1;
   }
-  const int R = balanced_rows(B, n_net, occ, 32, kHeadFusedMaxRows);
+  const int R = balanced_rows(B, n_net, occ, 32, head_fused_max_rows());
   dim3 grid((B + R - 1) / R, n_net);
   BNF_PROF("head_fused", st);
   launch_k(head_fused_kernel<__nv_bfloat16, true>, grid, dim3(256), smem, st, m, params, derived, h3, (const void*)z, y, idx,

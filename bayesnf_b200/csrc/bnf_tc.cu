@@ -1,4 +1,6 @@
-// tcgen05 GEMMs of the dense stack (bf16 operands, f32 accumulation in TMEM).
+// tcgen05 GEMMs of the dense stack (bf16 operands, f32 accumulation in TMEM) -- single-pass bf16
+// and the split-operand bf16x3 mode (f32-class accuracy: three / two bf16 planes per operand, six /
+// five products per GEMM into one accumulator; see kX3PlaneA and DESIGN.md section 3.3).
 //
 // One persistent, warp-specialised kernel template serves the GEMMs of a hidden layer
 // (models.py:263-268 forward and its jax.value_and_grad backward), one instantiation per
@@ -363,10 +365,10 @@ struct EncUnitT { float mult, k0; int kind, dim, dim2, c0, c1, pad; };        //
 constexpr int kBarBytes = kEpi16 ? 1024 : 512;     // mbarriers + TMEM base slot
 constexpr int kZRing = 2;                          // TC_DGRAD_ACT: per-warp ring of 32x32 z tiles
 constexpr int kAccCols = 1024;                     // TC_DGRAD_ACT: widest layer whose bias sums stay in smem
-// A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in smem by
-// encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B K-major;
-// 3 = A K-major, B MN-major (forward straight from the natural (in,out) bf16 kernel copy, so the
-// transposed staging copy and its cast kernel are not needed).
+// A_MODE: 0 = A,B K-major by TMA; 1 = A,B MN-major by TMA; 2 = A generated in two resident smem
+// buffers by encoder warps from the raw input rows (fused models.py:216-252 encode + Dense_0), B
+// MN-major; 3 = A K-major, B MN-major (forward straight from the natural (in,out) bf16 kernel copy,
+// so the transposed staging copy and its cast kernel are not needed).
 // CTA2: a pair of CTAs (one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2:
 // each CTA stages its own 128 A rows and HALF of the B tile, so operand traffic per FLOP
 // from L2 drops by a third and the ring gets deeper (32 KB stages).
