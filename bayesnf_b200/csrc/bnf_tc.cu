@@ -534,8 +534,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int net = t / tiles_per_net;
         int r = t % tiles_per_net;
         const int n_t = r % a.n_tiles; r /= a.n_tiles;
-        const int split = r % a.k_splits;
-        const int m_t = CTA2 ? 2 * (r / a.k_splits) + (int)cta_rank : r / a.k_splits;
+        // (the m unit varies faster than the split: the CTAs running side by side then share one
+        // block of reduction rows across all their m- and n-tiles, so wgrad's operand re-reads hit L2)
+        const int split = r / m_units;
+        const int m_t = CTA2 ? 2 * (r % m_units) + (int)cta_rank : r % m_units;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -620,7 +622,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int t = tile0; t < tile_end; t += tile_step) {
         int r = t % tiles_per_net;
         r /= a.n_tiles;
-        const int split = r % a.k_splits;
+        const int split = r / m_units;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(a.k_blocks, kb0 + kb_per_split);
         bool enc_last = false;
@@ -758,7 +760,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int net = t / tiles_per_net;
       int r = t % tiles_per_net;
       const int n_t = r % a.n_tiles; r /= a.n_tiles;
-      const int m_t = CTA2 ? 2 * (r / a.k_splits) + (int)cta_rank : r / a.k_splits;
+      const int m_t = CTA2 ? 2 * (r % m_units) + (int)cta_rank : r % m_units;
       const float* dv = a.derived ? a.derived + (size_t)net * kDerivedStride : nullptr;
       float c1 = a.isf, w_act = 0.f;
       float* sb = sbias + acc * 256;

@@ -421,3 +421,29 @@ def test_zinb_w512_l4_against_oracle(cuda, prec, ll_tol, g_tol):
       tol = g_tol * float(want.abs().max()) + floor * float(g64.abs().max()) + 1e-7
       assert float((got - want).abs().max()) <= tol, (prec, j, a, b, float((got - want).abs().max()), tol)
     assert float(grad[j, 0].abs()) == 0.0
+
+
+@pytest.mark.parametrize('width,depth,n', [(1024, 3, 300), (512, 6, 260)])
+def test_bf16x3_wide_and_deep_against_oracle(cuda, width, depth, n):
+  """The f32-parity tensor-core mode at the widest supported layer (K = 1024: 64 round-toward-zero
+  accumulation steps at full magnitude per GEMM) and at depth 6: forward <= 1e-5 of the output
+  scale, log-lik <= 2e-5, every gradient leaf <= 1e-4 of its scale vs the f64 oracle -- the same
+  bars as the small configurations."""
+  from bayesnf_b200 import inference
+  cfg = _cfg(width, depth, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 2)
+  om64 = O.OracleModel(**cfg, dtype=torch.float64)
+  eng = inference.Engine(spec, 'bf16x3')
+  loc = eng.forward(P.cuda(), xd).cpu()
+  ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+  ll, grad = ll.cpu(), grad.cpu()
+  parts = [(0, 1)] + [(o, o + (int(np.prod(s)) if s else 1)) for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+  for j in range(2):
+    want = om64.forward(om64.unflatten(P[j].double()), xd.cpu().double())
+    assert float((loc[j].double() - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-6
+    loss64, g64 = O.map_loss_and_grad(om64, P[j].double(), xd.cpu().double(), yd.cpu().double(), n, 0.0, 'NORMAL')
+    assert abs(float(ll[j]) + float(loss64)) <= 2e-5 * abs(float(loss64))
+    for a, b in parts:
+      w_, g_ = -g64[a:b], grad[j, a:b].double()
+      tol = 1e-4 * float(w_.abs().max()) + 1e-7 * float(g64.abs().max()) + 1e-7
+      assert float((g_ - w_).abs().max()) <= tol, (width, depth, j, a, b, float((g_ - w_).abs().max()), tol)
