@@ -525,11 +525,14 @@ struct StepGraphKey {
 };
 
 static void free_graph_cache(bnf_plan* p) {
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2 * bnf_plan::kGraphWays; ++k) {
     if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
     delete (StepGraphKey*)p->graph_key[k];
+    p->graph_exec[k] = p->graph_key[k] = nullptr;
+  }
+  for (int k = 0; k < 2; ++k) {
     delete (StepGraphKey*)p->last_key[k];
-    p->graph_exec[k] = p->graph_key[k] = p->last_key[k] = nullptr;
+    p->last_key[k] = nullptr;
   }
 }
 static bool pdl_scope_would_enable() {
@@ -544,10 +547,15 @@ static bool pdl_scope_would_enable() {
 template <typename F>
 static int replay_steps(const bnf_plan* p, int kind, const StepGraphKey& key, int n_steps, cudaStream_t st, F one_step) {
   bool use_graph = !prof_enabled() && !getenv("BNF_NO_GRAPH");
+  int way = -1;                     // cache entry of this call's graph
   if (use_graph) {
-    StepGraphKey* cached = (StepGraphKey*)p->graph_key[kind];
+    const int base = kind * bnf_plan::kGraphWays;
+    for (int w = 0; w < bnf_plan::kGraphWays; ++w) {
+      const StepGraphKey* c = (const StepGraphKey*)p->graph_key[base + w];
+      if (p->graph_exec[base + w] && c && *c == key) way = base + w;
+    }
     StepGraphKey* last = (StepGraphKey*)p->last_key[kind];
-    const bool hit = p->graph_exec[kind] && cached && *cached == key;
+    const bool hit = way >= 0;
     const bool seen = last && *last == key;
     if (!last) { last = new StepGraphKey(); p->last_key[kind] = last; }
     *last = key;
@@ -559,19 +567,24 @@ static int replay_steps(const bnf_plan* p, int kind, const StepGraphKey& key, in
         p->graph_stream = gs;
       }
       cudaStream_t gs = (cudaStream_t)p->graph_stream;
-      if (p->graph_exec[kind]) {
+      way = base;                                            // an empty way, else the least recently used
+      for (int w = 0; w < bnf_plan::kGraphWays; ++w) {
+        if (!p->graph_exec[base + w]) { way = base + w; break; }
+        if (p->graph_age[base + w] < p->graph_age[way]) way = base + w;
+      }
+      if (p->graph_exec[way]) {
         // the old graph may still be running on the caller's stream
         CU(cudaStreamSynchronize(st));
-        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[kind]);
-        p->graph_exec[kind] = nullptr;
+        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[way]);
+        p->graph_exec[way] = nullptr;
       }
       cudaGraph_t graph = nullptr;
       CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
       const unsigned long long before = bnf_debug_launch_count();
       const int rc = one_step(gs);
-      p->graph_launches[kind] = (long long)(bnf_debug_launch_count() - before);
+      p->graph_launches[way] = (long long)(bnf_debug_launch_count() - before);
       cudaError_t ce = cudaStreamEndCapture(gs, &graph);
-      prof_add_launches(-p->graph_launches[kind]);                 // captured, not launched
+      prof_add_launches(-p->graph_launches[way]);                 // captured, not launched
       if (rc || ce != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
@@ -582,14 +595,15 @@ static int replay_steps(const bnf_plan* p, int kind, const StepGraphKey& key, in
       ce = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
-      p->graph_exec[kind] = exec;
-      if (!cached) { cached = new StepGraphKey(); p->graph_key[kind] = cached; }
-      *cached = key;
+      p->graph_exec[way] = exec;
+      if (!p->graph_key[way]) p->graph_key[way] = new StepGraphKey();
+      *(StepGraphKey*)p->graph_key[way] = key;
     }
   }
   if (use_graph) {
-    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[kind], st));
-    prof_add_launches(p->graph_launches[kind] * n_steps);
+    p->graph_age[way] = ++p->graph_clock;
+    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[way], st));
+    prof_add_launches(p->graph_launches[way] * n_steps);
     return BNF_OK;
   }
   for (int s = 0; s < n_steps; ++s) {
@@ -647,8 +661,7 @@ static int map_steps_impl(const bnf_plan_t* p, int32_t prec, float* params, floa
   }
 
   // ---- prologue (once per call): zeroed accumulators, derived scalars, bf16 weight copies ----
-  CU(cudaMemsetAsync(w.grad, 0, (size_t)n_net * m.P * 4, st));
-  launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st, loss_slot, out_loss);
+  launch_prep(m, params, w.derived, n_net, w.ll, w.prior, slot /* + counter */, st, loss_slot, out_loss, w.grad);
   if (tc) tc_cast_weights(m, params, need_wt() ? w.wt : nullptr, w.wn, n_net, st);
   if (x3) tc_cast_weights_x3(m, params, w.wn, n_net, st);
   CUK();

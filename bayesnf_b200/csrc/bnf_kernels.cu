@@ -40,12 +40,20 @@ __device__ __forceinline__ void prep_one(const DevModel& m, const float* p, floa
 // zero_acc (optional): [ll | prior] accumulators of n_net floats each at zero_acc / zero_acc2,
 // zero_cursors (optional): two int32 cursors; loss_slot (optional): where map_update_kernel finds
 // the loss buffer of the current call -- the prologue of bnf_map_steps in one launch.
-__global__ void prep_kernel(const __grid_constant__ DevModel m, const float* params,
-                            float* __restrict__ derived, int n_net, float* zero_acc, float* zero_acc2,
-                            int32_t* zero_cursors, float** loss_slot, float* out_loss) {
-  pdl_enter(params, derived, zero_acc, zero_acc2, zero_cursors);
-  int net = blockIdx.x;
+__global__ void __launch_bounds__(256)
+prep_kernel(const __grid_constant__ DevModel m, const float* params, float* __restrict__ derived, int n_net,
+            float* zero_acc, float* zero_acc2, int32_t* zero_cursors, float** loss_slot, float* out_loss,
+            float* __restrict__ zero_rows) {
+  pdl_enter(params, derived, zero_acc, zero_acc2, zero_cursors, zero_rows);
+  const int net = blockIdx.y;
   if (net >= n_net) return;
+  // zero_rows (optional): the [n_net, P] gradient accumulator, cleared here instead of by a separate
+  // memset node (one launch less in front of every call's first step)
+  if (zero_rows) {
+    float* zr = zero_rows + (size_t)net * m.P;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.P; i += gridDim.x * blockDim.x) zr[i] = 0.f;
+  }
+  if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
     if (zero_acc) zero_acc[net] = 0.f;
     if (zero_acc2) zero_acc2[net] = 0.f;
@@ -54,7 +62,7 @@ __global__ void prep_kernel(const __grid_constant__ DevModel m, const float* par
     // cached CUDA graph of the step does not bake the caller's output buffer into its nodes
     if (net == 0 && loss_slot) *loss_slot = out_loss;
   }
-  prep_one(m, params + (size_t)net * m.P, derived + (size_t)net * kDerivedStride, threadIdx.x);
+  if (threadIdx.x < 32) prep_one(m, params + (size_t)net * m.P, derived + (size_t)net * kDerivedStride, threadIdx.x);
 }
 
 // =============================================================================
@@ -1563,14 +1571,20 @@ nb_quantile_kernel(const float* __restrict__ loc, const float* __restrict__ shap
 // host-side launch wrappers
 // =============================================================================
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, float* zero_acc,
-                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st, float** loss_slot, float* out_loss) {
+                 float* zero_acc2, int32_t* zero_cursors, cudaStream_t st, float** loss_slot, float* out_loss,
+                 float* zero_rows) {
+  int nb = 1;
+  if (zero_rows) {
+    nb = (m.P + 4095) / 4096;                 // ~16 floats per thread
+    const int cap = (148 * 8 + n_net - 1) / n_net;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+  }
   BNF_PROF("prep", st);
-  launch_k(prep_kernel, dim3(n_net), dim3(32), 0, st, m, params, derived, n_net, zero_acc, zero_acc2, zero_cursors,
-           loss_slot, out_loss);
+  launch_k(prep_kernel, dim3(nb, n_net), dim3(zero_rows ? 256 : 32), 0, st, m, params, derived, n_net, zero_acc,
+           zero_acc2, zero_cursors, loss_slot, out_loss, zero_rows);
 }
 
-// rows per block such that n_net * ceil(B / R) blocks fill a whole number of waves of
-// (SM count * blocks_per_sm) resident blocks, with min_rows <= R <= max_rows
 static int sm_count_cached() {     // per device: a process may move between GPUs
   static int sms[64] = {};
   int dev = 0;
@@ -1582,6 +1596,8 @@ static int sm_count_cached() {     // per device: a process may move between GPU
   }
   return sms[dev];
 }
+// rows per block such that n_net * ceil(B / R) blocks fill a whole number of waves of
+// (SM count * blocks_per_sm) resident blocks, with min_rows <= R <= max_rows
 static int balanced_rows(int B, int n_net, int blocks_per_sm, int min_rows, int max_rows) {
   const int sms = sm_count_cached();
   const long long slots = (long long)sms * blocks_per_sm;

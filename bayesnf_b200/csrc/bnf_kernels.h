@@ -11,7 +11,7 @@ namespace bnf {
 // two int32 cursors (the MAP prologue)
 void launch_prep(const DevModel& m, const float* params, float* derived, int n_net, float* zero_acc,
                  float* zero_acc2, int32_t* zero_cursors, cudaStream_t st, float** loss_slot = nullptr,
-                 float* out_loss = nullptr);
+                 float* out_loss = nullptr, float* zero_rows = nullptr);
 
 template <typename T>
 void launch_encode(const DevModel& m, const float* derived, const float* x, const int32_t* idx,

@@ -53,10 +53,15 @@ struct bnf_plan {
   int sm_count;
   // CUDA-graph replay of one full-batch MAP step (see bnf_map_steps); mutable
   // cache, so graph mode is single-threaded per plan.
-  // (slot 0: the MAP/MLE step, slot 1: the VI step)
+  // Cache of kGraphWays captured steps per kind (kind 0: the MAP/MLE step, 1: the VI step; entry =
+  // kind * kGraphWays + way): a caller that alternates between two input buffers (double-buffered
+  // host->device prefetch) replays both without re-capturing.  graph_age orders the ways (LRU).
+  static constexpr int kGraphWays = 2;
   mutable void* graph_stream = nullptr;   // capture stream (nothing executes on it)
-  mutable void* graph_exec[2] = {nullptr, nullptr};
-  mutable void* graph_key[2] = {nullptr, nullptr};    // StepGraphKey of graph_exec
-  mutable void* last_key[2] = {nullptr, nullptr};     // StepGraphKey of the previous replayable call
-  mutable long long graph_launches[2] = {0, 0};       // kernel nodes per replay
+  mutable void* graph_exec[2 * kGraphWays] = {};
+  mutable void* graph_key[2 * kGraphWays] = {};     // StepGraphKey of graph_exec
+  mutable void* last_key[2] = {nullptr, nullptr};   // StepGraphKey of the previous replayable call of the kind
+  mutable long long graph_launches[2 * kGraphWays] = {};   // kernel nodes per replay
+  mutable unsigned long long graph_age[2 * kGraphWays] = {};
+  mutable unsigned long long graph_clock = 0;
 };
