@@ -447,3 +447,61 @@ def test_bf16x3_wide_and_deep_against_oracle(cuda, width, depth, n):
       w_, g_ = -g64[a:b], grad[j, a:b].double()
       tol = 1e-4 * float(w_.abs().max()) + 1e-7 * float(g64.abs().max()) + 1e-7
       assert float((g_ - w_).abs().max()) <= tol, (width, depth, j, a, b, float((g_ - w_).abs().max()), tol)
+
+
+EDGE_CFGS = {
+    # one hidden layer: TC_FWD_HEAD consumes the feature planes directly, no fused dgrad at all
+    'depth1': dict(width=64, depth=1, input_scales=[99., 1, 1], num_seasonal_harmonics=[2, 3],
+                   seasonality_periods=[7.0, 30.0], fourier_degrees=[3, 2, 2], interactions=np.array([[1, 2]])),
+    # more than 64 features: Fp = 128 (two k-blocks in Dense_0, 128-wide dgrad_0 tile)
+    'wide_features': dict(width=128, depth=2, input_scales=[99., 1, 1], num_seasonal_harmonics=[10, 10],
+                          seasonality_periods=[30.0, 365.25], fourier_degrees=[9, 8, 8],
+                          interactions=np.array([[0, 1], [1, 2]])),
+    # F == Fp == 64 exactly: no pad column, so the Dense_0 bias gradient cannot ride on the wgrad GEMM
+    'no_pad_column': dict(width=64, depth=2, input_scales=[99., 1, 1], num_seasonal_harmonics=[3, 10],
+                          seasonality_periods=[7.0, 52.0], fourier_degrees=[6, 6, 5],
+                          interactions=np.array([[1, 2]])),
+}
+
+
+@pytest.mark.parametrize('prec,ll_tol,g_tol', [('bf16x3', 2e-5, 1e-4), ('bf16', 3e-2, 6e-2)])
+@pytest.mark.parametrize('rows,nets', [(1, 1), (130, 1), (257, 3)])
+@pytest.mark.parametrize('name', sorted(EDGE_CFGS))
+def test_edge_shapes_against_oracle(cuda, name, rows, nets, prec, ll_tol, g_tol):
+  """Shapes at the edges of the tensor-core kernels (a single row, one row past a tile, one network;
+  one hidden layer; 128 padded features; no pad column) in both tensor-core modes against the f64
+  oracle: forward, log-likelihood and every gradient leaf.  With Fourier degrees above the
+  reference's default 5 the f32 restatement ITSELF is up to 4e-4 away from its f64 twin on the
+  cancellation-prone log_scale_adjustment gradient (2*pi*2^d*x reaches hundreds of radians in f32),
+  so a leaf's tolerance is 1e-4 of its scale plus the f32 oracle's own distance from f64 -- measured,
+  bf16x3 then sits within 4e-6 of the f32 oracle there."""
+  from bayesnf_b200 import inference, models
+  from test_gpu_parity import _data, _random_params
+  cfg = dict(EDGE_CFGS[name], init_x=(rows, 3))
+  x, y = _data(cfg, rows)
+  om, om64 = O.OracleModel(**cfg), O.OracleModel(**cfg, dtype=torch.float64)
+  if name == 'no_pad_column':
+    assert om.F == 64
+  if name == 'wide_features':
+    assert 64 < om.F <= 128
+  P = _random_params(om, nets, y if rows > 1 else np.array([1.0, 2.0]), seed=41)
+  spec = models.ModelSpec(**cfg, observation_model='NORMAL')
+  eng = inference.Engine(spec, prec)
+  xd, yd = inference._to_device_data(x, y)
+  loc = eng.forward(P.cuda(), xd).cpu()
+  ll, grad = eng.loglik_grad(P.cuda(), xd, yd)
+  ll, grad = ll.cpu(), grad.cpu()
+  parts = [(0, 1)] + [(o, o + (int(np.prod(s)) if s else 1)) for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]
+  for j in range(nets):
+    want = om64.forward(om64.unflatten(P[j].double()), xd.cpu().double())
+    f_tol = 1e-5 if prec == 'bf16x3' else 3e-2
+    assert float((loc[j].double() - want).abs().max()) <= f_tol * float(want.abs().max()) + 1e-6, (name, rows, prec)
+    loss64, g64 = O.map_loss_and_grad(om64, P[j].double(), xd.cpu().double(), yd.cpu().double(), rows, 0.0, 'NORMAL')
+    _, g32 = O.map_loss_and_grad(om, P[j], xd.cpu(), yd.cpu(), rows, 0.0, 'NORMAL')
+    assert abs(float(ll[j]) + float(loss64)) <= ll_tol * abs(float(loss64)) + 1e-5, (name, rows, prec)
+    for a, b in parts:
+      w_, g_ = -g64[a:b], grad[j, a:b].double()
+      floor = 1e-3 * g_tol if prec == 'bf16' else 1e-7
+      f32_slack = 2.0 * float((g32[a:b].double() - g64[a:b]).abs().max())
+      tol = g_tol * float(w_.abs().max()) + floor * float(g64.abs().max()) + f32_slack + 1e-7
+      assert float((g_ - w_).abs().max()) <= tol, (name, rows, nets, prec, a, b, float((g_ - w_).abs().max()), tol)
