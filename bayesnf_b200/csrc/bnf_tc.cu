@@ -2034,7 +2034,12 @@ int tc_fwd_layer(const bnf_plan* p, int layer, const float* params, const float*
                  const bf16* wt, const bf16* wn, bf16* z, bf16* h, int n_net, int B, cudaStream_t st,
                  bool x3, float* zf) {
   const DevModel& m = p->m;
-  const int Kp = kp_of(m, layer), bn = pick_block_n_env(m.W, "BNF_BN_FWD");
+  const int Kp = kp_of(m, layer);
+  int bn = pick_block_n_env(m.W, "BNF_BN_FWD");
+  // bf16x3 Dense_0 at W = 256: the GEMM is short (K = Fp) and the epilogue writes 10 bytes per element,
+  // so the finer 128-wide tiles win (less wave quantisation: measured 62.3 -> 56.3 us, r2j-2); every
+  // other forward shape is faster with one 256-wide CTA-pair tile per row block
+  if (x3 && layer == 0 && m.W == 256 && !getenv("BNF_BN_FWD")) bn = 128;
   if (x3) {
     // split operands: a_in [n_net,B,3*Kp], wn [layer][Kp][3*W]; outputs zf [n_net,B,W] f32 (may be
     // NULL: forward only) and h [n_net,B,3*W]
