@@ -59,6 +59,13 @@ def get_default_precision() -> str:
   return _default_precision
 
 
+def precision_supported(spec: models.ModelSpec, name: str) -> bool:
+  """Whether the arithmetic mode `name` covers this model shape (`bnf_precision_supported`)."""
+  if name not in _PRECISIONS:
+    raise ValueError(f'unknown precision {name!r}')
+  return _lib.lib.bnf_precision_supported(spec.plan, _PRECISIONS[name]) == 0
+
+
 def _device() -> torch.device:
   if not torch.cuda.is_available():
     raise _lib.BnfError(

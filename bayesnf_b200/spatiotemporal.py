@@ -149,6 +149,10 @@ class BayesianNeuralFieldEstimator:
   _ensemble_dims: int
   _prior_weight: float = 1.0
   _scale_epochs_by_batch_size: bool = False
+  # Test hook: extra keyword arguments for inference.fit_map / fit_vi (init_params, batch_order,
+  # eps, ...), so that a fit can be replayed from the reference's recorded draws
+  # (tests/test_reference_goldens.py).  Empty in normal use.
+  _fit_hooks: dict = {}
 
   def __init__(
       self,
@@ -320,7 +324,8 @@ class BayesianNeuralFieldMAP(BayesianNeuralFieldEstimator):
         prior_weight=self._prior_weight,
         batch_size=batch_size,
         num_splits=num_splits,
-        precision=self.precision)
+        precision=self.precision,
+        **self._fit_hooks)
     return self
 
 
@@ -359,5 +364,6 @@ class BayesianNeuralFieldVI(BayesianNeuralFieldEstimator):
         sample_size_divergence=sample_size_divergence,
         kl_weight=kl_weight,
         batch_size=batch_size,
-        precision=self.precision)
+        precision=self.precision,
+        **self._fit_hooks)
     return self

@@ -5,16 +5,24 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` do, and only as the checker / the
 reported CPU baseline -- never as the thing shipped.
 
-PARITY UNPINNED (numerics): the reference is pure JAX/Flax/TFP/Optax and none of
-those packages is installable in the build container (no network, wheelhouse has
-no jax), so the reference itself cannot be executed here and its only numeric
-goldens (tests/test_data/bnf-*.mini.pred.csv) are skipped upstream and depend on
-JAX threefry streams.  What IS pinned (see tests/golden/ and
-tests/test_oracle_pins.py): the pure numpy/pandas bookkeeping of the reference
-executed from /root/reference by scripts/make_golden.py (seasonal frequencies,
-harmonics, data-handler outputs, parameter count, feature ordering via a
-numpy shim run of the reference's own model code) and the analytic sigma check
-on the reference's mini MAP/MLE golden predictions.
+PARITY PINNED against the reference's own code executed here.  The reference is pure
+JAX/Flax/TFP/Optax and none of those packages is installable in the build container (no
+network, wheelhouse has no jax), and its only numeric goldens
+(tests/test_data/bnf-*.mini.pred.csv) are skipped upstream and depend on JAX threefry streams.
+Instead, scripts/make_golden_numerics.py imports the reference's models.py / inference.py
+UNMODIFIED from /root/reference and executes them over oracle/jaxshim.py, a float64 stand-in for
+the third-party calls they make (array ops, vmap / scan / value_and_grad, Flax Module.param and
+Dense, optax.adam, the TFP log_prob formulas, checked against scipy).  The committed outputs
+(tests/golden/numerics_*.npz: model forward, NORMAL / NB / ZINB log-likelihoods, prior, their
+gradients, fit_map / fit_vi / predict_bnf end to end) are reproduced by this module to float64
+round-off (tests/test_reference_goldens.py), and the generator is re-run against the committed
+files whenever /root/reference is present.  What that does NOT pin: the third-party primitives
+themselves (restated in the shim from their documented behaviour) and the random streams of the
+TFP samplers (initial draws and VI noise are recorded in the goldens instead).  Also pinned (see
+tests/test_oracle_pins.py): the pure numpy/pandas bookkeeping of the reference executed from
+/root/reference by scripts/make_golden.py (seasonal frequencies, harmonics, data-handler
+outputs, parameter count, feature ordering) and the analytic sigma check on the reference's
+mini MAP/MLE golden predictions.
 
 Every function cites the reference lines it restates (paths relative to
 /root/reference).  Third-party semantics (Flax Dense, TFP log_probs,
@@ -137,10 +145,11 @@ class OracleModel:
   def seasonal_features(self, t):
     if len(self.freqs) == 0:
       return t.new_zeros(t.shape[0], 0)
-    if self.dtype == torch.float32:
-      w = torch.from_numpy(np.float32(_TWO_PI) * self.freqs.astype(np.float32))
-    else:  # float64 twin: exact-math version of the same f32 frequency table
-      w = torch.from_numpy(_TWO_PI * self.freqs.astype(np.float64))
+    # `2 * jnp.pi * frequencies` is a python float times the float32 numpy table of
+    # make_seasonal_frequencies: numpy evaluates it in float32 (weak scalar), in the reference as
+    # here; the float64 twin keeps that rounded table and is exact from there on (this is what
+    # the reference's own code gives when executed in float64, tests/golden/numerics_model_*).
+    w = torch.from_numpy(np.float32(_TWO_PI) * self.freqs.astype(np.float32))
     y = w.to(self.dtype) * t.reshape(-1, 1)          # (2*pi*f) * x, models.py:73
     feats = torch.cat([torch.cos(y), torch.sin(y)], 1)
     den = torch.from_numpy(np.tile(self.harmonics, 2)).to(self.dtype)
