@@ -33,27 +33,36 @@ _LIK_CODE = {LikelihoodDist.NORMAL: _lib.NORMAL, LikelihoodDist.NB: _lib.NB,
 
 
 def make_seasonal_frequencies(seasonality_periods, num_harmonics):
-  """Unique Fourier frequencies for the given periods and harmonics.
+  """Frequency table of the seasonal features: (frequencies, harmonic numbers).
 
-  Same contract as models.py:36-59: float32 ``h / p`` for ``h = 1..H_i``,
-  duplicates removed keeping the FIRST occurrence (in concatenation order),
-  and the harmonic index carried along.  Raises ValueError like the reference.
+  Contract of models.py:36-59, pinned bit for bit by tests/golden/bookkeeping.json: period i
+  contributes the float32 quotients ``h / p_i`` for ``h = 1 .. H_i``; a frequency that was already
+  produced by an earlier (period, harmonic) pair is dropped (a weekly 2nd harmonic and a
+  half-weekly 1st one are the same feature); the harmonic number travels with its frequency.
+  Same ValueErrors as the reference.
   """
-  periods = np.array(seasonality_periods, dtype=np.float32)
-  num_harmonics = np.asarray(num_harmonics)
-  if np.any(num_harmonics > periods / 2):
+  p = np.array(seasonality_periods, dtype=np.float32)
+  n_h = np.asarray(num_harmonics)
+  if np.any(n_h > p / 2):
     raise ValueError('Harmonic cannot exceed half seasonal period.')
-  if periods.shape != num_harmonics.shape:
+  if p.shape != n_h.shape:
     raise ValueError('Number of seasonal periods and harmonics must be equal.')
-  if len(num_harmonics.shape) != 1:
-    raise ValueError(
-        'Arguments `num_harmonics` and `seasonality_periods` must be rank 1.')
-  if periods.shape[0] == 0:
-    return (np.zeros(0), np.zeros(0))
-  per_period = [np.arange(1, h + 1, dtype=np.float32) for h in num_harmonics]
-  freqs = np.concatenate([h / p for h, p in zip(per_period, periods)])
-  first_seen = np.sort(np.unique(freqs, return_index=True)[1])
-  return freqs[first_seen], np.concatenate(per_period)[first_seen]
+  if n_h.ndim != 1:
+    raise ValueError('Arguments `num_harmonics` and `seasonality_periods` must be rank 1.')
+  if p.size == 0:
+    return np.zeros(0), np.zeros(0)
+  # one flat (harmonic, period) table instead of per-period pieces
+  counts = np.array([np.arange(1, h + 1).size for h in n_h])
+  owner = np.repeat(np.arange(p.size), counts)                  # period index of every entry
+  starts = np.cumsum(counts) - counts
+  harmonic = (np.arange(counts.sum()) - starts[owner] + 1).astype(np.float32)
+  freq = harmonic / p[owner]                                    # float32 / float32
+  seen, keep = set(), []
+  for i, bits in enumerate(freq.view(np.uint32).tolist()):      # first occurrence wins
+    if bits not in seen:
+      seen.add(bits)
+      keep.append(i)
+  return freq[keep], harmonic[keep]
 
 
 class ModelSpec:

@@ -19,65 +19,64 @@ import pandas as pd
 from . import inference
 from . import parallel
 
-_EPOCH = '2020-01-01'  # origin of the integer time index (spatiotemporal.py:101)
+_EPOCH = pd.Timestamp('2020-01-01')   # origin of the integer time index (spatiotemporal.py:101)
+
+
+def _ordinal(when, freq: str) -> int:
+  """Number of the ``freq`` period that contains ``when`` on pandas' period axis."""
+  return pd.Period(when, freq=freq).ordinal
 
 
 def seasonality_to_float(seasonality: str, freq: str) -> float:
   """Average number of ``freq`` periods per ``seasonality`` period.
 
-  Counted over the four years 2020..2023 so that leap days are averaged in, e.g.
-  ('Y','D') -> 365.25, ('M','D') -> 30.4375 (spatiotemporal.py:31-59).
+  Both are counted between the ``seasonality`` period that holds 2020-01-01 and the one that holds
+  2024-01-01 (four years, so one leap day is averaged in): ('Y', 'D') -> 365.25,
+  ('M', 'D') -> 30.4375.  Values of spatiotemporal.py:31-59, pinned by the golden table in
+  tests/golden/bookkeeping.json.
   """
-  year_starts = pd.date_range(_EPOCH, periods=5, freq='YS')
-  coarse = year_starts.to_period(seasonality)
-  n_coarse = (coarse[-1] - coarse[0]).n
-  fine = pd.date_range(coarse[0].start_time, coarse[-1].start_time).to_period(freq)
-  n_fine = (fine[-1] - fine[0]).n
-  return n_fine / n_coarse
+  first = pd.Period(_EPOCH, freq=seasonality)
+  last = pd.Period(_EPOCH + pd.DateOffset(years=4), freq=seasonality)
+  n_seasons = last.ordinal - first.ordinal
+  n_freq = _ordinal(last.start_time, freq) - _ordinal(first.start_time, freq)
+  return n_freq / n_seasons
 
 
 def seasonalities_to_array(seasonalities: Sequence[float | str], freq: str) -> np.ndarray:
-  """Periods (floats or pandas offset aliases) -> float durations in ``freq`` units.
+  """Periods given as floats or pandas offset aliases -> float durations in units of ``freq``.
 
-  Raises TypeError for anything shorter than one ``freq`` (spatiotemporal.py:62-95).
+  A period shorter than one ``freq`` is a TypeError with the reference's messages
+  (spatiotemporal.py:62-95).
   """
-  periods = []
-  for s in seasonalities:
-    if isinstance(s, str):
-      value = seasonality_to_float(s, freq)
-      if value < 1:
-        raise TypeError(
-            f'seasonality={s!r} should represent a time span greater than '
-            f'freq={freq!r}, but {s} is {value:.2f} of a {freq}')
-    else:
-      value = s
-      if value < 1:
-        raise TypeError(f'seasonality_float={value!r} should be larger than 1.')
-    periods.append(value)
-  return np.array(periods)
-
-
-def _index_time_column(table, column, timetype, freq, time_min=None):
-  """In place: datetime -> integer period index (or float), shifted to start at 0.
-
-  spatiotemporal.py:98-111.  Returns (table, time_min).
-  """
-  if timetype == 'index':
-    origin = pd.to_datetime(_EPOCH).to_period(freq)
-    as_period = table[column].dt.to_period(freq)
-    table[column] = (as_period - origin).apply(lambda delta: delta.n)
-  elif timetype == 'float':
-    table[column] = table[column].apply(float)
-  else:
-    raise ValueError(f'Unknown timetype: {timetype}')
-  if time_min is None:
-    time_min = table[column].min()
-  table[column] = table[column] - time_min
-  return table, time_min
+  def as_float(s):
+    if not isinstance(s, str):
+      if s < 1:
+        raise TypeError(f'seasonality_float={s!r} should be larger than 1.')
+      return s
+    value = seasonality_to_float(s, freq)
+    if value < 1:
+      raise TypeError(
+          f'seasonality={s!r} should represent a time span greater than '
+          f'freq={freq!r}, but {s} is {value:.2f} of a {freq}')
+    return value
+  return np.array([as_float(s) for s in seasonalities])
 
 
 class SpatiotemporalDataHandler:
-  """DataFrame -> float feature matrix (spatiotemporal.py:114-192)."""
+  """DataFrame -> feature matrix, with the reference's conventions (spatiotemporal.py:98-192):
+
+  * column 0 of ``feature_cols`` is time: ``timetype='index'`` turns datetimes into the number of
+    ``freq`` periods since 2020-01-01, ``'float'`` takes the values as they are; either way the
+    axis is shifted so that the first TRAINING time is 0 (test tables reuse that origin),
+  * rows whose target is NaN are dropped from training tables,
+  * the columns named in ``standardize`` are centred and scaled with the training mean / std,
+  * ``get_input_scales`` reports the training time span for column 0 and 1 elsewhere.
+
+  Nothing is written into the caller's DataFrame.  Outputs are equal, element for element, to the
+  reference's (tests/test_spatiotemporal.py, tests/test_reference_goldens.py).
+  """
+
+  _time_idx = 0
 
   def __init__(self, feature_cols, target_col, timetype, freq, standardize=None):
     self.feature_cols = feature_cols
@@ -91,51 +90,61 @@ class SpatiotemporalDataHandler:
     self.time_scale_ = None
 
   @property
-  def _time_idx(self) -> int:
-    return 0
-
-  @property
   def _time_column(self) -> str:
     return self.feature_cols[self._time_idx]
 
-  def _maybe_filter_target_nans(self, table: pd.DataFrame) -> pd.DataFrame:
-    if self.target_col in table.columns:
-      return table[table[self.target_col].notna()]
-    return table
+  # ---- rows ----
+  def _labelled_rows(self, table: pd.DataFrame) -> pd.DataFrame:
+    if self.target_col not in table.columns:
+      return table
+    return table.loc[table[self.target_col].notna()]
 
   def copy_and_filter_table(self, table: pd.DataFrame) -> pd.DataFrame:
-    return self._maybe_filter_target_nans(table.copy())
+    return self._labelled_rows(table).copy()
 
   def get_target(self, table: pd.DataFrame) -> np.ndarray:
-    return self._maybe_filter_target_nans(table)[self.target_col].values
+    return self._labelled_rows(table)[self.target_col].values
+
+  # ---- columns ----
+  def _raw_time(self, column: pd.Series) -> np.ndarray:
+    """Unshifted time axis of a table."""
+    if self.timetype == 'index':
+      periods = pd.PeriodIndex(column.dt.to_period(self.freq))
+      return periods.asi8 - _ordinal(_EPOCH, self.freq)
+    if self.timetype == 'float':
+      return column.to_numpy(dtype=float)
+    raise ValueError(f'Unknown timetype: {self.timetype}')
+
+  def _assemble(self, table: pd.DataFrame, time: np.ndarray) -> np.ndarray:
+    """Feature matrix with the shifted time axis in column 0 (dtype as DataFrame.values gives)."""
+    cols = {c: (time if i == self._time_idx else table[c].to_numpy())
+            for i, c in enumerate(self.feature_cols)}
+    return pd.DataFrame(cols, columns=list(self.feature_cols)).values
+
+  def _standardized(self, features: np.ndarray) -> np.ndarray:
+    return (features - self.mu_) / self.std_ if self.standardize else features
 
   def get_train(self, table: pd.DataFrame) -> np.ndarray:
-    """Training features; records time origin/scale and standardisation stats."""
-    table = self.copy_and_filter_table(table)
-    n_cols = len(self.feature_cols)
-    self.mu_, self.std_ = np.zeros(n_cols), np.ones(n_cols)
-    table, self.time_min_ = _index_time_column(
-        table, self._time_column, self.timetype, self.freq, None)
-    features = table[self.feature_cols].values
+    """Training features; fixes the time origin / span and the standardisation statistics."""
+    rows = self._labelled_rows(table)
+    time = self._raw_time(rows[self._time_column])
+    self.time_min_ = time.min()
+    features = self._assemble(rows, time - self.time_min_)
     self.time_scale_ = features[:, self._time_idx].max()
+    k = len(self.feature_cols)
+    self.mu_, self.std_ = np.zeros(k), np.ones(k)
     if self.standardize:
       if self._time_column in self.standardize:
         raise TypeError('Do not standardize the time column!')
-      cols = [self.feature_cols.index(c) for c in self.standardize]
-      block = features[:, cols].astype(float)
-      self.mu_[cols] = np.mean(block, axis=0)
-      self.std_[cols] = np.std(block, axis=0)
-      features = (features - self.mu_) / self.std_
-    return features
+      which = [self.feature_cols.index(c) for c in self.standardize]
+      block = features[:, which].astype(float)
+      self.mu_[which], self.std_[which] = block.mean(axis=0), block.std(axis=0)
+    return self._standardized(features)
 
   def get_test(self, table: pd.DataFrame) -> np.ndarray:
-    """Test features with the training origin / statistics (call after get_train)."""
-    table, _ = _index_time_column(
-        table.copy(), self._time_column, self.timetype, self.freq, self.time_min_)
-    features = table[self.feature_cols].values
-    if self.standardize:
-      features = (features - self.mu_) / self.std_
-    return features
+    """Features of a new table on the training time origin / statistics (after ``get_train``)."""
+    time = self._raw_time(table[self._time_column]) - self.time_min_
+    return self._standardized(self._assemble(table, time))
 
   def get_input_scales(self) -> np.ndarray:
     scales = np.ones(len(self.feature_cols))
