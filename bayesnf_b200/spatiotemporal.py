@@ -202,12 +202,13 @@ class BayesianNeuralFieldEstimator:
         self.feature_cols, self.target_col, self.timetype, self.freq,
         standardize=self.standardize)
 
-  # ---- kwargs -> model_args (spatiotemporal.py:296-370) ----
+  # ---- constructor keywords -> model_args (interface of spatiotemporal.py:296-370: the method
+  # names, defaults and error messages are the reference's, its tests call them directly) ----
   def _get_fourier_degrees(self, batch_shape) -> np.ndarray:
+    """One Fourier degree per input column: 5 unless given."""
     n_dims = batch_shape[-1]
-    if self.fourier_degrees is None:
-      return np.full(n_dims, 5, dtype=int)
-    degrees = np.atleast_1d(self.fourier_degrees).astype(int)
+    given = self.fourier_degrees
+    degrees = np.full(n_dims, 5, dtype=int) if given is None else np.atleast_1d(given).astype(int)
     if degrees.shape[-1] != n_dims:
       raise ValueError(
           'The length of fourier_degrees ({}) must match the input dimension '
@@ -215,52 +216,52 @@ class BayesianNeuralFieldEstimator:
     return degrees
 
   def _get_interactions(self) -> np.ndarray:
+    """(N, 2) integer column pairs; none by default."""
+    pairs = np.array([] if self.interactions is None else self.interactions).astype(int)
     if self.interactions is None:
-      return np.zeros((0, 2), dtype=int)
-    pairs = np.array(self.interactions).astype(int)
-    if np.ndim(pairs) != 2 or pairs.shape[-1] != 2:
+      pairs = pairs.reshape(0, 2)
+    if pairs.ndim != 2 or pairs.shape[-1] != 2:
       raise ValueError(
           'The argument for `interactions` should be a 2-d array of integers of '
           'shape (N, 2), indicating the column indices to interact (the passed '
           f'shape was {pairs.shape})')
     return pairs
 
-  def _get_seasonality_periods(self):
-    index_time = self.timetype == 'index'
-    if (index_time and self.freq is None) or (
-        self.timetype == 'float' and self.freq is not None):
+  def _check_time_axis(self):
+    """An integer time index needs the data frequency; a float axis must not name one."""
+    has_freq = self.freq is not None
+    if {'index': not has_freq, 'float': has_freq}.get(self.timetype, False):
       raise ValueError(f'Invalid {self.freq=} with {self.timetype=}.')
-    if self.seasonality_periods is None:
+
+  def _get_seasonality_periods(self):
+    self._check_time_axis()
+    given = self.seasonality_periods
+    if given is None:
       return np.zeros(0)
-    if index_time:
-      return seasonalities_to_array(self.seasonality_periods, self.freq)
+    assert self.timetype in ('index', 'float'), f'Impossible {self.timetype=}.'
     if self.timetype == 'float':
-      return np.asarray(self.seasonality_periods, dtype=float)
-    assert False, f'Impossible {self.timetype=}.'
+      return np.asarray(given, dtype=float)
+    return seasonalities_to_array(given, self.freq)
 
   def _get_num_seasonal_harmonics(self):
-    if self.timetype == 'index':       # discrete time: harmonics as given
-      if self.num_seasonal_harmonics is None:
-        return np.zeros(0)
-      return np.array(self.num_seasonal_harmonics)
-    if self.timetype == 'float':       # continuous time: exactly one harmonic/period
-      if self.num_seasonal_harmonics is not None:
-        raise ValueError(f'Cannot use num_seasonal_harmonics with {self.timetype=}.')
-      # any h in (0, min(.5, p/2)] yields arange(1, 1+h) == [1]  (spatiotemporal.py:351-357)
-      return np.fmin(.5, self._get_seasonality_periods() / 2)
-    assert False, f'Impossible {self.timetype=}.'
+    given = self.num_seasonal_harmonics
+    assert self.timetype in ('index', 'float'), f'Impossible {self.timetype=}.'
+    if self.timetype == 'index':        # discrete time: harmonics as given
+      return np.zeros(0) if given is None else np.array(given)
+    if given is not None:               # continuous time: exactly one harmonic per period
+      raise ValueError(f'Cannot use num_seasonal_harmonics with {self.timetype=}.')
+    # make_seasonal_frequencies builds arange(1, 1 + h): any h in (0, min(.5, p / 2)] gives [1]
+    return np.fmin(.5, self._get_seasonality_periods() / 2)
 
   def _model_args(self, batch_shape):
-    return {
-        'depth': self.depth,
-        'input_scales': self.data_handler.get_input_scales(),
-        'num_seasonal_harmonics': self._get_num_seasonal_harmonics(),
-        'seasonality_periods': self._get_seasonality_periods(),
-        'width': self.width,
-        'init_x': batch_shape,
-        'fourier_degrees': self._get_fourier_degrees(batch_shape),
-        'interactions': self._get_interactions(),
-    }
+    """The keyword set of inference.make_model for a batch of this shape."""
+    # (harmonics first: with both a float axis and harmonics given, that is the error reported)
+    seasonal = dict(num_seasonal_harmonics=self._get_num_seasonal_harmonics(),
+                    seasonality_periods=self._get_seasonality_periods())
+    features = dict(input_scales=self.data_handler.get_input_scales(),
+                    fourier_degrees=self._get_fourier_degrees(batch_shape),
+                    interactions=self._get_interactions())
+    return dict(depth=self.depth, width=self.width, init_x=batch_shape, **seasonal, **features)
 
   def predict(self, table, quantiles=(0.5,), approximate_quantiles=False):
     """Predict the target at new times / locations (spatiotemporal.py:372-408).
