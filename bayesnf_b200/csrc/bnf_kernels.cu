@@ -1002,6 +1002,213 @@ head_fused_kernel(const __grid_constant__ DevModel m, const float* __restrict__ 
 }
 
 // =============================================================================
+// head + activation backward of the last hidden layer with ONE WARP PER ROW (bf16 / bf16x3 at
+// W = 512 and 1024): a row's h stays in registers between the h.Ko dot and the Dense_L kernel
+// gradient r*h, so h, z and dU cross HBM exactly once (head_fused_kernel reads h twice, 8 instead
+// of 6 bytes per element: profiles/ncu_wind_tc_gemm_r2_summary.csv).  Lane l owns the columns
+// (j*32 + l)*8 + k (j < NC/8, k < 8) of every row, so its 2*NC column sums (bias of layer L-1,
+// Dense_L kernel) live in registers for the whole block and are flushed once.  RIF rows are in
+// flight per warp; lanes 0..RIF-1 evaluate the likelihood of one row each.
+// Same math as head_fused_kernel.
+// =============================================================================
+template <int NC, bool X3>
+__global__ void __launch_bounds__(256)
+head_rows_kernel(const __grid_constant__ DevModel m, const float* __restrict__ params,
+                 const float* __restrict__ derived, const __nv_bfloat16* __restrict__ h,
+                 const void* __restrict__ z_any, const float* __restrict__ y_all,
+                 const int32_t* __restrict__ idx, int64_t idx_stride, int B, int R /* rows per block */,
+                 __nv_bfloat16* __restrict__ dU, float* __restrict__ ll, float* __restrict__ grad) {
+  using T = __nv_bfloat16;
+  constexpr int W = NC * 32;
+  constexpr int NV = NC / 8;                          // 16-byte vectors per lane and row
+  constexpr int RIF = X3 ? 64 / NC : 128 / NC;        // rows in flight per warp (64 registers of h)
+  constexpr int NP = X3 ? 3 : 1;
+  const T* z = static_cast<const T*>(z_any);
+  const float* zf = static_cast<const float*>(z_any);
+  extern __shared__ float fsm[];
+  float* colsum = fsm;                                // [2W] bias / Dense_L kernel column sums
+  float* kos = fsm + 2 * W;                           // [W] Dense_L kernel
+  __shared__ float hred[8][8];
+  pdl_enter(params, derived, h, z, zf, y_all, idx, dU, ll, grad);
+  const int net = blockIdx.y;
+  const int b0 = blockIdx.x * R, b1 = min(B, b0 + R);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* p = params + (size_t)net * m.P;
+  const float* dv = derived + (size_t)net * kDerivedStride;
+  const float* Ko = p + m.off_kernel[m.L];
+  const float bo = p[m.off_bias[m.L]], s_out = dv[kDvSOut];
+  const int layer = m.L - 1;
+  const float w = dv[kDvActW], s_l = dv[kDvSLayer + layer];
+  const float c_head = s_out * m.inv_sqrt_W;
+  for (int i = threadIdx.x; i < 2 * W; i += 256) colsum[i] = 0.f;
+  for (int i = threadIdx.x; i < W; i += 256) kos[i] = Ko[i];
+  __syncthreads();
+  float g_b[NC], g_ko[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { g_b[c] = 0.f; g_ko[c] = 0.f; }
+  float a_ll = 0.f, a_gs = 0.f, a_gb = 0.f, g_w = 0.f, g_s = 0.f;
+  float gl3[3] = {0.f, 0.f, 0.f};
+  for (int base = b0 + warp * RIF; base < b1; base += 8 * RIF) {
+    // ---- the rows' h into registers (bf16: packed as loaded; bf16x3: the f32 sum of the planes)
+    uint4 hv[X3 ? 1 : RIF][X3 ? 1 : NV];
+    float hf[X3 ? RIF : 1][X3 ? NC : 1];
+#pragma unroll
+    for (int u = 0; u < RIF; ++u) {
+      const int b = min(base + u, b1 - 1);            // a ragged tail re-reads the last row (ignored below)
+      const T* hr = h + ((size_t)net * B + b) * NP * W;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c0 = (j * 32 + lane) * 8;
+        if constexpr (X3) {
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            alignas(16) T t8[8];
+            *reinterpret_cast<uint4*>(t8) = *reinterpret_cast<const uint4*>(hr + pl * W + c0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hf[u][j * 8 + k] = pl == 0 ? to_f<T>(t8[k]) : hf[u][j * 8 + k] + to_f<T>(t8[k]);
+          }
+        } else {
+          hv[u][j] = *reinterpret_cast<const uint4*>(hr + c0);
+        }
+      }
+    }
+    // ---- h.Ko of every row in flight
+    float dot[RIF];
+#pragma unroll
+    for (int u = 0; u < RIF; ++u) {
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c0 = (j * 32 + lane) * 8;
+        alignas(16) float kk[8];
+        *reinterpret_cast<float4*>(kk) = *reinterpret_cast<const float4*>(kos + c0);
+        *reinterpret_cast<float4*>(kk + 4) = *reinterpret_cast<const float4*>(kos + c0 + 4);
+        if constexpr (X3) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d = fmaf(hf[u][j * 8 + k], kk[k], d);
+        } else {
+          const T* t8 = reinterpret_cast<const T*>(&hv[u][j]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d = fmaf(to_f<T>(t8[k]), kk[k], d);
+        }
+      }
+      dot[u] = warp_sum(d);
+    }
+    // ---- likelihood: lane u owns row base + u
+    float mydot = 0.f;
+#pragma unroll
+    for (int u = 0; u < RIF; ++u) if (lane == u) mydot = dot[u];
+    float rr = 0.f;
+    if (lane < RIF && base + lane < b1) {
+      const int b = base + lane;
+      const float opre = mydot * m.inv_sqrt_W + bo;
+      const int64_t row = idx ? (int64_t)idx[(int64_t)net * idx_stride + b] : (int64_t)b;
+      a_ll += head_row_loglik(m.likelihood, dv, s_out * opre, y_all[row], &rr, gl3);
+      a_gs += rr * opre;
+      a_gb += rr * s_out;
+    }
+    // ---- activation backward of layer L-1, row by row, h from registers
+#pragma unroll
+    for (int u = 0; u < RIF; ++u) {
+      const int b = base + u;
+      const float rb = __shfl_sync(0xffffffffu, rr, u);
+      if (b < b1) {                                   // warp-uniform
+        const float rbs = rb * c_head;
+        const size_t orow = (size_t)net * B + b;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c0 = (j * 32 + lane) * 8;
+          float zr[8], du_r[8];
+          alignas(16) float kk[8];
+          if constexpr (X3) {
+            *reinterpret_cast<float4*>(zr) = *reinterpret_cast<const float4*>(zf + orow * W + c0);
+            *reinterpret_cast<float4*>(zr + 4) = *reinterpret_cast<const float4*>(zf + orow * W + c0 + 4);
+          } else {
+            alignas(16) T zv[8];
+            *reinterpret_cast<uint4*>(zv) = *reinterpret_cast<const uint4*>(z + orow * W + c0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) zr[k] = to_f<T>(zv[k]);
+          }
+          *reinterpret_cast<float4*>(kk) = *reinterpret_cast<const float4*>(kos + c0);
+          *reinterpret_cast<float4*>(kk + 4) = *reinterpret_cast<const float4*>(kos + c0 + 4);
+          const T* t8 = reinterpret_cast<const T*>(&hv[X3 ? 0 : u][X3 ? 0 : j]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float hh = X3 ? hf[X3 ? u : 0][X3 ? j * 8 + k : 0] : to_f<T>(t8[k]);
+            const float zz = zr[k];
+            const float dh = rbs * kk[k];
+            g_ko[j * 8 + k] = fmaf(rb, hh, g_ko[j * 8 + k]);
+            float diff, da;
+            if constexpr (X3) {
+              float unused;
+              da = act_grad_x3(zz, w, &diff, &unused);
+            } else {
+              da = act_grad_sel<true>(zz, w, &diff);
+            }
+            const float dz = dh * da;
+            g_w = fmaf(dh, diff, g_w);
+            g_s = fmaf(dz, zz, g_s);
+            const float du = dz * s_l;
+            g_b[j * 8 + k] += du;
+            du_r[k] = du;
+          }
+          if constexpr (X3) {
+            alignas(16) uint32_t pk[2][4];
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) split2_pair(du_r[k], du_r[k + 1], &pk[0][k / 2], &pk[1][k / 2]);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+              *reinterpret_cast<uint4*>(dU + orow * 2 * W + pl * W + c0) = *reinterpret_cast<const uint4*>(pk[pl]);
+          } else {
+            alignas(16) T out[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = from_f<T>(du_r[k]);
+            *reinterpret_cast<uint4*>(dU + orow * W + c0) = *reinterpret_cast<const uint4*>(out);
+          }
+        }
+      }
+    }
+  }
+  // ---- column sums: registers -> shared (8 warps) -> one global atomic per column and block
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = (j * 32 + lane) * 8 + k;
+      atomicAdd(&colsum[c], g_b[j * 8 + k]);
+      atomicAdd(&colsum[W + c], g_ko[j * 8 + k]);
+    }
+  }
+  a_ll = warp_sum(a_ll); gl3[0] = warp_sum(gl3[0]); gl3[1] = warp_sum(gl3[1]); gl3[2] = warp_sum(gl3[2]);
+  a_gs = warp_sum(a_gs); a_gb = warp_sum(a_gb); g_w = warp_sum(g_w); g_s = warp_sum(g_s);
+  if (lane == 0) {
+    hred[0][warp] = a_ll; hred[1][warp] = gl3[0]; hred[2][warp] = gl3[1]; hred[3][warp] = gl3[2];
+    hred[4][warp] = a_gs; hred[5][warp] = a_gb; hred[6][warp] = g_w; hred[7][warp] = g_s;
+  }
+  __syncthreads();
+  float* g = grad + (size_t)net * m.P;
+  for (int i = threadIdx.x; i < W; i += 256) {
+    atomicAdd(&g[m.off_bias[layer] + i], colsum[i]);
+    atomicAdd(&g[m.off_kernel[m.L] + i], colsum[W + i] * c_head);
+  }
+  if (threadIdx.x == 0) {
+    float t[8];
+    for (int k = 0; k < 8; ++k) { t[k] = 0.f; for (int i = 0; i < 8; ++i) t[k] += hred[k][i]; }
+    atomicAdd(&ll[net], t[0]);
+    if (m.likelihood == BNF_NORMAL) {
+      atomicAdd(&g[0], t[1] * expf(p[0]));
+    } else {
+      atomicAdd(&g[1], t[2] * sigmoid_f(p[1]));
+      if (m.likelihood == BNF_ZINB) { const float pi = dv[kDvPi]; atomicAdd(&g[2], t[3] * pi * (1.f - pi)); }
+    }
+    atomicAdd(&g[m.off_out_scale], t[4] * sigmoid_f(p[m.off_out_scale]));
+    atomicAdd(&g[m.off_bias[m.L]], t[5]);
+    atomicAdd(&g[m.off_actw], t[6] * w * (1.f - w));
+    atomicAdd(&g[m.off_layer_scale[layer]], (t[7] / s_l) * sigmoid_f(p[m.off_layer_scale[layer]]));
+  }
+}
+
+// =============================================================================
 // minibatch row windows drawn on the device
 //   MAP/MLE (inference.py:583-597): every member draws a fresh permutation of the n_total rows per
 //   epoch and walks it in windows of B rows (the ragged tail is dropped); VI (:704-709): one
@@ -1704,12 +1911,53 @@ template void launch_head<float>(const DevModel&, const float*, const float*, co
 template void launch_head<__nv_bfloat16>(const DevModel&, const float*, const float*, const __nv_bfloat16*, const float*, const int32_t*, int64_t, int, float*, float*, float*, float*, float*, int, cudaStream_t);
 
 // returns false when the shape does not fit the fused kernel (caller uses head + act_bwd)
+// one-warp-per-row variant (W = 512 / 1024, bf16 and bf16x3), opt-in with BNF_HEAD_ROWS=1: it moves
+// 6 instead of 8 bytes per element but is SLOWER than head_fused_kernel (air-quality 0.341 vs
+// 0.329 ms, ZINB 0.507 vs 0.394 ms, wind 2.98 vs 2.44 ms; profiles/experiments r2v) -- the kernel
+// is bound by issued instructions, not by the second read of h, and eight warps per SM at ~250
+// registers hide less latency.  Kept as the measured answer to "remove the re-read", tested in
+// tests/test_gpu_tc.py::test_head_rows_variant_agrees.
+constexpr int kHeadRowsMaxRows = 512;
+static bool head_rows_wanted(const DevModel& m) {
+  if (m.W != 512 && m.W != 1024) return false;
+  const char* e = getenv("BNF_HEAD_ROWS");
+  return e && e[0] == '1';
+}
+template <int NC, bool X3>
+static void launch_head_rows_t(const DevModel& m, const float* params, const float* derived, const __nv_bfloat16* h,
+                               const void* z, const float* y, const int32_t* idx, int64_t idx_stride, int B,
+                               __nv_bfloat16* dU, float* ll, float* grad, int n_net, cudaStream_t st) {
+  constexpr int RIF = X3 ? 64 / NC : 128 / NC;
+  const size_t smem = (size_t)3 * NC * 32 * sizeof(float);
+  static int occ = 0, dev_of = -1;
+  int dev_now = 0;
+  cudaGetDevice(&dev_now);
+  if (!occ || dev_of != dev_now) {
+    dev_of = dev_now;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, head_rows_kernel<NC, X3>, 256, smem);
+    if (occ < 1) occ = 1;
+  }
+  const char* e = getenv("BNF_HEAD_ROWS_MAX");
+  const int mx = e && atoi(e) >= 8 * RIF ? atoi(e) : kHeadRowsMaxRows;
+  const int R = balanced_rows(B, n_net, occ, 8 * RIF, mx);
+  dim3 grid((B + R - 1) / R, n_net);
+  BNF_PROF("head_fused", st);
+  launch_k(head_rows_kernel<NC, X3>, grid, dim3(256), smem, st, m, params, derived, h, z, y, idx, idx_stride, B, R, dU, ll, grad);
+}
+
 template <typename T>
 bool launch_head_fused(const DevModel& m, const float* params, const float* derived, const T* h, const T* z,
                        const float* y, const int32_t* idx, int64_t idx_stride, int B, T* dU, float* ll,
                        float* grad, int n_net, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   if (m.W % VEC != 0) return false;
+  if constexpr (sizeof(T) == 2) {
+    if (head_rows_wanted(m)) {
+      if (m.W == 512) launch_head_rows_t<16, false>(m, params, derived, h, (const void*)z, y, idx, idx_stride, B, dU, ll, grad, n_net, st);
+      else launch_head_rows_t<32, false>(m, params, derived, h, (const void*)z, y, idx, idx_stride, B, dU, ll, grad, n_net, st);
+      return true;
+    }
+  }
   const int G = m.W / VEC;
   if (G > 256 || 256 % G != 0) return false;
   const size_t smem = (size_t)(kHeadFusedMaxRows + 3 * m.W) * sizeof(float);
@@ -1741,6 +1989,11 @@ bool launch_head_fused_x3(const DevModel& m, const float* params, const float* d
                           const float* z, const float* y, const int32_t* idx, int64_t idx_stride, int B,
                           __nv_bfloat16* dU3, float* ll, float* grad, int n_net, cudaStream_t st) {
   if (!head_fused_x3_supported(m)) return false;
+  if (head_rows_wanted(m)) {
+    if (m.W == 512) launch_head_rows_t<16, true>(m, params, derived, h3, (const void*)z, y, idx, idx_stride, B, dU3, ll, grad, n_net, st);
+    else launch_head_rows_t<32, true>(m, params, derived, h3, (const void*)z, y, idx, idx_stride, B, dU3, ll, grad, n_net, st);
+    return true;
+  }
   const size_t smem = (size_t)(kHeadFusedMaxRows + 3 * m.W) * sizeof(float);
   static int occ = 0, w_of = 0, dev_of = -1;
   int dev_now = 0;

@@ -190,6 +190,30 @@ def test_alternative_kernel_paths_agree(cuda, flag, monkeypatch):
       assert float((g0[j, lo:hi] - g1[j, lo:hi]).abs().max()) <= 3e-2 * scale, (flag, lo, hi)
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'bf16x3'])
+@pytest.mark.parametrize('dist', ['NORMAL', 'ZINB'])
+def test_head_rows_variant_agrees(cuda, monkeypatch, dist, prec):
+  """BNF_HEAD_ROWS=1 (head + activation backward with one warp per row, h read once) computes what
+  head_fused_kernel computes, on a ragged row count (W = 512; opt-in because it is slower)."""
+  from bayesnf_b200 import inference
+  n = 1237
+  cfg = _cfg(512, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3, dist)
+  eng = inference.Engine(spec, prec)
+  monkeypatch.delenv('BNF_HEAD_ROWS', raising=False)
+  ll0, g0 = eng.loglik_grad(P.cuda(), xd, yd)
+  monkeypatch.setenv('BNF_HEAD_ROWS', '1')
+  ll1, g1 = eng.loglik_grad(P.cuda(), xd, yd)
+  tol = 2e-5 if prec == 'bf16x3' else 5e-3
+  assert float(((ll0 - ll1) / ll0).abs().max()) <= tol
+  g0, g1 = g0.cpu(), g1.cpu()
+  for j in range(3):
+    for lo, hi in [(0, 3)] + [(o, o + (int(np.prod(s)) if s else 1))
+                              for o, s in zip(spec.leaf_offsets, spec.leaf_shapes)]:
+      scale = float(g0[j, lo:hi].abs().max()) + 1e-3 * float(g0[j].abs().max())
+      assert float((g0[j, lo:hi] - g1[j, lo:hi]).abs().max()) <= (1e-4 if prec == 'bf16x3' else 3e-2) * scale, (lo, hi)
+
+
 def test_fused_head_matches_two_kernel_path(cuda, monkeypatch):
   """head_fused_kernel == head_kernel + act_bwd (fp32 mode: tight tolerance)."""
   from bayesnf_b200 import inference
