@@ -147,10 +147,17 @@ class ClockSampler(threading.Thread):
             'reasons': sorted(self.reasons)}
 
 
-NCU_SUMMARY = {'chickenpox_map_e8': 'ncu_chickenpox_r1u_summary.csv', 'wind_map_e16': 'ncu_wind_tc_gemm_r1u_summary.csv'}
-# kernel class -> template-argument substrings <BLOCK_N, A_MODE, MODE, CTA2> of its instantiations
-NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, ', ', 0, 0, '), 'tc_gemm_dgrad': (', 0, 5, ',), 'tc_gemm_wgrad': (', 1, 3, ',),
-               'tc_fwd_head': (', 3, 7, ',), 'tc_dgrad0_enc': (', 0, 6, ',)}
+# committed `ncu --set full` summaries of the same commands (profiles/), per (workload, precision)
+NCU_SUMMARY = {('chickenpox_map_e8', 'bf16'): 'ncu_chickenpox_bf16_r2_summary.csv',
+               ('chickenpox_map_e8', 'bf16x3'): 'ncu_chickenpox_bf16x3_r2_summary.csv',
+               ('wind_map_e16', 'bf16'): 'ncu_wind_tc_gemm_r2_summary.csv',
+               ('wind_map_e16', 'bf16x3'): 'ncu_wind_tc_gemm_bf16x3_r2_summary.csv'}
+# kernel class -> template-argument substrings <BLOCK_N, A_MODE, MODE, CTA2, X3> of its instantiations
+NCU_PATTERN = {'tc_gemm_fwd': (', 3, 0, 1, 0>', ', 3, 0, 0, 0>', ', 0, 0, 1, 0>', ', 0, 0, 0, 0>'),
+               'tc_gemm_dgrad': (', 0, 5, 1, 0>', ', 0, 5, 0, 0>'), 'tc_gemm_wgrad': (', 1, 3, ',),
+               'tc_fwd_head': (', 3, 7, 1, 0>', ', 3, 7, 0, 0>'), 'tc_dgrad0_enc': (', 0, 6, ',),
+               'tc_gemm_fwd_x3': (', 3, 0, 1, 1>', ', 3, 0, 0, 1>'), 'tc_fwd_head_x3': (', 3, 7, 1, 1>', ', 3, 7, 0, 1>'),
+               'tc_gemm_dgrad_x3': (', 0, 5, 1, 1>', ', 0, 5, 0, 1>')}
 
 
 def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head, precision='bf16'):
@@ -188,11 +195,11 @@ def algorithmic_work(rows, F, Fp, W, L, P_total, fused_head, precision='bf16'):
   }
 
 
-def ncu_traffic_gb(workload, kernel):
+def ncu_traffic_gb(workload, kernel, precision='bf16'):
   """DRAM bytes (read+write) per launch of `kernel` from the committed `ncu --set full` summary
   of the same workload (profiles/), or None."""
   import csv
-  path = os.path.join(ROOT, 'profiles', NCU_SUMMARY.get(workload, ''))
+  path = os.path.join(ROOT, 'profiles', NCU_SUMMARY.get((workload, precision), ''))
   if not os.path.isfile(path) or kernel not in NCU_PATTERN:
     return None
   rows = list(csv.reader(open(path)))
@@ -501,7 +508,7 @@ def run_workload(args, workload, precision, steps, warmup, env, do_e2e=True, do_
       avg_ms = d['ms_per_step'] / n_l
       t_tensor = wk['flops'] / (pk['tflops_sustained'] * 1e12)
       t_hbm = wk['bytes'] / (pk['hbm_gbs'] * 1e9)
-      traffic = ncu_traffic_gb(workload, best) if precision == 'bf16' else None
+      traffic = ncu_traffic_gb(workload, best, precision)
       if t_tensor >= t_hbm:
         ach, peak, unit, bound = d['tflops'], pk['tflops_sustained'], 'TFLOP/s', 'tensor'
       else:
