@@ -25,7 +25,10 @@ BNF_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control 
 BNF_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 32 --csv --log-file $O/launches_chickenpox_bf16x3_r2.csv python bench.py --precision bf16x3 --steps 5 --warmup 3 --repeats 3 $B > $O/l2.log 2>&1
 BNF_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -s 64 -c 8 -o $O/ncu_chickenpox_bf16_r2 python bench.py --steps 5 --warmup 3 --repeats 3 $B > $O/n1.log 2>&1
 BNF_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none --import-source on -s 64 -c 8 -o $O/ncu_chickenpox_bf16x3_r2 python bench.py --precision bf16x3 --steps 5 --warmup 3 --repeats 3 $B > $O/n2.log 2>&1
-for n in ncu_chickenpox_bf16_r2 ncu_chickenpox_bf16x3_r2; do
+# head + activation backward at W = 512: the default kernel and the one-warp-per-row variant (r2v)
+BNF_NO_GRAPH=1 timeout 600 ncu --set full --clock-control none -k regex:'head_fused_kernel' -s 3 -c 1 -o $O/ncu_aq_head_fused_r2 python bench.py --workload air_quality_map_e8 --steps 3 --warmup 3 --repeats 3 $B > $O/n3.log 2>&1
+BNF_NO_GRAPH=1 BNF_HEAD_ROWS=1 timeout 600 ncu --set full --clock-control none -k regex:'head_rows_kernel' -s 3 -c 1 -o $O/ncu_aq_head_rows_r2 python bench.py --workload air_quality_map_e8 --steps 3 --warmup 3 --repeats 3 $B > $O/n4.log 2>&1
+for n in ncu_chickenpox_bf16_r2 ncu_chickenpox_bf16x3_r2 ncu_aq_head_fused_r2 ncu_aq_head_rows_r2; do
   python scripts/ncu_summary.py $O/$n.ncu-rep $O/${n}_summary.csv
 done
 rm -f $O/*.ncu-rep
