@@ -41,6 +41,7 @@ ALGORITHM; float32 rounding is judged by the tolerances the parity tests state.
 
 from __future__ import annotations
 
+import collections
 import math
 import operator
 import sys
@@ -810,10 +811,16 @@ class JointDistributionCoroutine(Distribution):
     from bayesnf_b200 import jax_prng
     counter = [jax_prng.prng_key(0) if seed is None else _key(seed)]
 
+    names = []
+
     def visit(i, d):
       counter[0], sub = jax_prng.split(counter[0], 2)
+      names.append(d.name or f'var{i}')
       return d.sample(sample_shape, seed=sub)
-    return tuple(self._walk(visit))
+    values = self._walk(visit)
+    # TFP returns a StructTuple (a namedtuple keyed by the component names); the reference relies on
+    # `_fields` / `_replace` (spatiotemporal.py:459-462)
+    return collections.namedtuple('StructTuple', names)(*values)
 
   def sample_with(self, eps):
     """Reparameterised draw of a surrogate of Normals from given standard-normal tensors."""

@@ -318,6 +318,13 @@ def gen_estimator(kind):
       feature_cols=dc['feature_cols'], target_col=dc['target_col'], timetype=dc['timetype'],
       freq=dc['freq'], standardize=dc['standardize'],
       **{k: (np.asarray(v).tolist() if not isinstance(v, (int, str)) else v) for k, v in mc.items()}))
+  # likelihood_model(table): the predictive distribution object (spatiotemporal.py:433-468)
+  y_test = test[dc['target_col']].to_numpy(dtype=np.float64)
+  lm = est.likelihood_model(test)
+  out['y_test'] = y_test
+  out['lm_log_prob'] = np.asarray(lm.log_prob(A(y_test)))
+  out['lm_loc'] = np.asarray(lm.distribution.loc)
+  out['lm_scale'] = np.asarray(lm.distribution.scale)
   for approx in (True, False):
     means, quants = est.predict(test, quantiles=qs, approximate_quantiles=approx)
     out['means'] = np.asarray(means)

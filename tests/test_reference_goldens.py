@@ -249,6 +249,10 @@ def test_oracle_estimator_fit_predict_against_reference_execution(kind):
     finals.append(p)
   P = torch.stack(finals)
   xt = _t(g['x_test'])
+  # likelihood_model(test).log_prob(y_test): one log-likelihood per member (spatiotemporal.py:433-468)
+  for m in range(P.shape[0]):
+    ll = O.log_likelihood(om, om.unflatten(P[m]), xt, _t(g['y_test']), 'NORMAL')
+    assert abs(float(ll) - g['lm_log_prob'][0, m]) <= 1e-9 * abs(g['lm_log_prob'][0, m])
   means = torch.stack([om.forward(om.unflatten(P[m]), xt) for m in range(P.shape[0])])
   scales = (0.01 + torch.exp(P[:, 0]))[:, None]
   assert _relmax(means, g['means'][0]) <= 1e-9
@@ -492,6 +496,11 @@ def test_cuda_estimator_against_reference_execution(cuda, kind, prec):
     live[k0 + r * args['width']:k0 + (r + 1) * args['width']] = False
   assert np.quantile(d[..., live], 0.995) <= 2e-4, np.quantile(d[..., live], 0.995)
   scale = np.abs(g['means']).max()
+  lm = est.likelihood_model(test)
+  assert tuple(lm.batch_shape) == g['lm_log_prob'].shape and tuple(lm.event_shape) == (len(test),)
+  np.testing.assert_allclose(lm.log_prob(g['y_test']), g['lm_log_prob'], rtol=2e-3)
+  np.testing.assert_allclose(lm.distribution.scale, np.broadcast_to(g['lm_scale'], np.shape(lm.distribution.scale)), rtol=2e-3)
+  assert np.abs(lm.distribution.loc - g['lm_loc']).max() <= 2e-3 * scale
   for approx, key in ((True, 'q_approx'), (False, 'q_root')):
     means, quants = est.predict(test, quantiles=tuple(g['quantiles']), approximate_quantiles=approx)
     assert np.asarray(means).shape == g['means'].shape
