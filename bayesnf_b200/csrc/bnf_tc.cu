@@ -1392,6 +1392,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n_t * BLOCK_N + c;
+        if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 11);       // first chunk: accumulator in registers
         if (MODE == TC_FWD) {
           uint32_t zp[16], hp[16];
           const ActConst2 ak(w_act);
@@ -1411,8 +1412,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // full 64-byte rows leave the SM as bulk writes instead of 32 scattered
           // 16-byte stores per instruction; rows >= B are clipped by the tensor map.
           uint8_t* stg = staging + warp * Cfg::kStgWarp;
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 12);     // math done
           if (lane == 0 && !DBG(4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 13);     // staging tile free
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int off = lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4);
@@ -1427,6 +1430,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (a.out0) tma_store_3d(&map_o0, stg + 2048, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 14);     // stores issued
         } else if (MODE == TC_DGRAD_ACT) {
           // dh = acc/sqrt(fan_in); dz = dh*act'(z); dU = s*dz; plus the reductions that the
           // separate act_bwd kernel used to do (bias column sums, activation-mix and
@@ -1467,8 +1471,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             pk[j >> 1] = f2_to_bf16x2(du2);
           }
           uint8_t* stg = staging + warp * Cfg::kStgWarp;
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 12);     // math done
           if (lane == 0 && !DBG(4)) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 13);     // staging tile free
           // every lane holds its z values in registers: refill the slot with the tile kZRing ahead
           if (lane == 0 && c + 32 * kParts * kZRing < BLOCK_N && !DBG(1)) {
             mbar_arrive_expect_tx(&zb[zsl], 2048);
@@ -1485,6 +1491,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_store_3d(&map_o0, stg, col0, m_t * 128 + q * 32, net);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (epi_tid == 0 && c == 0) TL((t - tile0) / tile_step, 14);     // store issued
           if (DBG(2) || a.skip_bias) continue;      // skip_bias: the Dense_0 wgrad GEMM delivers these sums
           // bias gradient: column sums over this warp's 32 rows by a transpose-reduce (31
           // shuffles; lane L ends up with column L), added to the CTA's shared-memory partial
@@ -1925,7 +1932,7 @@ static int launch_tc_k(const CUtensorMap& ma, const CUtensorMap& mb, const OutMa
         const long long t0 = h[(c * 16 + 0) * 16 + 15];
         for (int ti = 0; ti < 6; ++ti) {
           fprintf(stderr, "TL mode %d cta %3d tile %d:", MODE, c, ti);
-          for (int ev = 0; ev < 11; ++ev) {
+          for (int ev = 0; ev < 15; ++ev) {
             const long long v = h[(c * 16 + ti) * 16 + ev];
             fprintf(stderr, " %7lld", v ? v - t0 : -1);
           }

@@ -23,7 +23,7 @@ def main():
   x, y, margs = bench.synth(wl)
   dev = torch.device('cuda', 0)
   spec = models.ModelSpec(**margs, observation_model='NORMAL')
-  eng = inference.Engine(spec, 'bf16')
+  eng = inference.Engine(spec, os.environ.get('PREC', 'bf16'))
   E, n_total = wl['members_per_gpu'], len(y)
   B = wl['batch'] or n_total
   xd, yd = inference._to_device_data(x, y)
@@ -55,9 +55,11 @@ def main():
     for line in buf.value.decode().strip().splitlines():
       name, cnt, tot = line.split()
       d[name] = float(tot) / k
-    print('%s mask %2d  fwd %.3f  dgrad %.3f  wgrad %.3f  total %.3f ms/step' % (
+    print('%s mask %2d  fwd %.4f  dgrad %.4f  wgrad %.4f  total %.4f ms/step' % (
         os.environ.get('TAG', ''), mask, d.get('tc_gemm_fwd', 0), d.get('tc_gemm_dgrad', 0),
         d.get('tc_gemm_wgrad', 0), sum(d.values())), flush=True)
+    if os.environ.get('ALL_KERNELS'):
+      print('   ', '  '.join('%s %.4f' % kv for kv in sorted(d.items())), flush=True)
 
 
 if __name__ == '__main__':
