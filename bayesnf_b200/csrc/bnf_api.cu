@@ -527,8 +527,9 @@ struct StepGraphKey {
 static void free_graph_cache(bnf_plan* p) {
   for (int k = 0; k < 2 * bnf_plan::kGraphWays; ++k) {
     if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+    if (p->graph_exec_multi[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec_multi[k]);
     delete (StepGraphKey*)p->graph_key[k];
-    p->graph_exec[k] = p->graph_key[k] = nullptr;
+    p->graph_exec[k] = p->graph_exec_multi[k] = p->graph_key[k] = nullptr;
   }
   for (int k = 0; k < 2; ++k) {
     delete (StepGraphKey*)p->last_key[k];
@@ -538,6 +539,45 @@ static void free_graph_cache(bnf_plan* p) {
 static bool pdl_scope_would_enable() {
   const char* e = getenv("BNF_PDL");
   return !(e && e[0] == '0');
+}
+
+// Steps per launch of the unrolled step graph (BNF_GRAPH_UNROLL; 1 = one graph launch per step).
+static int graph_unroll() {
+  const char* e = getenv("BNF_GRAPH_UNROLL");
+  int u = e ? atoi(e) : 8;
+  return u < 1 ? 1 : (u > 64 ? 64 : u);
+}
+
+// Captures `reps` consecutive steps on the plan's capture stream and instantiates the graph.
+template <typename F>
+static int capture_steps(const bnf_plan* p, int reps, F& one_step, cudaGraphExec_t* out, long long* launches_per_step) {
+  if (!p->graph_stream) {
+    cudaStream_t gs;
+    CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+    p->graph_stream = gs;
+  }
+  cudaStream_t gs = (cudaStream_t)p->graph_stream;
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+  const unsigned long long before = bnf_debug_launch_count();
+  int rc = 0;
+  for (int r = 0; r < reps && !rc; ++r) rc = one_step(gs);
+  const long long captured = (long long)(bnf_debug_launch_count() - before);
+  cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+  prof_add_launches(-captured);                                   // captured, not launched
+  if (rc || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc) return rc;
+    return fail(BNF_ERR_CUDA, "CUDA graph capture of the training step failed (%s)", cudaGetErrorString(ce));
+  }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+  *out = exec;
+  if (launches_per_step) *launches_per_step = captured / reps;
+  return BNF_OK;
 }
 
 // Replays `one_step` n_steps times on `st`: as a cached CUDA graph (slot `kind`: 0 MAP, 1 VI) when
@@ -561,48 +601,50 @@ static int replay_steps(const bnf_plan* p, int kind, const StepGraphKey& key, in
     *last = key;
     if (!hit && n_steps < 4 && !seen) use_graph = false;     // not worth a capture yet
     if (use_graph && !hit) {
-      if (!p->graph_stream) {
-        cudaStream_t gs;
-        CU(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
-        p->graph_stream = gs;
-      }
-      cudaStream_t gs = (cudaStream_t)p->graph_stream;
       way = base;                                            // an empty way, else the least recently used
       for (int w = 0; w < bnf_plan::kGraphWays; ++w) {
         if (!p->graph_exec[base + w]) { way = base + w; break; }
         if (p->graph_age[base + w] < p->graph_age[way]) way = base + w;
       }
       if (p->graph_exec[way]) {
-        // the old graph may still be running on the caller's stream
+        // the old graphs may still be running on the caller's stream
         CU(cudaStreamSynchronize(st));
         cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[way]);
-        p->graph_exec[way] = nullptr;
-      }
-      cudaGraph_t graph = nullptr;
-      CU(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
-      const unsigned long long before = bnf_debug_launch_count();
-      const int rc = one_step(gs);
-      p->graph_launches[way] = (long long)(bnf_debug_launch_count() - before);
-      cudaError_t ce = cudaStreamEndCapture(gs, &graph);
-      prof_add_launches(-p->graph_launches[way]);                 // captured, not launched
-      if (rc || ce != cudaSuccess || !graph) {
-        if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        if (rc) return rc;
-        return fail(BNF_ERR_CUDA, "CUDA graph capture of the training step failed (%s)", cudaGetErrorString(ce));
+        if (p->graph_exec_multi[way]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec_multi[way]);
+        p->graph_exec[way] = p->graph_exec_multi[way] = nullptr;
       }
       cudaGraphExec_t exec = nullptr;
-      ce = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) return fail(BNF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      const int rc = capture_steps(p, 1, one_step, &exec, &p->graph_launches[way]);
+      if (rc) return rc;
       p->graph_exec[way] = exec;
       if (!p->graph_key[way]) p->graph_key[way] = new StepGraphKey();
       *(StepGraphKey*)p->graph_key[way] = key;
     }
+    // long calls: the step captured `unroll` times back to back, one launch per `unroll` steps
+    // (no graph-launch boundary and an unbroken programmatic-dependent-launch chain between the
+    // fused update of one step and the first kernel of the next)
+    const int unroll = graph_unroll();
+    if (use_graph && unroll > 1 && n_steps >= 2 * unroll &&
+        (!p->graph_exec_multi[way] || p->graph_multi_steps[way] != unroll)) {
+      if (p->graph_exec_multi[way]) {
+        CU(cudaStreamSynchronize(st));
+        cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec_multi[way]);
+        p->graph_exec_multi[way] = nullptr;
+      }
+      cudaGraphExec_t exec = nullptr;
+      const int rc = capture_steps(p, unroll, one_step, &exec, nullptr);
+      if (rc) return rc;
+      p->graph_exec_multi[way] = exec;
+      p->graph_multi_steps[way] = unroll;
+    }
   }
   if (use_graph) {
     p->graph_age[way] = ++p->graph_clock;
-    for (int s = 0; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[way], st));
+    int s = 0;
+    const int ms = p->graph_exec_multi[way] ? p->graph_multi_steps[way] : 0;
+    if (ms > 1 && ms == graph_unroll())
+      for (; s + ms <= n_steps; s += ms) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec_multi[way], st));
+    for (; s < n_steps; ++s) CU(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[way], st));
     prof_add_launches(p->graph_launches[way] * n_steps);
     return BNF_OK;
   }

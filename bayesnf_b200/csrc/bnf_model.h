@@ -60,6 +60,10 @@ struct bnf_plan {
   mutable void* graph_stream = nullptr;   // capture stream (nothing executes on it)
   mutable void* graph_exec[2 * kGraphWays] = {};
   mutable void* graph_key[2 * kGraphWays] = {};     // StepGraphKey of graph_exec
+  // the same step captured kGraphUnroll times back to back (one launch = several steps: the
+  // programmatic-dependent-launch chain then also spans the step boundary); built on demand
+  mutable void* graph_exec_multi[2 * kGraphWays] = {};
+  mutable int graph_multi_steps[2 * kGraphWays] = {};
   mutable void* last_key[2] = {nullptr, nullptr};   // StepGraphKey of the previous replayable call of the kind
   mutable long long graph_launches[2 * kGraphWays] = {};   // kernel nodes per replay
   mutable unsigned long long graph_age[2 * kGraphWays] = {};

@@ -469,7 +469,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* rowdot = kos_s + 2 * 256;                   // TC_FWD_HEAD: [kParts][128] partial h.Ko of the quarter's warps
   float* sxt = gtile + 128 * (BLOCK_N + 1);          // TC_DGRAD_ENC: [2][128][kMaxD+1] scaled inputs + raw time
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index through a shuffle: the compiler then knows it (and every address / coordinate
+  // derived from it) is warp-uniform, so the TMA / mbarrier instructions take uniform-register
+  // operands directly instead of a per-lane R2UR loop in front of every one of them
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   pdl_trigger();                       // the next kernel's CTAs may start their own prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -1156,11 +1159,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         w_act = p_wact;
         s_prev = p_sprev;
         cdu2 = f2_dup(a.isf * s_prev);
+        const uint32_t zc_u = __shfl_sync(0xffffffffu, zc, 0);   // (warp-uniform for the compiler: see `warp`)
         if (lane == 0 && !DBG(1)) {
 #pragma unroll
           for (int i = 0; i < kZRing; ++i) {
             if (half * 32 + 32 * kParts * i >= BLOCK_N) break;
-            const uint32_t sl = (zc + i) % kZRing;
+            const uint32_t sl = (zc_u + i) % kZRing;
             mbar_arrive_expect_tx(&zb[sl], kZSlot);
             tma_load_3d(zring + sl * kZSlot, &map_o1, &zb[sl], n_t * BLOCK_N + half * 32 + 32 * kParts * i, m_t * 128 + q * 32, net);
           }
@@ -1233,7 +1237,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // (ring of kZRing 4 KB slots, 128B swizzle); dU leaves as two bf16 planes.
             // Staging per warp: [z ring | dU planes 2 x 2 KB]
             uint8_t* so = staging + warp * Cfg::kStgWarp + kZRing * 4096;
-            const uint32_t zsl = zc % kZRing;
+            const uint32_t zsl = __shfl_sync(0xffffffffu, zc, 0) % kZRing;
             mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
             const uint8_t* zt = zring + zsl * 4096 + lane * 128;
             uint32_t pk[kDuPlanes][16];
@@ -1337,7 +1341,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           } else {
-            const uint32_t zsl = zc % kZRing;
+            const uint32_t zsl = __shfl_sync(0xffffffffu, zc, 0) % kZRing;
             mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
             const uint8_t* zt = zring + zsl * 2048 + lane * 64;
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1436,7 +1440,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // separate act_bwd kernel used to do (bias column sums, activation-mix and
           // layer-scale scalars).  models.py:255-268 backward.
           uint32_t zw[16];
-          const uint32_t zsl = zc % kZRing;
+          const uint32_t zsl = __shfl_sync(0xffffffffu, zc, 0) % kZRing;
           if (!DBG(1)) {
             mbar_wait(&zb[zsl], (zc / kZRing) & 1u);
             const uint8_t* zt = zring + zsl * 2048 + lane * 64;

@@ -603,13 +603,14 @@ def test_vi_five_steps_with_subbatch_against_oracle(cuda):
       assert float(torch.quantile(dr, 0.995)) <= 1e-4 and float(dr.max()) <= 2 * steps * lr
 
 
-def test_vi_device_steps_graph_equals_direct_launches(cuda, monkeypatch):
+@pytest.mark.parametrize('steps', [6, 19])
+def test_vi_device_steps_graph_equals_direct_launches(cuda, monkeypatch, steps):
   """bnf_vi_steps (eps + per-step sub-batch drawn on the device, one CUDA graph replayed) is
   deterministic in its seed and equals the same call issued as direct launches, and -- split
   into single-step calls -- the same sequence (device-side step counters)."""
   from bayesnf_b200 import inference, models
   cfg = _cfgs()['small']
-  n, B, S, E, steps = 200, 96, 4, 3, 6
+  n, B, S, E = 200, 96, 4, 3           # 19 steps: two unrolled graph launches (8 steps each) + three single
   x, y = _data(cfg, n)
   spec = models.ModelSpec(**cfg)
   eng = inference.Engine(spec, 'fp32')
@@ -632,8 +633,12 @@ def test_vi_device_steps_graph_equals_direct_launches(cuda, monkeypatch):
   d = run([1] * steps)
   assert np.isfinite(a[0]).all() and a[0].shape == (steps, E)
   for other in (b, c, d):
-    np.testing.assert_allclose(a[0], other[0], rtol=2e-5)          # f32 atomics reorder sums
-    assert float(np.abs(a[1] - other[1]).max()) <= 2e-4 and float(np.abs(a[2] - other[2]).max()) <= 2e-4
+    np.testing.assert_allclose(a[0], other[0], rtol=2e-5 * max(1, steps // 6))    # f32 atomics reorder sums
+    for k in (1, 2):
+      diff = np.abs(a[k] - other[k])
+      # (Adam normalises the step: over many steps an entry whose gradient is summation noise may
+      # walk the other way; everything else stays together)
+      assert float(np.quantile(diff, 0.995)) <= 2e-4 and float(diff.max()) <= (2e-4 if steps <= 6 else 2 * steps * 0.01)
   assert a[0][-1].mean() < a[0][0].mean()                          # the ELBO loss goes down
 
 

@@ -346,6 +346,43 @@ def test_fused_step_variants_agree(cuda, monkeypatch, flag, val):
   assert float(np.quantile(np.abs(f0 - f1), 0.999)) <= 2e-3
 
 
+@pytest.mark.parametrize('prec', ['bf16x3', 'bf16', 'fp32'])
+def test_unrolled_step_graph_equals_single_step_graph(cuda, monkeypatch, prec):
+  """Long calls replay the step captured BNF_GRAPH_UNROLL (default 8) times per graph launch, so the
+  programmatic-dependent-launch chain also spans the step boundary (fused update of step s -> first
+  kernel of step s+1).  Device-drawn minibatches (the batch window is keyed by the device-side step
+  count), 21 steps = two unrolled launches + five single-step launches: same losses and parameters
+  as one graph launch per step, as direct launches, and as another unroll factor."""
+  from bayesnf_b200 import inference
+  n, B, epochs = 1500, 500, 7
+  steps = epochs * (n // B)                       # 21
+  cfg = _cfg(256, 2, n)
+  om, spec, P, xd, yd = _setup(cfg, n, 3)
+  eng = inference.Engine(spec, prec)
+
+  def run():
+    p = P.cuda().clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sc = torch.zeros(1, dtype=torch.int32, device=cuda)
+    ls = eng.map_epochs(p, m, v, sc, xd, yd, B, n, epochs, 0.005, 1.0, 11, 0)
+    torch.cuda.synchronize()
+    assert int(sc[0]) == steps
+    return p.cpu().numpy(), ls.cpu().numpy()
+  monkeypatch.delenv('BNF_GRAPH_UNROLL', raising=False)
+  monkeypatch.delenv('BNF_NO_GRAPH', raising=False)
+  p0, l0 = run()
+  assert np.isfinite(l0).all() and l0.shape[0] == steps
+  # (atomic-order noise through 21 Adam steps; a wrong batch window or step count moves a loss by percents)
+  tol_l, tol_p = (5e-4, 2e-3) if prec != 'bf16' else (5e-3, 5e-3)
+  for flag, val in (('BNF_GRAPH_UNROLL', '1'), ('BNF_GRAPH_UNROLL', '3'), ('BNF_NO_GRAPH', '1')):
+    monkeypatch.setenv(flag, val)
+    p1, l1 = run()
+    monkeypatch.delenv(flag)
+    np.testing.assert_allclose(l0, l1, rtol=tol_l, err_msg=f'{flag}={val}')
+    # (Adam normalises the step: an entry whose gradient is summation noise may walk the other way)
+    assert float(np.quantile(np.abs(p0 - p1), 0.999)) <= tol_p, (flag, val)
+
+
 def test_single_step_calls_replay_cached_graph(cuda):
   """bnf_map_steps called one step at a time (what bench.py's e2e loop does) == one call with
   all the steps: the cached graph is keyed on its baked arguments and the device-side cursors
