@@ -503,13 +503,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = et; i < 2 * kEncMaxKb * Cfg::kABytes / 16; i += 32 * kEncWarps) pz[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // the TMA descriptors into the descriptor cache (kernel parameters: nothing the previous kernel
+  // writes), so the first load / store of every role does not wait for its descriptor fetch
+  if (warp == kProd && lane == 0) {
+    if (!ENCODE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    if ((MODE == TC_FWD && a.out0) || MODE == TC_FWD_HEAD || MODE == TC_DGRAD_ACT || MODE == TC_DGRAD_BF16)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o0)) : "memory");
+    if (MODE == TC_FWD || MODE == TC_DGRAD_ACT)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_o1)) : "memory");
+  }
   tc_fence_before();
   __syncthreads();
   if (CTA2) cluster_sync_all();        // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                          // everything above overlapped the previous kernel's tail
-  if (threadIdx.x == 0) TL(0, 15);
 
   // work items: (net, m unit, split, n tile); a unit is one 128-row tile, or a PAIR of them for
   // a CTA pair (this CTA takes rows of tile 2*unit + cta_rank)
@@ -528,6 +538,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int tile0 = contiguous ? (int)((long long)total_tiles * cta_id / n_ctas) : cta_id;
   const int tile_end = contiguous ? (int)((long long)total_tiles * (cta_id + 1) / n_ctas) : total_tiles;
   const int tile_step = contiguous ? 1 : n_ctas;
+
+  pdl_wait();                          // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) TL(0, 15);
+
 
   if (warp == kProd) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
