@@ -376,6 +376,9 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   static_assert(!X3 || MODE == TC_FWD || MODE == TC_FWD_HEAD || MODE == TC_DGRAD_ACT || MODE == TC_DGRAD_ENC,
                 "x3 epilogues: fwd, fwd+head, dgrad+act, dgrad0+encode");
   static_assert(!X3 || !kEpi16, "the x3 epilogues have no sixteen-warp variant");
+#ifdef BNF_HEAD_ROLLED
+  static_assert(!kEpi16, "BNF_HEAD_ROLLED is written for the eight-warp TC_FWD_HEAD epilogue");
+#endif
   // TC_DGRAD_ENC: the dfeat tile stays on chip -- a 128 x (BLOCK_N+1) f32 tile in shared memory.
   // Its epilogue (the encode backward) is latency-bound, so the kernel is sized for TWO CTAs per
   // SM at Fp = 64: two ring stages, no TMA-store staging tiles (~100 KB, 128 TMEM columns each).
@@ -384,7 +387,17 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   // + the tile's h = act(z) as bf16 in per-warp 64B-swizzled 32x32 tiles (pass 1 -> pass 2)
   static constexpr int kHeadScratch = (MODE == TC_FWD_HEAD && !X3)     // (x3 recomputes instead of stashing h)
       ? epi_warps_of(MODE, A_MODE) * ((BLOCK_N / 32 + epi_warps_of(MODE, A_MODE) / 4 - 1) / (epi_warps_of(MODE, A_MODE) / 4)) * 2048 : 0;
-  static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadScratch : 0;
+  // BNF_HEAD_ROLLED: the per-lane column sums of TC_FWD_HEAD's pass 2 live in shared memory
+  // ([warp][chunk][2][32] floats) instead of statically indexed registers, so the pass-2 chunk loop
+  // need not be unrolled (a third of the kernel's code: ncu attributes 13 % (bf16) / 28 % (bf16x3)
+  // of its warp samples to instruction-fetch stalls)
+#ifdef BNF_HEAD_ROLLED
+  static constexpr int kHeadColBytes = MODE == TC_FWD_HEAD
+      ? (X3 ? 8 : epi_warps_of(MODE, A_MODE)) * ((BLOCK_N / 32 + (X3 ? 8 : epi_warps_of(MODE, A_MODE)) / 4 - 1) / ((X3 ? 8 : epi_warps_of(MODE, A_MODE)) / 4)) * 64 * 4 : 0;
+#else
+  static constexpr int kHeadColBytes = 0;
+#endif
+  static constexpr int kHeadBytes = MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadScratch + kHeadColBytes : 0;
   // per epilogue warp: two 32x32 bf16 tiles (TMA-store staging); TC_DGRAD_ACT: one output tile
   // plus a ring of kZRing z tiles landed by TMA
   // X3: TC_FWD [z f32 4 KB | h planes 3 x 2 KB]; TC_DGRAD_ACT [z ring kZRing x 4 KB | dU planes 3 x 2 KB]
@@ -409,7 +422,7 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   static constexpr int kBOff = A_MODE == 2 ? 0 : kABytes;       // B tile inside a ring stage
   // X3 (bigger staging tiles): as many ring stages as fit beside them, at most 6
   static constexpr int kX3Fixed = kEpi * kStgWarp + kBarBytes + 2 * 256 * 4 + (MODE == TC_DGRAD_ACT ? (kAccCols + 32) * 4 : 0) +
-                                  (MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 : 0);
+                                  (MODE == TC_FWD_HEAD ? (2 * 256 + 4 * 128) * 4 + kHeadColBytes : 0);
   static constexpr int kStagesX3 = (232448 - kX3Fixed) / kStageBytes > 6 ? 6 : (232448 - kX3Fixed) / kStageBytes;
   static constexpr int kStages = (X3 && MODE != TC_DGRAD_ENC) ? kStagesX3 : kStagesBf16;
   static_assert(kStages >= 2, "at least two ring stages");
@@ -467,6 +480,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* kos_s = sbias + 2 * 256;                    // TC_FWD_HEAD: [2][256] Dense_L kernel of the tile's network
   uint8_t* hscr = (uint8_t*)(kos_s + 2 * 256 + 4 * 128);   // TC_FWD_HEAD: [kEpi][chunks][2 KB] bf16 h tiles
   float* rowdot = kos_s + 2 * 256;                   // TC_FWD_HEAD: [kParts][128] partial h.Ko of the quarter's warps
+#ifdef BNF_HEAD_ROLLED
+  float* hcol_s = reinterpret_cast<float*>(hscr + Cfg::kHeadScratch);   // [kEpi][chunks][2][32] column sums
+#endif
   float* sxt = gtile + 128 * (BLOCK_N + 1);          // TC_DGRAD_ENC: [2][128][kMaxD+1] scaled inputs + raw time
 
   // the warp index through a shuffle: the compiler then knows it (and every address / coordinate
@@ -485,6 +501,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < Cfg::kAccFloats; i += Cfg::kThreads) colacc[i] = 0.f;
+#ifdef BNF_HEAD_ROLLED
+  for (int i = threadIdx.x; i < Cfg::kHeadColBytes / 4; i += Cfg::kThreads) hcol_s[i] = 0.f;
+#endif
   if (warp == kMma) {
     if (CTA2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -746,6 +765,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         } else {
           const int c = half * 32 + i * 32 * kParts;
+#ifdef BNF_HEAD_ROLLED
+          float* hc = hcol_s + ((warp * kHeadChunks + i) * 2) * 32 + lane;     // this lane's own words
+          hcol_b[i] = hc[0]; hcol_k[i] = hc[32];
+          hc[0] = 0.f; hc[32] = 0.f;
+#endif
           if (c < BLOCK_N) {
             atomicAdd(g + a.off_bias + c + lane, hcol_b[i]);
             atomicAdd(g + dm.off_kernel[dm.L] + c + lane, hcol_k[i] * (h_sout * dm.inv_sqrt_W));
@@ -863,7 +887,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float rk = rr * hc;                     // dh[col] = rk * Ko[col]
           const float rks = rk * s_l;
           float gw = 0.f, gs = 0.f;
+#ifdef BNF_HEAD_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
           for (int ci = 0; ci < kHeadChunks; ++ci) {
             const int c = half * 32 + ci * 32 * kParts;
             if (c >= BLOCK_N) break;
@@ -907,8 +935,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             warp_transpose_sum(du, lane);
             warp_transpose_sum(gk, lane);
+#ifdef BNF_HEAD_ROLLED
+            float* hc = hcol_s + ((warp * kHeadChunks + ci) * 2) * 32 + lane;
+            hc[0] += du[0];
+            hc[32] += gk[0];
+#else
             hcol_b[ci] += du[0];
             hcol_k[ci] += gk[0];
+#endif
           }
           tc_fence_before();
           if (CTA2) mbar_arrive_remote(&tempty[acc], 0);
@@ -1014,7 +1048,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- pass 2: dU = kd*(rk*s_l), column sums of dU (bias gradient) and of r*h (Dense_L kernel)
         const f32x2 rr2 = f2_dup(rr);
         const f32x2 rks2 = f2_dup(rk * s_l);
+#ifdef BNF_HEAD_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int ci = 0; ci < kHeadChunks; ++ci) {
           const int c = half * 32 + ci * 32 * kParts;
           if (c >= BLOCK_N) break;
@@ -1094,8 +1132,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // column sums over this warp's 32 rows by transpose-reduce (lane L ends with column L)
           warp_transpose_sum(du, lane);
           warp_transpose_sum(gk, lane);
+#ifdef BNF_HEAD_ROLLED
+          float* hc = hcol_s + ((warp * kHeadChunks + ci) * 2) * 32 + lane;
+          hc[0] += du[0];
+          hc[32] += gk[0];
+#else
           hcol_b[ci] += du[0];
           hcol_k[ci] += gk[0];
+#endif
         }
         if (epi_tid == 0) TL((t - tile0) / tile_step, 10);
         tc_fence_before();
