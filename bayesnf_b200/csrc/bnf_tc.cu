@@ -323,6 +323,14 @@ struct TcArgs {
 // register file caps the count (12 warps <-> 146 registers/thread, 16 <-> 112 = spills).
 // Measured (profiles/experiments/README.md): TC_DGRAD_ACT with 12 warps: wind dgrad -8 %,
 // chickenpox -4 % (one ring stage less); TC_FWD / TC_FWD_HEAD: no change (HBM-write / MUFU bound).
+// TC_FWD_HEAD pass 2: the chunk loop is a real loop and the per-lane column sums live in shared memory
+// (default; measured r2y: chickenpox bf16 0.1613 -> 0.1569 ms/step, bf16x3 0.3851 -> 0.3771).  With statically
+// indexed register sums the loop had to be unrolled, a third of the kernel's code, and ncu attributed 13 %
+// (bf16) / 28 % (bf16x3) of the kernel's warp samples to instruction-fetch stalls.  -DBNF_HEAD_UNROLLED
+// restores the unrolled form (the sixteen-warp experiment build keeps it as well).
+#if !defined(BNF_HEAD_UNROLLED) && !defined(BNF_EPI16)
+#define BNF_HEAD_ROLLED 1
+#endif
 #ifdef BNF_EPI16
 // EXPERIMENT (not validated on hardware yet): sixteen epilogue warps
 // (four per SM sub-partition) for the three activation epilogues.  To fit 576 threads in the
@@ -387,10 +395,8 @@ template <int BLOCK_N, int A_MODE = 0, bool CTA2 = false, int MODE = 0, bool X3 
   // + the tile's h = act(z) as bf16 in per-warp 64B-swizzled 32x32 tiles (pass 1 -> pass 2)
   static constexpr int kHeadScratch = (MODE == TC_FWD_HEAD && !X3)     // (x3 recomputes instead of stashing h)
       ? epi_warps_of(MODE, A_MODE) * ((BLOCK_N / 32 + epi_warps_of(MODE, A_MODE) / 4 - 1) / (epi_warps_of(MODE, A_MODE) / 4)) * 2048 : 0;
-  // BNF_HEAD_ROLLED: the per-lane column sums of TC_FWD_HEAD's pass 2 live in shared memory
-  // ([warp][chunk][2][32] floats) instead of statically indexed registers, so the pass-2 chunk loop
-  // need not be unrolled (a third of the kernel's code: ncu attributes 13 % (bf16) / 28 % (bf16x3)
-  // of its warp samples to instruction-fetch stalls)
+  // BNF_HEAD_ROLLED (default): the per-lane column sums of TC_FWD_HEAD's pass 2 live in shared memory
+  // ([warp][chunk][2][32] floats, lane-private words) instead of statically indexed registers
 #ifdef BNF_HEAD_ROLLED
   static constexpr int kHeadColBytes = MODE == TC_FWD_HEAD
       ? (X3 ? 8 : epi_warps_of(MODE, A_MODE)) * ((BLOCK_N / 32 + (X3 ? 8 : epi_warps_of(MODE, A_MODE)) / 4 - 1) / ((X3 ? 8 : epi_warps_of(MODE, A_MODE)) / 4)) * 64 * 4 : 0;

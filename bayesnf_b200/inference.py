@@ -143,14 +143,16 @@ class Engine:
   def forward_slab_rows(self, n_net: int, budget_bytes: int | None = None) -> int:
     """Rows per forecast slab so that the forward workspace of `n_net` networks stays within a
     memory budget (the reference forecasts in 1024-row batches for the same reason,
-    inference.py:129-181): clamp(budget // bytes_per_row, 128, 16384)."""
+    inference.py:129-181): clamp(budget // bytes_per_row, 128, 65536).  (Up to 65 536 rows per call --
+    the batch size of the largest training configuration: at 16 384 the 1 Mi-row forecast of the bench's
+    predict block was 64 calls of ~150 us of kernels each and bound by the host's launch rate.)"""
     if budget_bytes is None:
       free, _ = torch.cuda.mem_get_info(self.device)
       budget_bytes = min(8 << 30, free // 4)
     probe = 1024
     per_row = _lib.lib.bnf_workspace_bytes(self.spec.plan, self.prec, n_net, probe, _lib.WS_FORWARD) / probe
     rows = int(budget_bytes // max(per_row, 1.0))
-    return max(128, min(16384, rows // 128 * 128))
+    return max(128, min(65536, rows // 128 * 128))
 
   # ---- mlp.apply over networks (forecast_inner, inference.py:103-126) ----
   def forward(self, params: torch.Tensor, x: torch.Tensor, slab: int | None = None) -> torch.Tensor:
@@ -160,6 +162,12 @@ class Engine:
     if slab is None:
       slab = self.forward_slab_rows(M)
     slab = max(1, min(slab, N))
+    if slab == N:                                     # one slab: the kernels write `out` directly
+      ws = self.workspace(_lib.WS_FORWARD, M, N)
+      _lib.check(_lib.lib.bnf_forward(
+          self.spec.plan, self.prec, _ptr(params), M, _ptr(x), None, 0, N,
+          _ptr(out), _ptr(ws), ws.numel(), _stream()))
+      return out
     tmp = torch.empty((M, slab), dtype=torch.float32, device=self.device)
     for s in range(0, N, slab):
       rows = min(slab, N - s)

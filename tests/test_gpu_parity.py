@@ -110,6 +110,36 @@ def test_forward_fp32(cuda, name, prec):
     assert float((loc[j].double() - want64).abs().max()) <= 1e-5 * scale + 1e-6
 
 
+@pytest.mark.parametrize('prec', ['bf16x3', 'bf16', 'fp32'])
+def test_forward_slab_sizes_agree(cuda, prec):
+  """Engine.forward cuts the test rows into slabs sized from a memory budget (the reference forecasts
+  in 1024-row batches, inference.py:129-181): 70 000 rows as 65 536 + 4 464 (the default cap), as
+  4 096-row slabs and with a tiny budget give the same means; forward_slab_rows clamps to [128, 65 536]."""
+  from bayesnf_b200 import inference
+  cfg = _cfgs()['chickenpox']
+  n = 70000
+  g = torch.Generator().manual_seed(5)
+  x = torch.stack([torch.rand(n, generator=g) * 99.0, torch.randn(n, generator=g), torch.randn(n, generator=g)], 1)
+  om = O.OracleModel(**cfg)
+  P = _random_params(om, 4, np.random.default_rng(0).normal(size=64))
+  eng, spec = _engine(cfg, prec=prec)
+  xd = x.to(cuda).float().contiguous()
+  assert eng.forward_slab_rows(4) == 65536 and eng.forward_slab_rows(4, budget_bytes=1) == 128
+  mid = eng.forward_slab_rows(4, budget_bytes=64 << 20)
+  assert 128 <= mid < 65536 and mid % 128 == 0
+  a = eng.forward(P.to(cuda), xd)
+  b = eng.forward(P.to(cuda), xd, slab=4096)
+  c = eng.forward(P.to(cuda), xd, slab=eng.forward_slab_rows(4, budget_bytes=1))
+  torch.cuda.synchronize()
+  assert torch.isfinite(a).all()
+  # every row's mean is a function of that row alone: the same whatever slab it was computed in
+  scale = float(a.abs().max())
+  assert float((a - b).abs().max()) <= 1e-6 * scale and float((a - c).abs().max()) <= 1e-6 * scale
+  want = om.forward(om.unflatten(P[1]), x[:2000].float())
+  tol = 1e-5 if prec != 'bf16' else 3e-2
+  assert float((a[1, :2000].cpu() - want).abs().max()) <= tol * float(want.abs().max()) + 1e-6
+
+
 @pytest.mark.parametrize('prec', PARITY_MODES)
 @pytest.mark.parametrize('dist', ['NORMAL', 'NB', 'ZINB'])
 @pytest.mark.parametrize('name', ['small', 'chickenpox', 'odd'])
