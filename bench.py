@@ -148,8 +148,8 @@ class ClockSampler(threading.Thread):
 
 
 # committed `ncu --set full` summaries of the same commands (profiles/), per (workload, precision)
-NCU_SUMMARY = {('chickenpox_map_e8', 'bf16'): 'ncu_chickenpox_bf16_r2_summary.csv',
-               ('chickenpox_map_e8', 'bf16x3'): 'ncu_chickenpox_bf16x3_r2_summary.csv',
+NCU_SUMMARY = {('chickenpox_map_e8', 'bf16'): 'ncu_chickenpox_bf16_r2z_summary.csv',
+               ('chickenpox_map_e8', 'bf16x3'): 'ncu_chickenpox_bf16x3_r2z_summary.csv',
                ('wind_map_e16', 'bf16'): 'ncu_wind_tc_gemm_r2_summary.csv',
                ('wind_map_e16', 'bf16x3'): 'ncu_wind_tc_gemm_bf16x3_r2_summary.csv'}
 # kernel class -> template-argument substrings <BLOCK_N, A_MODE, MODE, CTA2, X3> of its instantiations
